@@ -1,0 +1,239 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).
+// Flat C entry points over the restatement so tests/ and bench.py's cpu_baseline leg can drive it
+// through ctypes.  Clouds are float32 [n,4] (x,y,z,intensity); poses are double[7]
+// [tx ty tz qx qy qz qw].  Never linked into the product library.
+#include "orc_pipeline.hpp"
+#include <cstdio>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+static Cloud to_cloud(const float *p, int n) {
+  Cloud c(n);
+  if (n > 0) std::memcpy(c.data(), p, sizeof(PointI) * (size_t)n);
+  return c;
+}
+static Pose to_pose(const double *x) { return Pose{Q4{x[3], x[4], x[5], x[6]}, V3{x[0], x[1], x[2]}}; }
+
+// opts layout shared by the pipeline calls
+enum {
+  O_MAX_OUTER = 0, O_MAX_INNER, O_HUBER, O_EIG_THRE, O_N_NEIGH, O_CHECK_FOV, O_POINT_PLANE, O_POINT_EDGE,
+  O_COV_TRACE, O_DIST_SQ_THR, O_NEARBY_SCAN, O_MIN_MATCH_SQ, O_MIN_PLANE_DIS, O_COUNT
+};
+static MatchParams mp_from(const double *o) {
+  MatchParams mp;
+  mp.distance_sq_threshold = (float)o[O_DIST_SQ_THR];
+  mp.nearby_scan = (float)o[O_NEARBY_SCAN];
+  mp.min_match_sq_dis = (float)o[O_MIN_MATCH_SQ];
+  mp.min_plane_dis = (float)o[O_MIN_PLANE_DIS];
+  return mp;
+}
+
+extern "C" {
+
+int orc_num_opts() { return O_COUNT; }
+void orc_default_opts(double *o) {
+  Scan2MapOptions d;
+  o[O_MAX_OUTER] = d.max_outer, o[O_MAX_INNER] = d.max_inner, o[O_HUBER] = d.huber_a, o[O_EIG_THRE] = d.eig_thre;
+  o[O_N_NEIGH] = d.n_neigh, o[O_CHECK_FOV] = d.check_fov, o[O_POINT_PLANE] = d.point_plane, o[O_POINT_EDGE] = d.point_edge;
+  o[O_COV_TRACE] = d.cov_trace, o[O_DIST_SQ_THR] = d.mp.distance_sq_threshold, o[O_NEARBY_SCAN] = d.mp.nearby_scan;
+  o[O_MIN_MATCH_SQ] = d.mp.min_match_sq_dis, o[O_MIN_PLANE_DIS] = d.mp.min_plane_dis;
+}
+
+// ---- small dense kernels (known-answer tests)
+void orc_eig3f(const float *A9, float *w3, float *V9) { eig3f(A9, w3, V9); }
+int orc_lsq_plane(const float *A, int K, float *n3) { return lsq_plane_f(A, K, n3) ? 1 : 0; }
+void orc_eig_sym(int N, const double *A, double *w, double *V) { eig_sym(N, A, w, V); }
+double orc_logdet(int N, const double *H) { return logdet_chol(N, H); }
+void orc_huber(double a, double s, double *out2) { huber(a, s, &out2[0], &out2[1]); }
+double orc_map_sqrt_info(double cov_trace) { return map_sqrt_info(cov_trace); }
+void orc_associate(const float *pts, int n, const double *pose7, float *out) {
+  Pose p = to_pose(pose7);
+  for (int i = 0; i < n; i++) {
+    PointI o = associate(PointI{pts[i * 4], pts[i * 4 + 1], pts[i * 4 + 2], pts[i * 4 + 3]}, p);
+    out[i * 4] = o.x, out[i * 4 + 1] = o.y, out[i * 4 + 2] = o.z, out[i * 4 + 3] = o.intensity;
+  }
+}
+void orc_pose_mul(const double *a7, const double *b7, double *out7) { pose_to_param(pose_mul(to_pose(a7), to_pose(b7)), out7); }
+void orc_pose_inv(const double *a7, double *out7) { pose_to_param(pose_inv(to_pose(a7)), out7); }
+
+// PoseLocalParameterization::Plus with optional V_update (row-major 6x6; null = identity)
+void orc_plus(const double *x7, const double *delta6, const double *V36, double *out7) {
+  PoseLocalParameterization lp;
+  if (V36) std::memcpy(lp.V_update, V36, sizeof(lp.V_update));
+  lp.Plus(x7, delta6, out7);
+}
+void orc_eval_degeneracy(const double *H36, double thre, double *V36, double *eig6, int *degenerate) {
+  PoseLocalParameterization lp;
+  eval_degeneracy(H36, thre, lp, eig6);
+  std::memcpy(V36, lp.V_update, sizeof(lp.V_update));
+  *degenerate = lp.is_degenerate ? 1 : 0;
+}
+
+// ---- kNN.  Missing slots: idx -1, sqdist +inf.
+void orc_knn(const float *map, int m, const float *q, int nq, int k, int *idx, float *sqd, int brute) {
+  Cloud c = to_cloud(map, m);
+  KdTree t;
+  if (!brute) t.setInputCloud(&c);
+  for (int i = 0; i < nq; i++) {
+    int got = brute ? knn_brute(c, q[i * 4], q[i * 4 + 1], q[i * 4 + 2], k, idx + (size_t)i * k, sqd + (size_t)i * k)
+                    : t.nearestKSearch(q[i * 4], q[i * 4 + 1], q[i * 4 + 2], k, idx + (size_t)i * k, sqd + (size_t)i * k);
+    for (int j = got; j < k; j++) idx[(size_t)i * k + j] = -1, sqd[(size_t)i * k + j] = INFINITY;
+  }
+}
+
+// ---- voxel grid; out has capacity n; returns 1 normally, 0 on the int32-overflow copy path
+int orc_voxel_grid(const float *in, int n, float leaf, int intensity_last, float *out, int *n_out) {
+  Cloud c = to_cloud(in, n), o;
+  bool ok = voxel_grid(c, leaf, o, intensity_last != 0);
+  *n_out = (int)o.size();
+  if (!o.empty()) std::memcpy(out, o.data(), sizeof(PointI) * o.size());
+  return ok ? 1 : 0;
+}
+
+// ---- extractCloud.  Each out_* has capacity n points; counts = {sharp, less_sharp, flat, less_flat}.
+void orc_extract_cloud(const float *cloud, int n, const int *scan_start, const int *scan_end, int n_scans,
+                       float *sharp, float *less_sharp, float *flat, float *less_flat, int *counts, float *curvature,
+                       int *label) {
+  Cloud c = to_cloud(cloud, n);
+  ScanInfo si;
+  si.scan_start_ind.assign(scan_start, scan_start + n_scans);
+  si.scan_end_ind.assign(scan_end, scan_end + n_scans);
+  CloudFeature f;
+  extract_cloud(c, si, n_scans, f);
+  auto put = [](const Cloud &s, float *dst) {
+    if (!s.empty()) std::memcpy(dst, s.data(), sizeof(PointI) * s.size());
+    return (int)s.size();
+  };
+  counts[0] = put(f.corner_points_sharp, sharp);
+  counts[1] = put(f.corner_points_less_sharp, less_sharp);
+  counts[2] = put(f.surf_points_flat, flat);
+  counts[3] = put(f.surf_points_less_flat, less_flat);
+  if (curvature) std::memcpy(curvature, f.curvature.data(), sizeof(float) * n);
+  if (label) std::memcpy(label, f.label.data(), sizeof(int) * n);
+}
+
+// ---- scan-to-map association. type 'c' or 's'. valid[n]; coeffs[n*6]; nn[n*n_neigh] (-1 when invalid)
+int orc_match_from_map(int type, const float *map, int m, const float *data, int n, const double *pose7, int n_neigh,
+                       int check_fov, const double *opts, unsigned char *valid, double *coeffs, int *nn) {
+  Cloud cm = to_cloud(map, m), cd = to_cloud(data, n);
+  KdTree t;
+  t.setInputCloud(&cm);
+  Pose p = to_pose(pose7);
+  MatchParams mp = mp_from(opts);
+  int cnt = 0;
+  for (int i = 0; i < n; i++) {
+    Feature f;
+    bool ok = type == 'c' ? match_corner_point_from_map(t, cm, cd[i], p, f, i, n_neigh, check_fov != 0, mp)
+                          : match_surf_point_from_map(t, cm, cd[i], p, f, i, n_neigh, check_fov != 0, mp);
+    valid[i] = ok ? 1 : 0;
+    for (int j = 0; j < 6; j++) coeffs[(size_t)i * 6 + j] = ok ? f.coeffs[j] : 0.0;
+    if (nn)
+      for (int j = 0; j < n_neigh; j++) nn[(size_t)i * n_neigh + j] = ok ? f.nn[j] : -1;
+    cnt += ok;
+  }
+  return cnt;
+}
+
+// ---- scan-to-scan association (tracker). type 'c': coeffs 6, 's': coeffs 4. Output compacted in query
+// order like the reference: feat_idx[cnt], coeffs[cnt*6]. Returns cnt.
+int orc_match_from_scan(int type, const float *scan, int m, const float *data, int n, const double *pose7,
+                        const double *opts, int *feat_idx, double *coeffs) {
+  Cloud cs = to_cloud(scan, m), cd = to_cloud(data, n);
+  KdTree t;
+  t.setInputCloud(&cs);
+  std::vector<Feature> fs;
+  if (type == 'c') match_corner_from_scan(t, cs, cd, to_pose(pose7), fs, mp_from(opts));
+  else match_surf_from_scan(t, cs, cd, to_pose(pose7), fs, mp_from(opts));
+  for (size_t i = 0; i < fs.size(); i++) {
+    feat_idx[i] = (int)fs[i].idx;
+    for (int j = 0; j < 6; j++) coeffs[i * 6 + j] = fs[i].coeffs[j];
+  }
+  return (int)fs.size();
+}
+
+// ---- factors. kind = FactorKind. x = up to 3 parameter blocks (21 doubles). r[3], J[3*21]:
+// single-pose kinds write J rows of 7; F_EDGE_VEC writes 3 rows of 7; odom kinds write [Jp|Ji|Je] (21).
+void orc_factor_eval(int kind, const double *point3, const double *coeffs6, double sqrt_info, const double *x21,
+                     double *r, double *J) {
+  V3 p{point3[0], point3[1], point3[2]};
+  switch (kind) {
+    case F_PLANE: plane_factor(p, coeffs6, sqrt_info, x21, r, J); break;
+    case F_EDGE: edge_factor(p, coeffs6, sqrt_info, x21, r, J); break;
+    case F_EDGE_VEC: edge_vector_factor(p, coeffs6, x21, r, J); break;
+    case F_ODOM_PLANE: odom_plane_factor(p, coeffs6, sqrt_info, x21, x21 + 7, x21 + 14, r, J, J ? J + 7 : nullptr, J ? J + 14 : nullptr); break;
+    case F_ODOM_EDGE: odom_edge_factor(p, coeffs6, sqrt_info, x21, x21 + 7, x21 + 14, r, J, J ? J + 7 : nullptr, J ? J + 14 : nullptr); break;
+  }
+}
+
+// ---- normal equations of a single-pose problem (map factors) at x: features given as SoA.
+// types[n] ('s' plane / 'c' edge), points[n*3] double, coeffs[n*6] double. Outputs H36, g6, cost.
+void orc_normal_eq(const unsigned char *types, const double *points, const double *coeffs, int n, double sqrt_info,
+                   double huber_a, const double *x7, double *H36, double *g6, double *cost) {
+  Problem pr;
+  pr.huber_a = huber_a;
+  double xx[7];
+  std::memcpy(xx, x7, sizeof(xx));
+  int pid = pr.add_param(xx);
+  for (int i = 0; i < n; i++) {
+    ResidualBlock b{types[i] == 's' ? F_PLANE : F_EDGE, V3{points[i * 3], points[i * 3 + 1], points[i * 3 + 2]}, {0, 0, 0, 0, 0, 0},
+                    sqrt_info, {pid, 0, 0}};
+    for (int j = 0; j < 6; j++) b.coeffs[j] = coeffs[(size_t)i * 6 + j];
+    pr.blocks.push_back(b);
+  }
+  NormalEq ne;
+  std::vector<const double *> xs{xx};
+  pr.evaluate(xs, true, ne);
+  std::memcpy(H36, ne.H.data(), 36 * sizeof(double));
+  std::memcpy(g6, ne.g.data(), 6 * sizeof(double));
+  *cost = ne.cost;
+}
+
+// ---- scan2MapOptimization. stats[16]: ran, n_surf, n_corner, lm_iterations, final_cost, degenerate,
+// t_kdtree, t_match, t_solver, eig[0..5]
+void orc_scan2map(const float *surf_map, int n_sm, const float *corner_map, int n_cm, const float *surf_scan, int n_ss,
+                  const float *corner_scan, int n_cs, const double *pose_init7, const double *opts, double *pose_out7,
+                  double *stats, double *H36) {
+  Scan2MapOptions o;
+  o.max_outer = (int)opts[O_MAX_OUTER], o.max_inner = (int)opts[O_MAX_INNER], o.huber_a = opts[O_HUBER];
+  o.eig_thre = opts[O_EIG_THRE], o.n_neigh = (int)opts[O_N_NEIGH], o.check_fov = opts[O_CHECK_FOV] != 0;
+  o.point_plane = opts[O_POINT_PLANE] != 0, o.point_edge = opts[O_POINT_EDGE] != 0, o.cov_trace = opts[O_COV_TRACE];
+  o.mp = mp_from(opts);
+  Cloud sm = to_cloud(surf_map, n_sm), cm = to_cloud(corner_map, n_cm), ss = to_cloud(surf_scan, n_ss),
+        cs = to_cloud(corner_scan, n_cs);
+  Scan2MapResult r = scan2map(sm, cm, ss, cs, to_pose(pose_init7), o);
+  pose_to_param(r.pose, pose_out7);
+  if (stats) {
+    stats[0] = r.ran, stats[1] = r.n_surf, stats[2] = r.n_corner, stats[3] = r.lm_iterations, stats[4] = r.final_cost;
+    stats[5] = r.degenerate, stats[6] = r.t_kdtree, stats[7] = r.t_match, stats[8] = r.t_solver;
+    for (int i = 0; i < 6; i++) stats[9 + i] = r.eig_last[i];
+    stats[15] = 0;
+  }
+  if (H36) std::memcpy(H36, r.H_last, sizeof(r.H_last));
+}
+
+// ---- LidarTracker::trackCloud. stats[3]: n_corner, n_surf, lm_iterations
+void orc_track_cloud(const float *prev_less_sharp, int n_pls, const float *prev_less_flat, int n_plf,
+                     const float *cur_sharp, int n_cs, const float *cur_flat, int n_cf, const double *pose_ini7,
+                     const double *opts, double *pose_out7, double *stats) {
+  TrackOptions o;
+  o.max_outer = (int)opts[O_MAX_OUTER], o.max_inner = (int)opts[O_MAX_INNER], o.huber_a = opts[O_HUBER];
+  o.mp = mp_from(opts);
+  Cloud a = to_cloud(prev_less_sharp, n_pls), b = to_cloud(prev_less_flat, n_plf), c = to_cloud(cur_sharp, n_cs),
+        d = to_cloud(cur_flat, n_cf);
+  TrackResult r = track_cloud(a, b, c, d, to_pose(pose_ini7), o);
+  pose_to_param(r.pose, pose_out7);
+  if (stats) stats[0] = r.n_corner, stats[1] = r.n_surf, stats[2] = r.lm_iterations;
+}
+
+int orc_max_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""ctypes binding of the CPU oracle (oracle/liborc.so) and of oracle/_ref/libref_knn.so.
+
+Test infrastructure: imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_DIR = os.path.join(ROOT, "oracle")
+
+F_PLANE, F_EDGE, F_EDGE_VEC, F_ODOM_PLANE, F_ODOM_EDGE = 0, 1, 2, 3, 4
+(O_MAX_OUTER, O_MAX_INNER, O_HUBER, O_EIG_THRE, O_N_NEIGH, O_CHECK_FOV, O_POINT_PLANE, O_POINT_EDGE, O_COV_TRACE,
+ O_DIST_SQ_THR, O_NEARBY_SCAN, O_MIN_MATCH_SQ, O_MIN_PLANE_DIS) = range(13)
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> None:
+    so = os.path.join(ORC_DIR, "liborc.so")
+    srcs = [os.path.join(ORC_DIR, f) for f in os.listdir(ORC_DIR) if f.endswith((".hpp", ".cpp"))]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", ORC_DIR, "liborc.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference") and (force or not os.path.exists(os.path.join(ORC_DIR, "_ref", "libref_knn.so"))):
+        subprocess.check_call(["make", "-C", ORC_DIR, "ref"], stdout=subprocess.DEVNULL)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(os.path.join(ORC_DIR, "liborc.so"))
+        _lib.orc_logdet.restype = C.c_double
+        _lib.orc_map_sqrt_info.restype = C.c_double
+        _lib.orc_map_sqrt_info.argtypes = [C.c_double]
+    return _lib
+
+
+def ref_lib():
+    """oracle/_ref/libref_knn.so — the reference's own nanoflann, or None when not built."""
+    global _ref
+    if _ref is None:
+        p = os.path.join(ORC_DIR, "_ref", "libref_knn.so")
+        if not os.path.exists(p):
+            return None
+        _ref = C.CDLL(p)
+    return _ref
+
+
+def cloud(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] == 4
+    return a
+
+
+def default_opts() -> np.ndarray:
+    o = np.zeros(lib().orc_num_opts(), dtype=np.float64)
+    lib().orc_default_opts(o.ctypes.data_as(C.c_void_p))
+    return o
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def knn(map_, q, k, brute=False):
+    map_, q = cloud(map_), cloud(q)
+    idx = np.empty((q.shape[0], k), np.int32)
+    sqd = np.empty((q.shape[0], k), np.float32)
+    lib().orc_knn(_p(map_), map_.shape[0], _p(q), q.shape[0], k, _p(idx), _p(sqd), int(brute))
+    return idx, sqd
+
+
+def ref_knn(map_, q, k):
+    r = ref_lib()
+    assert r is not None
+    map_, q = cloud(map_), cloud(q)
+    idx = np.empty((q.shape[0], k), np.int32)
+    sqd = np.empty((q.shape[0], k), np.float32)
+    r.ref_knn(_p(map_), map_.shape[0], _p(q), q.shape[0], k, _p(idx), _p(sqd))
+    return idx, sqd
+
+
+def eig3f(A):
+    A = np.ascontiguousarray(A, np.float32).reshape(9)
+    w = np.empty(3, np.float32)
+    V = np.empty(9, np.float32)
+    lib().orc_eig3f(_p(A), _p(w), _p(V))
+    return w, V.reshape(3, 3)
+
+
+def lsq_plane(A):
+    A = np.ascontiguousarray(A, np.float32)
+    n = np.empty(3, np.float32)
+    ok = lib().orc_lsq_plane(_p(A), A.shape[0], _p(n))
+    return bool(ok), n
+
+
+def eig_sym(A):
+    A = np.ascontiguousarray(A, np.float64)
+    N = A.shape[0]
+    w = np.empty(N)
+    V = np.empty((N, N))
+    lib().orc_eig_sym(N, _p(A), _p(w), _p(V))
+    return w, V
+
+
+def huber(a, s):
+    out = np.empty(2)
+    lib().orc_huber(C.c_double(a), C.c_double(s), _p(out))
+    return out
+
+
+def associate(pts, pose7):
+    pts = cloud(pts)
+    out = np.empty_like(pts)
+    pose7 = np.ascontiguousarray(pose7, np.float64)
+    lib().orc_associate(_p(pts), pts.shape[0], _p(pose7), _p(out))
+    return out
+
+
+def plus(x7, d6, V=None):
+    x7 = np.ascontiguousarray(x7, np.float64)
+    d6 = np.ascontiguousarray(d6, np.float64)
+    out = np.empty(7)
+    Vp = None if V is None else _p(np.ascontiguousarray(V, np.float64))
+    lib().orc_plus(_p(x7), _p(d6), Vp, _p(out))
+    return out
+
+
+def eval_degeneracy(H, thre):
+    H = np.ascontiguousarray(H, np.float64)
+    V = np.empty((6, 6))
+    eig = np.empty(6)
+    flag = C.c_int(0)
+    lib().orc_eval_degeneracy(_p(H), C.c_double(thre), _p(V), _p(eig), C.byref(flag))
+    return V, eig, bool(flag.value)
+
+
+def voxel_grid(pts, leaf, intensity_last=False):
+    pts = cloud(pts)
+    out = np.empty_like(pts)
+    n = C.c_int(0)
+    ok = lib().orc_voxel_grid(_p(pts), pts.shape[0], C.c_float(leaf), int(intensity_last), _p(out), C.byref(n))
+    return out[: n.value].copy(), bool(ok)
+
+
+def extract_cloud(pts, scan_start, scan_end):
+    pts = cloud(pts)
+    n = pts.shape[0]
+    ss = np.ascontiguousarray(scan_start, np.int32)
+    se = np.ascontiguousarray(scan_end, np.int32)
+    bufs = [np.empty((n, 4), np.float32) for _ in range(4)]
+    counts = np.zeros(4, np.int32)
+    curv = np.zeros(n, np.float32)
+    label = np.zeros(n, np.int32)
+    lib().orc_extract_cloud(_p(pts), n, _p(ss), _p(se), ss.shape[0], _p(bufs[0]), _p(bufs[1]), _p(bufs[2]), _p(bufs[3]),
+                            _p(counts), _p(curv), _p(label))
+    keys = ["corner_points_sharp", "corner_points_less_sharp", "surf_points_flat", "surf_points_less_flat"]
+    out = {k: bufs[i][: counts[i]].copy() for i, k in enumerate(keys)}
+    out["laser_cloud"] = pts
+    out["curvature"] = curv
+    out["label"] = label
+    return out
+
+
+def match_from_map(kind, map_, data, pose7, n_neigh=5, check_fov=False, opts=None):
+    map_, data = cloud(map_), cloud(data)
+    opts = default_opts() if opts is None else np.ascontiguousarray(opts, np.float64)
+    pose7 = np.ascontiguousarray(pose7, np.float64)
+    n = data.shape[0]
+    valid = np.zeros(n, np.uint8)
+    coeffs = np.zeros((n, 6))
+    nn = np.zeros((n, n_neigh), np.int32)
+    lib().orc_match_from_map(ord(kind), _p(map_), map_.shape[0], _p(data), n, _p(pose7), n_neigh, int(check_fov), _p(opts),
+                             _p(valid), _p(coeffs), _p(nn))
+    return valid.astype(bool), coeffs, nn
+
+
+def match_from_scan(kind, scan, data, pose7, opts=None):
+    scan, data = cloud(scan), cloud(data)
+    opts = default_opts() if opts is None else np.ascontiguousarray(opts, np.float64)
+    pose7 = np.ascontiguousarray(pose7, np.float64)
+    n = data.shape[0]
+    fidx = np.zeros(n, np.int32)
+    coeffs = np.zeros((n, 6))
+    cnt = lib().orc_match_from_scan(ord(kind), _p(scan), scan.shape[0], _p(data), n, _p(pose7), _p(opts), _p(fidx), _p(coeffs))
+    return fidx[:cnt].copy(), coeffs[:cnt].copy()
+
+
+def factor_eval(kind, point, coeffs, sqrt_info, x, want_jac=True):
+    point = np.ascontiguousarray(point, np.float64)
+    c6 = np.zeros(6)
+    c6[: len(coeffs)] = coeffs
+    x21 = np.zeros(21)
+    xx = np.ascontiguousarray(x, np.float64).reshape(-1)
+    x21[: xx.shape[0]] = xx
+    r = np.zeros(3)
+    J = np.zeros(63)
+    lib().orc_factor_eval(kind, _p(point), _p(c6), C.c_double(sqrt_info), _p(x21), _p(r), _p(J) if want_jac else None)
+    return r, J
+
+
+def normal_eq(types, points, coeffs, sqrt_info, huber_a, x7):
+    types = np.ascontiguousarray(types, np.uint8)
+    points = np.ascontiguousarray(points, np.float64)
+    coeffs = np.ascontiguousarray(coeffs, np.float64)
+    x7 = np.ascontiguousarray(x7, np.float64)
+    H = np.empty((6, 6))
+    g = np.empty(6)
+    cost = C.c_double(0)
+    lib().orc_normal_eq(_p(types), _p(points), _p(coeffs), types.shape[0], C.c_double(sqrt_info), C.c_double(huber_a), _p(x7),
+                        _p(H), _p(g), C.byref(cost))
+    return H, g, cost.value
+
+
+def scan2map(surf_map, corner_map, surf_scan, corner_scan, pose_init, opts=None):
+    sm, cm, ss, cs = cloud(surf_map), cloud(corner_map), cloud(surf_scan), cloud(corner_scan)
+    opts = default_opts() if opts is None else np.ascontiguousarray(opts, np.float64)
+    pose_init = np.ascontiguousarray(pose_init, np.float64)
+    out = np.empty(7)
+    stats = np.zeros(16)
+    H = np.zeros((6, 6))
+    lib().orc_scan2map(_p(sm), sm.shape[0], _p(cm), cm.shape[0], _p(ss), ss.shape[0], _p(cs), cs.shape[0], _p(pose_init),
+                       _p(opts), _p(out), _p(stats), _p(H))
+    names = ["ran", "n_surf", "n_corner", "lm_iterations", "final_cost", "degenerate", "t_kdtree", "t_match", "t_solver"]
+    st = {k: stats[i] for i, k in enumerate(names)}
+    st["eig"] = stats[9:15].copy()
+    st["H"] = H
+    return out, st
+
+
+def track_cloud(prev_less_sharp, prev_less_flat, cur_sharp, cur_flat, pose_ini, opts=None):
+    a, b, c, d = cloud(prev_less_sharp), cloud(prev_less_flat), cloud(cur_sharp), cloud(cur_flat)
+    if opts is None:
+        opts = default_opts()
+        opts[O_MAX_OUTER], opts[O_MAX_INNER] = 2, 4
+    opts = np.ascontiguousarray(opts, np.float64)
+    pose_ini = np.ascontiguousarray(pose_ini, np.float64)
+    out = np.empty(7)
+    stats = np.zeros(3)
+    lib().orc_track_cloud(_p(a), a.shape[0], _p(b), b.shape[0], _p(c), c.shape[0], _p(d), d.shape[0], _p(pose_ini), _p(opts),
+                          _p(out), _p(stats))
+    return out, {"n_corner": int(stats[0]), "n_surf": int(stats[1]), "lm_iterations": int(stats[2])}
