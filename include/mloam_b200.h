@@ -1,0 +1,201 @@
+/* mloam_b200.h — C ABI of the B200-native M-LOAM per-scan hot path.
+ *
+ * Plain C, POD only, no torch / Eigen / PCL / Ceres types.  Every entry point names the reference
+ * interface (file:line, relative to gogojjh/M-LOAM) it replaces.  All functions return 0 on success
+ * and a negative MLOAM_E_* code otherwise; mloam_last_error() gives the text.  There is no CPU
+ * fallback: with no CUDA device mloam_ctx_create() fails with MLOAM_E_NO_DEVICE.
+ *
+ * One context == one CUDA device + one stream + grow-only device arenas.  A context is not shared
+ * between host threads (the reference calls extractCloud/trackCloud from one OpenMP thread per LiDAR,
+ * estimator.cpp:249,423 — use one context per thread).
+ *
+ * Pointers named h_* are HOST buffers (pinned optional); d_* are DEVICE buffers on the context's
+ * device.  Points are float4 (x, y, z, intensity) == the payload of pcl::PointXYZI
+ * (common::PointI, mloam_common/libs/include/common/types/type.h:20); intensity = ring id + relative
+ * time (image_segmenter.hpp:128).  Poses are 7 doubles [tx ty tz qx qy qz qw]
+ * (pose_local_parameterization.h:20).
+ */
+#ifndef MLOAM_B200_H_
+#define MLOAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLOAM_OK 0
+#define MLOAM_E_INVALID (-1)   /* bad argument */
+#define MLOAM_E_NO_DEVICE (-2) /* no CUDA device / wrong architecture */
+#define MLOAM_E_CUDA (-3)      /* CUDA runtime error, see mloam_last_error */
+#define MLOAM_E_STATE (-4)     /* call order (e.g. match before map build) */
+#define MLOAM_E_NCCL (-5)
+
+#define MLOAM_MAP_CORNER 0 /* kdtree_corner_from_map, lidar_mapper_keyframe.cpp:434 */
+#define MLOAM_MAP_SURF 1   /* kdtree_surf_from_map,   lidar_mapper_keyframe.cpp:433 */
+#define MLOAM_NUM_MAPS 4   /* 2,3: scan-to-scan targets (lidar_tracker.cpp:33-34) */
+#define MLOAM_MAP_SCAN_CORNER 2
+#define MLOAM_MAP_SCAN_SURF 3
+
+typedef struct mloam_ctx mloam_ctx_t;
+
+typedef struct {
+  float x, y, z, intensity;
+} mloam_point_t;
+
+/* The globals of estimator/src/estimator/parameters.h:45-133 that steer the path, plus the hard-coded
+ * constants of the orchestrators, as one POD (defaults: mloam_default_params). */
+typedef struct {
+  int n_scans;                 /* N_SCANS */
+  float distance_sq_threshold; /* DISTANCE_SQ_THRESHOLD, feature_extract.hpp:158 */
+  float nearby_scan;           /* NEARBY_SCAN,           feature_extract.hpp:171 */
+  float min_match_sq_dis;      /* MIN_MATCH_SQ_DIS,      feature_extract.hpp:667 */
+  float min_plane_dis;         /* MIN_PLANE_DIS,         feature_extract.hpp:832 */
+  int n_neigh;                 /* N_NEIGH (5; lidar_mapper.h:253) */
+  int check_fov;               /* CHECK_FOV (false for all *PointFromMap callers) */
+  int point_plane_factor;      /* POINT_PLANE_FACTOR */
+  int point_edge_factor;       /* POINT_EDGE_FACTOR */
+  double huber_a;              /* ceres::HuberLoss(0.1), lidar_mapper_keyframe.cpp:443 */
+  double eig_thre;             /* MAP_EIG_THRE, lidar_mapper_keyframe.cpp:1180 */
+  double cov_trace;            /* trace(COV_MEASUREMENT) when with_ua=false, :541-545 */
+  int max_outer;               /* max_iter = 2, lidar_mapper_keyframe.cpp:439 */
+  int max_inner;               /* options.max_num_iterations = 30, :590 */
+  float map_cell;              /* voxel-hash cell edge [m] for the scan-to-map maps (<= 0: auto) */
+  float corner_leaf;           /* MAP_CORNER_RES (scan down-sampling before matching) */
+  float surf_leaf;             /* MAP_SURF_RES */
+  int reserved[8];
+} mloam_params_t;
+
+/* Per-solve report (what the reference prints through summary.BriefReport / timers). */
+typedef struct {
+  int ran;            /* 0 when the map-size gate (lidar_mapper_keyframe.cpp:429) rejected the frame */
+  int n_surf;         /* matched surf features, last outer iteration */
+  int n_corner;       /* matched corner features, last outer iteration */
+  int lm_iterations;  /* LM iterations over all outer iterations */
+  int degenerate;     /* PoseLocalParameterization::is_degenerate_ of the last outer iteration */
+  int termination;    /* last Solve: 0 max-iter, 1 function tol, 2 parameter tol, 3 gradient tol, 4 failure */
+  double final_cost;
+  double eig[6];      /* eigenvalues of J^T J (evalDegenracy) of the last outer iteration */
+  double H[36];       /* loss-corrected J^T J evaluated before the last Solve (:575-581) */
+  int n_surf_in;      /* features that entered matching (after scan down-sampling) */
+  int n_corner_in;
+  int reserved[6];
+} mloam_solve_stats_t;
+
+/* Feature sets of FeatureExtract::extractCloud (cloudFeature, parameters.h:161). Host buffers are
+ * caller-owned with capacity cap points each (cap >= n input points is always enough). */
+typedef struct {
+  mloam_point_t *corner_points_sharp;
+  mloam_point_t *corner_points_less_sharp;
+  mloam_point_t *surf_points_flat;
+  mloam_point_t *surf_points_less_flat;
+  int n_sharp, n_less_sharp, n_flat, n_less_flat;
+  int cap;
+} mloam_features_t;
+
+/* ---- context -------------------------------------------------------------------------------- */
+void mloam_default_params(mloam_params_t *p);
+int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out);
+void mloam_ctx_destroy(mloam_ctx_t *ctx);
+int mloam_set_params(mloam_ctx_t *ctx, const mloam_params_t *params);
+/* Run on an external CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream. */
+int mloam_set_stream(mloam_ctx_t *ctx, void *cuda_stream);
+int mloam_sync(mloam_ctx_t *ctx);
+const char *mloam_last_error(mloam_ctx_t *ctx);
+const char *mloam_version(void);
+/* Kernels launched by this context since creation (bench's gpu_launches). */
+long long mloam_launch_count(mloam_ctx_t *ctx);
+/* Per-kernel device timing with CUDA events on the context stream.  name: "map_build", "match",
+ * "linearize", "lm", "extract", "voxel".  Returns total ms and launch count since the last reset. */
+int mloam_profile_enable(mloam_ctx_t *ctx, int on);
+int mloam_profile_get(mloam_ctx_t *ctx, const char *name, double *ms_total, long long *launches);
+int mloam_profile_reset(mloam_ctx_t *ctx);
+
+/* ---- FeatureExtract::extractCloud (feature_extract.cpp:118-297) -------------------------------- */
+int mloam_extract_features(mloam_ctx_t *ctx, const mloam_point_t *h_cloud, int n, const int *h_scan_start,
+                           const int *h_scan_end, int n_scans, mloam_features_t *out);
+/* Optional per-point by-products of the last extraction (curvature feature_extract.cpp:138, label :141). */
+int mloam_extract_debug(mloam_ctx_t *ctx, float *h_curvature, int *h_label, int n);
+
+/* ---- pcl::VoxelGrid<PointI>::filter (feature_extract.cpp:267-270, estimator.cpp:488-494) and
+ *      VoxelGridCovarianceMLOAM on plain points (intensity_last=1; lidar_mapper_keyframe.cpp:359-368) */
+int mloam_voxel_downsample(mloam_ctx_t *ctx, const mloam_point_t *h_in, int n, float leaf, int intensity_last,
+                           mloam_point_t *h_out, int *n_out);
+
+/* ---- pcl::KdTreeFLANN::setInputCloud (lidar_mapper_keyframe.cpp:433-434, lidar_tracker.cpp:33-34,
+ *      estimator.cpp:1129-1130,1231-1233): build the GPU voxel-hash over a cloud. */
+int mloam_map_build(mloam_ctx_t *ctx, int slot, const mloam_point_t *h_pts, int m, float cell);
+int mloam_map_build_device(mloam_ctx_t *ctx, int slot, const mloam_point_t *d_pts, int m, float cell);
+int mloam_map_size(mloam_ctx_t *ctx, int slot);
+
+/* ---- pcl::KdTreeFLANN::nearestKSearch (feature_extract.hpp:155,293,406,570,666,813): exact K nearest
+ * within sqrt(max_sqdist), ascending (squared distance, index).  Queries are transformed by pose7 first
+ * when it is non-null (pointAssociateToMap, utility.h:103-117).  Slots with no neighbour inside the
+ * radius get idx -1 / sqdist +inf.  k in {1,5,10}. */
+int mloam_knn(mloam_ctx_t *ctx, int slot, const mloam_point_t *h_q, int nq, const double *pose7, int k,
+              float max_sqdist, int *h_idx, float *h_sqdist);
+
+/* ---- FeatureExtract::matchCornerFromMap / matchSurfFromMap (feature_extract.hpp:378-643; per-point
+ * forms :645-883).  type 'c' | 's'.  Outputs per query i: valid[i]; coeffs[i*6..] ('c': [X1;X2], 's':
+ * (n,d,0,0)); nn[i*n_neigh..] neighbour indices (may be null). */
+int mloam_match_from_map(mloam_ctx_t *ctx, int slot, int type, const mloam_point_t *h_pts, int n, const double *pose7,
+                         unsigned char *h_valid, double *h_coeffs, int *h_nn);
+
+/* ---- Lidar*Factor::Evaluate, batched (lidar_map_factor.hpp:44-68,143-171; lidar_scan_factor.hpp:33-60,
+ * 245-279; lidar_pure_odom_factor.hpp:38-101,209-281; lidar_online_calib_factor.hpp:34-60,135-163).
+ * kind: 0 plane (1x7), 1 edge scalar (1x7), 2 edge 3-vector (3x7), 3 odom plane (1x21 = [pivot|i|ext]),
+ * 4 odom edge (1x21).  points n*3, coeffs n*6, sqrt_info n (null = 1).  params: 7 doubles (kinds 0-2) or
+ * 21 (kinds 3-4), shared by the batch.  residuals n*rows; jacobians n*rows*cols row-major (may be null). */
+int mloam_factor_evaluate(mloam_ctx_t *ctx, int kind, int n, const double *h_points, const double *h_coeffs,
+                          const double *h_sqrt_info, const double *h_params, double *h_residuals,
+                          double *h_jacobians);
+
+/* ---- normal equations of a single-pose problem (what Ceres assembles inside Solve / what
+ * problem.Evaluate -> evalHessian returns, lidar_mapper_keyframe.cpp:575-581,1160-1169): types[n] 's'|'c',
+ * Huber-corrected J^T J (6x6 row-major), J^T r, cost = 1/2 sum rho. */
+int mloam_normal_equations(mloam_ctx_t *ctx, int n, const unsigned char *h_types, const double *h_points,
+                           const double *h_coeffs, double sqrt_info, double huber_a, const double *pose7,
+                           double *H36, double *g6, double *cost);
+
+/* ---- PoseLocalParameterization::Plus (pose_local_parameterization.cpp:26-46), V36 may be null. */
+int mloam_pose_plus(mloam_ctx_t *ctx, const double *x7, const double *delta6, const double *V36, double *out7);
+
+/* ---- scan2MapOptimization (lidar_mapper_keyframe.cpp:423-639, gf_method wo_gf).  Maps must have been
+ * built in slots MLOAM_MAP_SURF / MLOAM_MAP_CORNER.  The scan features are the (already down-sampled)
+ * laser_cloud_surf_cov / laser_cloud_corner_cov in the sensor(base) frame. */
+int mloam_scan2map(mloam_ctx_t *ctx, const mloam_point_t *h_surf_scan, int n_surf, const mloam_point_t *h_corner_scan,
+                   int n_corner, const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats);
+int mloam_scan2map_device(mloam_ctx_t *ctx, const mloam_point_t *d_surf_scan, int n_surf,
+                          const mloam_point_t *d_corner_scan, int n_corner, const double *pose_init7,
+                          double *pose_out7, mloam_solve_stats_t *stats);
+
+/* ---- the whole per-scan hot path for one LiDAR sweep (extractCloud -> scan down-sampling ->
+ * scan2MapOptimization), inputs in host memory (mloam_frame) or already resident in HBM
+ * (mloam_frame_device).  rebuild_maps != 0 re-runs setInputCloud on the two maps first, as the reference
+ * does every frame (lidar_mapper_keyframe.cpp:433-434). */
+int mloam_frame(mloam_ctx_t *ctx, const mloam_point_t *h_cloud, int n, const int *h_scan_start, const int *h_scan_end,
+                int n_scans, const mloam_point_t *h_surf_map, int n_surf_map, const mloam_point_t *h_corner_map,
+                int n_corner_map, int rebuild_maps, const double *pose_init7, double *pose_out7,
+                mloam_solve_stats_t *stats);
+int mloam_frame_device(mloam_ctx_t *ctx, const mloam_point_t *d_cloud, int n, const int *d_scan_start,
+                       const int *d_scan_end, int n_scans, const mloam_point_t *d_surf_map, int n_surf_map,
+                       const mloam_point_t *d_corner_map, int n_corner_map, int rebuild_maps,
+                       const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats);
+
+/* ---- LidarTracker::trackCloud (lidar_tracker.cpp:23-129). */
+int mloam_track_cloud(mloam_ctx_t *ctx, const mloam_point_t *h_prev_less_sharp, int n_pls,
+                      const mloam_point_t *h_prev_less_flat, int n_plf, const mloam_point_t *h_cur_sharp, int n_cs,
+                      const mloam_point_t *h_cur_flat, int n_cf, const double *pose_ini7, double *pose_out7,
+                      mloam_solve_stats_t *stats);
+
+/* ---- multi-GPU: one LiDAR per GPU, one all-reduce of the packed normal equations per LM evaluation
+ * (SURVEY.md §8e).  id128 is an ncclUniqueId (128 bytes) created on rank 0 and shared by the caller. */
+int mloam_comm_unique_id(void *id128);
+int mloam_comm_init(mloam_ctx_t *ctx, int nranks, int rank, const void *id128);
+int mloam_comm_destroy(mloam_ctx_t *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLOAM_B200_H_ */

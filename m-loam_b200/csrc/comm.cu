@@ -1,0 +1,101 @@
+// comm.cu — multi-GPU plumbing: one LiDAR per GPU, one all-reduce of the packed normal equations per LM
+// evaluation.  NCCL over NVLink 5 / NVSwitch; the collective is enqueued on the context stream
+// between the block-partial reduction and the LM step, so an iteration never returns to the host.
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is bound at run time (see nccl_api())
+
+#include <cstring>
+
+#include "ctx.h"
+#include "host_util.h"
+
+using namespace mloam;
+
+// NCCL is resolved with dlopen instead of a link-time dependency: a process that also hosts PyTorch already
+// carries torch's bundled libnccl.so.2, and binding a second copy at load time would clash with it.  dlopen
+// returns the resident library when there is one, the system library otherwise.
+namespace {
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy && api.GetErrorString;
+    }
+  }
+  return api.ok ? &api : nullptr;
+}
+}  // namespace
+
+namespace mloam {
+int comm_allreduce_doubles(Ctx *c, double *d_buf, int count) {
+  if (!c->nccl_comm) return MLOAM_OK;
+  ncclResult_t r = nccl_api()->AllReduce(d_buf, d_buf, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)c->nccl_comm, c->stream);
+  if (r != ncclSuccess) {
+    c->err = std::string("ncclAllReduce: ") + nccl_api()->GetErrorString(r);
+    return MLOAM_E_NCCL;
+  }
+  return MLOAM_OK;
+}
+}  // namespace mloam
+
+extern "C" {
+
+int mloam_comm_unique_id(void *id128) {
+  if (!id128) return MLOAM_E_INVALID;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (!nccl_api() || nccl_api()->GetUniqueId(&id) != ncclSuccess) return MLOAM_E_NCCL;
+  memcpy(id128, &id, sizeof(id));
+  return MLOAM_OK;
+}
+
+int mloam_comm_init(mloam_ctx_t *h, int nranks, int rank, const void *id128) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  if (c->nccl_comm) mloam_comm_destroy(h);
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm;
+  if (!nccl_api()) return fail(c, MLOAM_E_NCCL, "libnccl.so.2 could not be loaded");
+  ncclResult_t r = nccl_api()->CommInitRank(&comm, nranks, id, rank);
+  if (r != ncclSuccess) {
+    c->err = std::string("ncclCommInitRank: ") + nccl_api()->GetErrorString(r);
+    return MLOAM_E_NCCL;
+  }
+  c->nccl_comm = comm;
+  c->nranks = nranks, c->rank = rank;
+  return MLOAM_OK;
+}
+
+int mloam_comm_destroy(mloam_ctx_t *h) {
+  if (!h) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  if (c->nccl_comm) {
+    cudaStreamSynchronize(c->stream);
+    nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm);
+    c->nccl_comm = nullptr;
+    c->nranks = 1, c->rank = 0;
+  }
+  return MLOAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// ctx.h — host-side context behind the C ABI (include/mloam_b200.h) and the kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mloam_b200.h"
+#include "common.cuh"
+
+namespace mloam {
+
+// Grow-only device buffer (cudaMalloc only when capacity is exceeded; steady-state frames allocate nothing).
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t want = bytes + bytes / 4 + 256;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+struct MapStorage {
+  DevBuf sorted, orig, table, slot_of, rank_of, scan_tmp;
+  unsigned capacity = 0;  // hash slots (power of two)
+  int m = 0;
+  float cell = 0.f;
+  bool built = false;
+  MapView view() const {
+    MapView v;
+    v.sorted = sorted.as<float4>();
+    v.orig = orig.as<float4>();
+    v.table = table.as<HashEntry>();
+    v.mask = capacity - 1;
+    v.cell = cell;
+    v.inv_cell = 1.0f / cell;
+    v.m = m;
+    return v;
+  }
+};
+
+struct ProfSlot {
+  double ms = 0;
+  long long launches = 0;
+};
+
+// Parameters the kernels need, flattened from mloam_params_t.
+struct MatchCfg {
+  float min_match_sq_dis, min_plane_dis;
+  int n_neigh, check_fov;
+};
+
+struct Ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  mloam_params_t params;
+  std::string err;
+  long long launches = 0;
+
+  MapStorage maps[MLOAM_NUM_MAPS];
+
+  // scan features (device copies when the caller passes host buffers)
+  DevBuf scan_pts[2];             // [0] corner, [1] surf
+  DevBuf feat_valid[2];           // unsigned char per query
+  DevBuf feat_coeff[2];           // float[6] per query
+  DevBuf feat_nn[2];              // int[n_neigh] per query (optional)
+  DevBuf partials;                // per-block packed normal equations
+  DevBuf lm_state;                // LMState
+  DevBuf scratch[8];              // general scratch (knn outputs, factor batches, extraction, voxel)
+  void *pinned = nullptr;         // pinned host staging (LMState mirror + small results)
+  size_t pinned_cap = 0;
+
+  // profiling with CUDA events on `stream`
+  bool prof_on = false;
+  std::map<std::string, ProfSlot> prof;
+  struct PendingEvt {
+    std::string name;
+    cudaEvent_t a, b;
+  };
+  std::vector<PendingEvt> pending;
+  std::vector<cudaEvent_t> evt_pool;
+
+  // NCCL (multi-GPU); opaque here
+  int *d_extract_status = nullptr;  // device flag of the last extraction (1: ring window overflow / bad ScanInfo)
+  void *nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+// RAII-less helper: bracket a kernel (or a few) with events when profiling is on.
+struct ProfScope {
+  Ctx *c;
+  cudaEvent_t a = nullptr, b = nullptr;
+  const char *name;
+  ProfScope(Ctx *ctx, const char *nm);
+  ~ProfScope();
+};
+void prof_collect(Ctx *c);
+
+#define MLOAM_CUDA_OK(ctx, expr)                                                                      \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                                \
+      return MLOAM_E_CUDA;                                                                            \
+    }                                                                                                 \
+  } while (0)
+
+// ---------------------------------------------------------------- launchers (one per .cu)
+// map_kernels.cu
+int map_build_device(Ctx *c, int slot, const float4 *d_pts, int m, float cell);
+int knn_device(Ctx *c, int slot, const float4 *d_q, int nq, const double *d_pose7_or_null, int k, float max_sqdist,
+               int *d_idx, float *d_sqd);
+// type 'c' / 's'.  d_pose7 device pointer to 7 doubles.  Outputs: valid[n], coeff[n*6] float, nn[n*n_neigh] (nullable)
+// d_n (nullable): device-side feature count, n is then the launch upper bound.
+int match_from_map_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const int *d_n, const double *d_pose7,
+                          const MatchCfg &cfg, unsigned char *d_valid, float *d_coeff, int *d_nn);
+
+// solve_kernels.cu
+struct FeatSet {
+  const float4 *pts;           // sensor-frame points
+  const unsigned char *valid;
+  const float *coeff;          // float[6]
+  int n;                       // count, or launch upper bound when d_n is set
+  int is_plane;                // 1: LidarMapPlaneNormFactor, 0: LidarMapEdgeFactor
+  const int *d_n;              // nullable device-side count
+};
+// Accumulate loss-corrected normal equations of both feature sets at pose *d_pose7 (or LMState x / xc when
+// use_state != 0: 1 -> x, 2 -> xc) into c->partials, then run the LM state machine step (`lm_mode`):
+//   0: none (partials only, reduced into d_out28 if non-null)   1: begin Solve   2: iterate
+int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, double huber_a, const double *d_pose7,
+                     int use_state, int lm_mode, double *d_out29);
+int lm_init_state(Ctx *c, const double *pose7_host, int max_inner, double eig_thre);
+int factor_evaluate_device(Ctx *c, int kind, int n, const double *d_points, const double *d_coeffs, const double *d_sqrt_info,
+                           const double *d_params, double *d_res, double *d_jac);
+
+// comm.cu: in-place sum over ranks on the context stream (no-op without a communicator)
+int comm_allreduce_doubles(Ctx *c, double *d_buf, int count);
+
+// extract_kernels.cu
+struct ExtractOut {
+  float4 *sharp, *less_sharp, *flat, *less_flat;  // device buffers, capacity n each
+  int *counts;                                     // device int[4]
+};
+int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
+                   ExtractOut out, float *d_curv_or_null, int *d_label_or_null);
+// d_n_in (nullable): device-side input count (n is then the upper bound the kernels are sized for).
+int voxel_downsample_device(Ctx *c, const float4 *d_in, int n, const int *d_n_in, float leaf, int intensity_last, float4 *d_out,
+                            int *d_n_out, int work_slot = 5);
+
+}  // namespace mloam
+
+struct mloam_ctx {
+  mloam::Ctx c;
+};

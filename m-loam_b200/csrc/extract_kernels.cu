@@ -1,0 +1,628 @@
+// extract_kernels.cu — FeatureExtract::extractCloud (feature_extract.cpp:118-297) and the PCL voxel-grid
+// filters on its path (pcl::VoxelGrid<PointI>, feature_extract.cpp:267-270; VoxelGridCovarianceMLOAM<PointI>,
+// lidar_mapper_keyframe.cpp:359-364; algorithm mirrored in-tree at voxel_grid_covariance_mloam_impl.hpp:84-250).
+//
+//   k_curvature      11-tap stencil over the flat ring-major array (:133-142) + consecutive-gap flags (:194-197)
+//   k_ring_pick      one CTA per ring: per-sector bitonic sort of (curvature, index) in shared memory (:162),
+//                    then the data-dependent sharp / less-sharp / flat picks with +-5 suppression (:165-256)
+//   k_less_flat_*    label <= 0 compaction (:258-264)
+//   voxel pipeline   segment bbox -> voxel index -> stable radix sort -> run heads -> ordered centroid sums,
+//                    segments = rings for the per-ring filter (:266-271), one segment for whole-cloud filters
+//
+// Float arithmetic follows the reference's evaluation order; integer/index results are exact.
+#include "ctx.h"
+#include "primitives.cuh"
+
+namespace mloam {
+
+// ------------------------------------------------------------------------------------------ primitives
+__global__ void k_prim_tile_sums(const int *__restrict__ in, int n, int *__restrict__ tile_sums) {
+  const int base = blockIdx.x * PRIM_TILE + threadIdx.x * PRIM_ITEMS;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < PRIM_ITEMS; k++)
+    if (base + k < n) s += in[base + k];
+  int total;
+  prim_block_scan(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void k_prim_scan_tiles(int *tile_sums, int n_tiles, int *total_out) {
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += PRIM_THREADS) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_tiles ? tile_sums[i] : 0;
+    int total;
+    const int ex = prim_block_scan(v, &total);
+    if (i < n_tiles) tile_sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+__global__ void k_prim_scan_apply(const int *__restrict__ in, int n, const int *__restrict__ tile_sums, int *__restrict__ out) {
+  const int base = blockIdx.x * PRIM_TILE + threadIdx.x * PRIM_ITEMS;
+  int c[PRIM_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < PRIM_ITEMS; k++) {
+    c[k] = (base + k < n) ? in[base + k] : 0;
+    s += c[k];
+  }
+  int ex = prim_block_scan(s, nullptr) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < PRIM_ITEMS; k++) {
+    if (base + k < n) out[base + k] = ex;
+    ex += c[k];
+  }
+}
+
+// exclusive scan d_in[0..n) -> d_out (may alias), optional device total.  tmp must hold ceil(n/PRIM_TILE) ints.
+static void scan_exclusive(Ctx *c, const int *d_in, int *d_out, int n, int *d_tmp, int *d_total) {
+  if (n <= 0) {
+    if (d_total) cudaMemsetAsync(d_total, 0, sizeof(int), c->stream);
+    return;
+  }
+  const int nt = (n + PRIM_TILE - 1) / PRIM_TILE;
+  k_prim_tile_sums<<<nt, PRIM_THREADS, 0, c->stream>>>(d_in, n, d_tmp);
+  k_prim_scan_tiles<<<1, PRIM_THREADS, 0, c->stream>>>(d_tmp, nt, d_total);
+  k_prim_scan_apply<<<nt, PRIM_THREADS, 0, c->stream>>>(d_in, n, d_tmp, d_out);
+  c->launches += 3;
+}
+
+// Stable LSD radix sort, 8-bit digits.  Tile layout: warp w of the block owns keys
+// [blk*TILE + w*256, +256), visited in 8 rounds of 32 consecutive keys -> input order is preserved per digit.
+__global__ void k_rs_hist(const unsigned long long *__restrict__ keys, int n, int shift, int *__restrict__ hist, int nblk) {
+  __shared__ int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * PRIM_TILE;
+#pragma unroll
+  for (int k = 0; k < PRIM_ITEMS; k++) {
+    const int i = base + k * PRIM_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & 0xffull)], 1);
+  }
+  __syncthreads();
+  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+__global__ void k_rs_scatter(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, int n, int shift,
+                             const int *__restrict__ offs, int nblk, unsigned long long *__restrict__ keys_out,
+                             unsigned *__restrict__ vals_out) {
+  __shared__ int cnt[PRIM_THREADS / 32][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < (PRIM_THREADS / 32) * 256; k += PRIM_THREADS) (&cnt[0][0])[k] = 0;
+  __syncthreads();
+  const int wbase = blockIdx.x * PRIM_TILE + w * (PRIM_ITEMS * 32);
+  unsigned long long kk[PRIM_ITEMS];
+  int rank[PRIM_ITEMS];
+#pragma unroll
+  for (int it = 0; it < PRIM_ITEMS; it++) {
+    const int i = wbase + it * 32 + lane;
+    const bool ok = i < n;
+    kk[it] = ok ? keys[i] : 0ull;
+    const int d = (int)((kk[it] >> shift) & 0xffull);
+    const unsigned act = __ballot_sync(MLOAM_FULL_MASK, ok);
+    rank[it] = 0;
+    if (ok) {
+      const unsigned peers = __match_any_sync(act, d);
+      const int before = __popc(peers & ((1u << lane) - 1u));
+      rank[it] = cnt[w][d] + before;
+      __syncwarp(act);
+      if (before == 0) cnt[w][d] += __popc(peers);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // per digit: exclusive prefix over the block's warps
+    const int d = threadIdx.x;
+    int run = 0;
+#pragma unroll
+    for (int ww = 0; ww < PRIM_THREADS / 32; ww++) {
+      const int t = cnt[ww][d];
+      cnt[ww][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < PRIM_ITEMS; it++) {
+    const int i = wbase + it * 32 + lane;
+    if (i < n) {
+      const int d = (int)((kk[it] >> shift) & 0xffull);
+      const int pos = offs[d * nblk + blockIdx.x] + cnt[w][d] + rank[it];
+      keys_out[pos] = kk[it];
+      vals_out[pos] = vals[i];
+    }
+  }
+}
+
+struct SortBufs {
+  unsigned long long *k0, *k1;
+  unsigned *v0, *v1;
+  int *hist;  // 256 * nblk
+  int *tmp;   // scan tiles
+};
+// Sorts (k0,v0) by the low `nbits` of the key; returns which buffer holds the result (0 or 1).
+static int radix_sort(Ctx *c, SortBufs b, int n, int nbits) {
+  if (n <= 0) return 0;
+  const int nblk = (n + PRIM_TILE - 1) / PRIM_TILE;
+  int cur = 0;
+  for (int shift = 0; shift < nbits; shift += 8) {
+    unsigned long long *ki = cur ? b.k1 : b.k0, *ko = cur ? b.k0 : b.k1;
+    unsigned *vi = cur ? b.v1 : b.v0, *vo = cur ? b.v0 : b.v1;
+    k_rs_hist<<<nblk, PRIM_THREADS, 0, c->stream>>>(ki, n, shift, b.hist, nblk);
+    c->launches++;
+    scan_exclusive(c, b.hist, b.hist, 256 * nblk, b.tmp, nullptr);
+    k_rs_scatter<<<nblk, PRIM_THREADS, 0, c->stream>>>(ki, vi, n, shift, b.hist, nblk, ko, vo);
+    c->launches++;
+    cur ^= 1;
+  }
+  return cur;
+}
+
+// ------------------------------------------------------------------------------------------ voxel grid
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+struct SegBox {           // per segment
+  unsigned mn[3], mx[3];  // ordered-uint encodings of min / max
+};
+
+__global__ void k_seg_init(SegBox *box, int n_seg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_seg) {
+    for (int d = 0; d < 3; d++) box[i].mn[d] = 0xffffffffu, box[i].mx[d] = 0u;
+  }
+}
+// getMinMax3D over finite points (voxel_grid_covariance_mloam_impl.hpp:84-90)
+__global__ void k_seg_bbox(const float4 *__restrict__ pts, const int *__restrict__ seg, int n, const int *__restrict__ d_n_valid,
+                           SegBox *box) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_n_valid) n = min(n, *d_n_valid);
+  const bool in = i < n;
+  float4 p = in ? pts[i] : make_float4(0, 0, 0, 0);
+  const bool ok = in && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+  const int s = in ? (seg ? seg[i] : 0) : -1;
+  const int s0 = __shfl_sync(MLOAM_FULL_MASK, s, 0);
+  const bool uniform = __all_sync(MLOAM_FULL_MASK, s == s0 || !in);
+  unsigned mn[3] = {ok ? f2ord(p.x) : 0xffffffffu, ok ? f2ord(p.y) : 0xffffffffu, ok ? f2ord(p.z) : 0xffffffffu};
+  unsigned mx[3] = {ok ? f2ord(p.x) : 0u, ok ? f2ord(p.y) : 0u, ok ? f2ord(p.z) : 0u};
+  if (uniform && s0 >= 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      mn[d] = __reduce_min_sync(MLOAM_FULL_MASK, mn[d]);
+      mx[d] = __reduce_max_sync(MLOAM_FULL_MASK, mx[d]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        if (mn[d] != 0xffffffffu) atomicMin(&box[s0].mn[d], mn[d]);
+        if (mx[d] != 0u) atomicMax(&box[s0].mx[d], mx[d]);
+      }
+    }
+  } else if (ok) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) atomicMin(&box[s].mn[d], mn[d]), atomicMax(&box[s].mx[d], mx[d]);
+  }
+}
+
+// Voxel key per point: (segment << 32) | idx with idx = ijk . (1, div0, div0*div1)   (:206-222).
+// A segment whose index space would overflow int32 is passed through unchanged (:92-101): every point gets
+// its own key (position inside the segment).  Non-finite points get the all-ones key and are dropped later.
+__global__ void k_voxel_keys(const float4 *__restrict__ pts, const int *__restrict__ seg, const int *__restrict__ seg_begin, int n,
+                             const int *__restrict__ d_n_valid, float inv, const SegBox *__restrict__ box,
+                             unsigned long long *__restrict__ keys, unsigned *__restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  vals[i] = (unsigned)i;
+  if (d_n_valid && i >= *d_n_valid) {  // beyond the device-side count: dropped like a non-finite point
+    keys[i] = 0xffffffffffffffffull;
+    return;
+  }
+  const float4 p = pts[i];
+  const int s = seg ? seg[i] : 0;
+  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {
+    keys[i] = 0xffffffffffffffffull;
+    return;
+  }
+  const SegBox b = box[s];
+  const float mn0 = ord2f(b.mn[0]), mn1 = ord2f(b.mn[1]), mn2 = ord2f(b.mn[2]);
+  const float mx0 = ord2f(b.mx[0]), mx1 = ord2f(b.mx[1]), mx2 = ord2f(b.mx[2]);
+  const long long dx = (long long)((mx0 - mn0) * inv) + 1, dy = (long long)((mx1 - mn1) * inv) + 1,
+                  dz = (long long)((mx2 - mn2) * inv) + 1;
+  unsigned idx;
+  if (dx * dy * dz > 2147483647ll) {
+    idx = (unsigned)(i - (seg_begin ? seg_begin[s] : 0));
+  } else {
+    const int minb0 = (int)floorf(mn0 * inv), minb1 = (int)floorf(mn1 * inv), minb2 = (int)floorf(mn2 * inv);
+    const int maxb0 = (int)floorf(mx0 * inv), maxb1 = (int)floorf(mx1 * inv);
+    const int div0 = maxb0 - minb0 + 1, div1 = maxb1 - minb1 + 1;
+    const int i0 = (int)(floorf(p.x * inv) - (float)minb0);
+    const int i1 = (int)(floorf(p.y * inv) - (float)minb1);
+    const int i2 = (int)(floorf(p.z * inv) - (float)minb2);
+    idx = (unsigned)(i0 + i1 * div0 + i2 * (div0 * div1));
+  }
+  keys[i] = ((unsigned long long)(unsigned)s << 32) | idx;
+}
+
+__global__ void k_run_heads(const unsigned long long *__restrict__ keys, int n, int *__restrict__ head) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  head[i] = (k != 0xffffffffffffffffull && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+}
+
+// One thread per run head: accumulate the run in sorted (= input) order in float, divide by the float count
+// (Eigen 3.3 `centroid /= float(n)`).  intensity_last: VoxelGridCovarianceMLOAM keeps the last point's intensity
+// (voxel_grid_covariance_mloam_impl.hpp:417-428); otherwise pcl::VoxelGrid averages every field.
+__global__ void k_centroids(const float4 *__restrict__ pts, const unsigned long long *__restrict__ keys,
+                            const unsigned *__restrict__ vals, const int *__restrict__ head, const int *__restrict__ slot, int n,
+                            int intensity_last, float4 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !head[i]) return;
+  const unsigned long long k = keys[i];
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f, last = 0.f;
+  int j = i;
+  for (; j < n && keys[j] == k; j++) {
+    const float4 p = pts[vals[j]];
+    sx = sx + p.x, sy = sy + p.y, sz = sz + p.z, si = si + p.w;
+    last = p.w;
+  }
+  const float cnt = (float)(j - i);
+  out[slot[i]] = make_float4(sx / cnt, sy / cnt, sz / cnt, intensity_last ? last : si / cnt);
+}
+
+// Shared voxel pipeline.  scratch layout is owned by the caller (VoxelWork).
+struct VoxelWork {
+  SegBox *box;
+  unsigned long long *k0, *k1;
+  unsigned *v0, *v1;
+  int *hist, *tmp, *head, *slot;
+};
+static int voxel_pipeline(Ctx *c, const float4 *d_pts, const int *d_seg, const int *d_seg_begin, int n, const int *d_n_valid,
+                          int n_seg, float leaf, int intensity_last, VoxelWork w, float4 *d_out, int *d_n_out) {
+  cudaStream_t st = c->stream;
+  if (n <= 0) {
+    cudaMemsetAsync(d_n_out, 0, sizeof(int), st);
+    return MLOAM_OK;
+  }
+  const float inv = 1.0f / leaf;
+  const int nb = (n + 255) / 256;
+  k_seg_init<<<(n_seg + 127) / 128, 128, 0, st>>>(w.box, n_seg);
+  k_seg_bbox<<<nb, 256, 0, st>>>(d_pts, d_seg, n, d_n_valid, w.box);
+  k_voxel_keys<<<nb, 256, 0, st>>>(d_pts, d_seg, d_seg_begin, n, d_n_valid, inv, w.box, w.k0, w.v0);
+  c->launches += 3;
+  int seg_bits = 0;
+  while ((1 << seg_bits) < n_seg) seg_bits++;
+  SortBufs sb{w.k0, w.k1, w.v0, w.v1, w.hist, w.tmp};
+  // all-ones keys (non-finite points) must sort last: include the full 64 bits only when a segment id is present
+  const int nbits = n_seg > 1 ? 32 + ((seg_bits + 7) / 8) * 8 : 32;
+  const int cur = radix_sort(c, sb, n, nbits);
+  const unsigned long long *ks = cur ? w.k1 : w.k0;
+  const unsigned *vs = cur ? w.v1 : w.v0;
+  k_run_heads<<<nb, 256, 0, st>>>(ks, n, w.head);
+  c->launches++;
+  scan_exclusive(c, w.head, w.slot, n, w.tmp, d_n_out);
+  k_centroids<<<nb, 256, 0, st>>>(d_pts, ks, vs, w.head, w.slot, n, intensity_last, d_out);
+  c->launches++;
+  return MLOAM_OK;
+}
+
+static int voxel_work_reserve(Ctx *c, DevBuf &buf, int n, int n_seg, VoxelWork *w) {
+  const int nblk = (n + PRIM_TILE - 1) / PRIM_TILE + 1;
+  const int n_hist = 256 * nblk;
+  const int n_tmp = (std::max(n, n_hist) + PRIM_TILE - 1) / PRIM_TILE + 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_box = take(sizeof(SegBox) * (size_t)(n_seg + 1));
+  const size_t o_k0 = take(8 * (size_t)(n + 1)), o_k1 = take(8 * (size_t)(n + 1));
+  const size_t o_v0 = take(4 * (size_t)(n + 1)), o_v1 = take(4 * (size_t)(n + 1));
+  const size_t o_hist = take(4 * (size_t)n_hist), o_tmp = take(4 * (size_t)n_tmp);
+  const size_t o_head = take(4 * (size_t)(n + 1)), o_slot = take(4 * (size_t)(n + 1));
+  MLOAM_CUDA_OK(c, buf.reserve(off));
+  char *p = buf.as<char>();
+  w->box = reinterpret_cast<SegBox *>(p + o_box);
+  w->k0 = reinterpret_cast<unsigned long long *>(p + o_k0), w->k1 = reinterpret_cast<unsigned long long *>(p + o_k1);
+  w->v0 = reinterpret_cast<unsigned *>(p + o_v0), w->v1 = reinterpret_cast<unsigned *>(p + o_v1);
+  w->hist = reinterpret_cast<int *>(p + o_hist), w->tmp = reinterpret_cast<int *>(p + o_tmp);
+  w->head = reinterpret_cast<int *>(p + o_head), w->slot = reinterpret_cast<int *>(p + o_slot);
+  return MLOAM_OK;
+}
+
+int voxel_downsample_device(Ctx *c, const float4 *d_in, int n, const int *d_n_in, float leaf, int intensity_last, float4 *d_out,
+                            int *d_n_out, int work_slot) {
+  if (!(leaf > 0.f) || n < 0) {
+    c->err = "voxel_downsample: bad leaf / size";
+    return MLOAM_E_INVALID;
+  }
+  ProfScope ps(c, "voxel");
+  VoxelWork w;
+  int rc = voxel_work_reserve(c, c->scratch[work_slot], n, 1, &w);
+  if (rc) return rc;
+  rc = voxel_pipeline(c, d_in, nullptr, nullptr, n, d_n_in, 1, leaf, intensity_last, w, d_out, d_n_out);
+  if (rc) return rc;
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  return MLOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ extractCloud
+constexpr int CURV_THREADS = 256;
+
+// :133-142.  Also gap_ok[i] = |p[i+1]-p[i]|^2 <= 0.05 (the suppression test of :194-197 / :205-208, which
+// compares a float against the double literal 0.05) and the ring id of every point inside a ring's
+// [scan_start, scan_end) window (-1 elsewhere).
+__global__ void __launch_bounds__(CURV_THREADS)
+    k_curvature(const float4 *__restrict__ P, int n, float *__restrict__ curv, unsigned char *__restrict__ gap_ok,
+                int *__restrict__ label) {
+  __shared__ float sx[CURV_THREADS + 10], sy[CURV_THREADS + 10], sz[CURV_THREADS + 10];
+  const int base = blockIdx.x * CURV_THREADS;
+  for (int t = threadIdx.x; t < CURV_THREADS + 10; t += CURV_THREADS) {
+    const int g = base + t - 5;
+    float4 p = (g >= 0 && g < n) ? P[g] : make_float4(0, 0, 0, 0);
+    sx[t] = p.x, sy[t] = p.y, sz[t] = p.z;
+  }
+  __syncthreads();
+  const int i = base + threadIdx.x;
+  if (i >= n) return;
+  const int t = threadIdx.x + 5;
+  float c = 0.f;
+  if (i >= 5 && i < n - 5) {
+    const float dx = sx[t - 5] + sx[t - 4] + sx[t - 3] + sx[t - 2] + sx[t - 1] - 10 * sx[t] + sx[t + 1] + sx[t + 2] + sx[t + 3] +
+                     sx[t + 4] + sx[t + 5];
+    const float dy = sy[t - 5] + sy[t - 4] + sy[t - 3] + sy[t - 2] + sy[t - 1] - 10 * sy[t] + sy[t + 1] + sy[t + 2] + sy[t + 3] +
+                     sy[t + 4] + sy[t + 5];
+    const float dz = sz[t - 5] + sz[t - 4] + sz[t - 3] + sz[t - 2] + sz[t - 1] - 10 * sz[t] + sz[t + 1] + sz[t + 2] + sz[t + 3] +
+                     sz[t + 4] + sz[t + 5];
+    c = dx * dx + dy * dy + dz * dz;
+  }
+  curv[i] = c;
+  label[i] = 0;
+  unsigned char g = 0;
+  if (i + 1 < n) {
+    const float ex = sx[t + 1] - sx[t], ey = sy[t + 1] - sy[t], ez = sz[t + 1] - sz[t];
+    g = ((double)(ex * ex + ey * ey + ez * ez) > 0.05) ? 0 : 1;
+  }
+  gap_ok[i] = g;
+}
+
+constexpr int RING_THREADS = 256;
+constexpr int RING_MAX = 12288;      // points per ring handled on chip (picked/gap bytes)
+constexpr int SECTOR_MAX = 2048;     // sort capacity per sector (RING_MAX / 6)
+constexpr int PICK_SHARP = 12, PICK_LESS = 120, PICK_FLAT = 24;  // per ring: 6 sectors x (2, 20, 4)
+
+struct RingStage {  // per ring picks, indices into the cloud
+  int n_sharp, n_less, n_flat, pad;
+  int sharp[PICK_SHARP];
+  int less[PICK_LESS];
+  int flat[PICK_FLAT];
+};
+
+__global__ void __launch_bounds__(RING_THREADS)
+    k_ring_pick(const float *__restrict__ curv, const unsigned char *__restrict__ gap_ok_g, int n, const int *__restrict__ scan_start,
+                const int *__restrict__ scan_end, int *__restrict__ label, int *__restrict__ ring_of, RingStage *__restrict__ stage,
+                int *__restrict__ status) {
+  __shared__ unsigned long long keys[SECTOR_MAX];
+  __shared__ unsigned char picked[RING_MAX + 16];
+  __shared__ unsigned char gap[RING_MAX + 16];
+  const int ring = blockIdx.x;
+  RingStage &S = stage[ring];
+  if (threadIdx.x == 0) S.n_sharp = S.n_less = S.n_flat = 0;
+  const int s = scan_start[ring], e = scan_end[ring];
+  if (e - s < 6) return;  // :155
+  // on-chip window [lo, hi) = [s-5, e+5): every index the picks can touch (ind +- 5, ind in [s, e-1])
+  const int lo = s - 5, hi = e + 5;
+  if (hi - lo > RING_MAX || lo < 0 || hi > n) {
+    if (threadIdx.x == 0) atomicExch(status, 1);  // ring too long for the on-chip window / ScanInfo out of range
+    return;
+  }
+  for (int t = threadIdx.x; t < hi - lo; t += RING_THREADS) {
+    picked[t] = 0;
+    gap[t] = gap_ok_g[lo + t];
+  }
+  for (int k = s + threadIdx.x; k < e; k += RING_THREADS) ring_of[k] = ring;  // :258 range [sp_0, ep_5] = [s, e-1]
+  __syncthreads();
+  for (int j = 0; j < 6; j++) {
+    const int sp = s + (e - s) * j / 6;            // :160
+    const int ep = s + (e - s) * (j + 1) / 6 - 1;  // :161
+    const int len = ep - sp + 1;
+    int P2 = 1;
+    while (P2 < len) P2 <<= 1;
+    if (P2 > SECTOR_MAX) {
+      if (threadIdx.x == 0) atomicExch(status, 1);
+      return;
+    }
+    // :162 sort ascending by curvature; ties by index (the reference's std::sort leaves ties unspecified)
+    for (int t = threadIdx.x; t < P2; t += RING_THREADS)
+      keys[t] = t < len ? (((unsigned long long)__float_as_uint(curv[sp + t]) << 32) | (unsigned)(sp + t)) : 0xffffffffffffffffull;
+    __syncthreads();
+    for (int k2 = 2; k2 <= P2; k2 <<= 1) {
+      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+        for (int t = threadIdx.x; t < P2; t += RING_THREADS) {
+          const int ixj = t ^ j2;
+          if (ixj > t) {
+            const unsigned long long a = keys[t], b = keys[ixj];
+            const bool up = (t & k2) == 0;
+            if ((a > b) == up) keys[t] = b, keys[ixj] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x == 0) {
+      // :165-215 edge points, largest curvature first
+      int largest = 0;
+      for (int k = len - 1; k >= 0; k--) {
+        const unsigned long long kk = keys[k];
+        const float cv = __uint_as_float((unsigned)(kk >> 32));
+        if (!((double)cv > 0.1)) break;  // sorted: nothing below can pass `curvature > 0.1`
+        const int ind = (int)(unsigned)(kk & 0xffffffffu);
+        const int o = ind - lo;
+        if (picked[o] == 0) {
+          largest++;
+          if (largest <= 2) {
+            label[ind] = 2;
+            S.sharp[S.n_sharp++] = ind;
+            S.less[S.n_less++] = ind;
+          } else if (largest <= 20) {
+            label[ind] = 1;
+            S.less[S.n_less++] = ind;
+          } else {
+            break;
+          }
+          picked[o] = 1;
+          for (int l = 1; l <= 5; l++) {
+            if (!gap[o + l - 1]) break;
+            picked[o + l] = 1;
+          }
+          for (int l = -1; l >= -5; l--) {
+            if (!gap[o + l]) break;
+            picked[o + l] = 1;
+          }
+        }
+      }
+      // :218-256 flat points, smallest curvature first; the 4th pick breaks before any marking (:227-231)
+      int smallest = 0;
+      for (int k = 0; k < len; k++) {
+        const unsigned long long kk = keys[k];
+        const float cv = __uint_as_float((unsigned)(kk >> 32));
+        if (!((double)cv < 0.1)) break;
+        const int ind = (int)(unsigned)(kk & 0xffffffffu);
+        const int o = ind - lo;
+        if (picked[o] == 0) {
+          label[ind] = -1;
+          S.flat[S.n_flat++] = ind;
+          smallest++;
+          if (smallest >= 4) break;
+          picked[o] = 1;
+          for (int l = 1; l <= 5; l++) {
+            if (!gap[o + l - 1]) break;
+            picked[o + l] = 1;
+          }
+          for (int l = -1; l >= -5; l--) {
+            if (!gap[o + l]) break;
+            picked[o + l] = 1;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Emit the staged picks in ring order (the order the reference's push_backs produce).
+__global__ void k_emit_picks(const float4 *__restrict__ P, const RingStage *__restrict__ stage, int n_scans, float4 *__restrict__ sharp,
+                             float4 *__restrict__ less, float4 *__restrict__ flat, int *__restrict__ counts) {
+  __shared__ int off[3][129];
+  if (threadIdx.x == 0) {
+    int a = 0, b = 0, c = 0;
+    for (int r = 0; r < n_scans; r++) {
+      off[0][r] = a, off[1][r] = b, off[2][r] = c;
+      a += stage[r].n_sharp, b += stage[r].n_less, c += stage[r].n_flat;
+    }
+    counts[0] = a, counts[1] = b, counts[2] = c;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < n_scans; r += blockDim.x) {
+    const RingStage &S = stage[r];
+    for (int k = 0; k < S.n_sharp; k++) sharp[off[0][r] + k] = P[S.sharp[k]];
+    for (int k = 0; k < S.n_less; k++) less[off[1][r] + k] = P[S.less[k]];
+    for (int k = 0; k < S.n_flat; k++) flat[off[2][r] + k] = P[S.flat[k]];
+  }
+}
+
+__global__ void k_ring_of_init(int *ring_of, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ring_of[i] = -1;
+}
+// :258-264: every point of a processed ring window with label <= 0
+__global__ void k_less_flat_flags(const int *__restrict__ ring_of, const int *__restrict__ label, int n, int *__restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (ring_of[i] >= 0 && label[i] <= 0) ? 1 : 0;
+}
+__global__ void k_less_flat_gather(const float4 *__restrict__ P, const int *__restrict__ ring_of, const int *__restrict__ flag,
+                                   const int *__restrict__ pos, const int *__restrict__ scan_start, int n, float4 *__restrict__ out,
+                                   int *__restrict__ seg, int *__restrict__ seg_begin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = ring_of[i];
+  if (r >= 0 && i == scan_start[r]) seg_begin[r] = pos[i];
+  if (flag[i]) {
+    out[pos[i]] = P[i];
+    seg[pos[i]] = r;
+  }
+}
+
+int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
+                   ExtractOut out, float *d_curv_or_null, int *d_label_or_null) {
+  if (n < 0 || n_scans <= 0 || n_scans > 128) {
+    c->err = "extract: n_scans must be in 1..128";
+    return MLOAM_E_INVALID;
+  }
+  ProfScope ps(c, "extract");
+  cudaStream_t st = c->stream;
+  // scratch[4]: curv | label | ring_of | flag | pos | gap | stage | seg | seg_begin | status | less-flat points
+  DevBuf &B = c->scratch[4];
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t N1 = (size_t)n + 16;
+  const size_t o_curv = take(4 * N1), o_label = take(4 * N1), o_ring = take(4 * N1), o_flag = take(4 * N1), o_pos = take(4 * N1);
+  const size_t o_gap = take(N1), o_stage = take(sizeof(RingStage) * 128), o_seg = take(4 * N1), o_segb = take(4 * 130);
+  const size_t o_status = take(16), o_lf = take(16 * N1), o_tmp = take(4 * (N1 / PRIM_TILE + 2));
+  MLOAM_CUDA_OK(c, B.reserve(off));
+  char *p = B.as<char>();
+  float *curv = reinterpret_cast<float *>(p + o_curv);
+  int *label = reinterpret_cast<int *>(p + o_label), *ring_of = reinterpret_cast<int *>(p + o_ring);
+  int *flag = reinterpret_cast<int *>(p + o_flag), *pos = reinterpret_cast<int *>(p + o_pos);
+  unsigned char *gap = reinterpret_cast<unsigned char *>(p + o_gap);
+  RingStage *stage = reinterpret_cast<RingStage *>(p + o_stage);
+  int *seg = reinterpret_cast<int *>(p + o_seg), *seg_begin = reinterpret_cast<int *>(p + o_segb);
+  int *status = reinterpret_cast<int *>(p + o_status);
+  int *n_lf = status + 1;
+  c->d_extract_status = status;
+  float4 *lf = reinterpret_cast<float4 *>(p + o_lf);
+  int *tmp = reinterpret_cast<int *>(p + o_tmp);
+  VoxelWork vw;
+  int rc = voxel_work_reserve(c, c->scratch[5], n, n_scans, &vw);
+  if (rc) return rc;
+  MLOAM_CUDA_OK(c, cudaMemsetAsync(out.counts, 0, 4 * sizeof(int), st));
+  MLOAM_CUDA_OK(c, cudaMemsetAsync(status, 0, sizeof(int), st));
+  MLOAM_CUDA_OK(c, cudaMemsetAsync(seg_begin, 0, 130 * sizeof(int), st));
+  if (n == 0) return MLOAM_OK;
+  const int nb = (n + 255) / 256;
+  k_curvature<<<(n + CURV_THREADS - 1) / CURV_THREADS, CURV_THREADS, 0, st>>>(d_cloud, n, curv, gap, label);
+  k_ring_of_init<<<nb, 256, 0, st>>>(ring_of, n);
+  k_ring_pick<<<n_scans, RING_THREADS, 0, st>>>(curv, gap, n, d_scan_start, d_scan_end, label, ring_of, stage, status);
+  k_emit_picks<<<1, 128, 0, st>>>(d_cloud, stage, n_scans, out.sharp, out.less_sharp, out.flat, out.counts);
+  k_less_flat_flags<<<nb, 256, 0, st>>>(ring_of, label, n, flag);
+  c->launches += 5;
+  scan_exclusive(c, flag, pos, n, tmp, out.counts + 3 /* provisional: points entering the per-ring voxel grid */);
+  k_less_flat_gather<<<nb, 256, 0, st>>>(d_cloud, ring_of, flag, pos, d_scan_start, n, lf, seg, seg_begin);
+  c->launches++;
+  // :266-271 per-ring pcl::VoxelGrid(0.2) == one segmented voxel pipeline over all rings.  The number of
+  // less-flat candidates is only known on the device: the pipeline runs over the upper bound n with the
+  // device-side count gating the tail, so no host round trip is needed.
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(n_lf, out.counts + 3, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  rc = voxel_pipeline(c, lf, seg, seg_begin, n, n_lf, n_scans, 0.2f, 0, vw, out.less_flat, out.counts + 3);
+  if (rc) return rc;
+  if (d_curv_or_null) MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_curv_or_null, curv, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (d_label_or_null) MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_label_or_null, label, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  return MLOAM_OK;
+}
+
+}  // namespace mloam

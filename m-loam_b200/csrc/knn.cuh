@@ -1,0 +1,156 @@
+// knn.cuh — exact K-nearest-neighbour search over the GPU voxel-hash map, one WARP per query.
+//
+// Replaces pcl::KdTreeFLANN::nearestKSearch (feature_extract.hpp:155,293,406,570,666,813).
+// Semantics: the K nearest map points in ascending (squared distance, original index) order, where the
+// squared distance is FLANN's L2_Simple in float (dx*dx + dy*dy + dz*dz, rounded per operation), limited
+// to points with d2 < max_sqdist — which is all the callers look at: every reference caller rejects the
+// query unless sqdist[K-1] < MIN_MATCH_SQ_DIS (or sqdist[0] < DISTANCE_SQ_THRESHOLD for K=1).
+//
+// Search: cells are visited in Chebyshev shells around the query's cell.  In a shell each lane owns one
+// cell: it probes the hash (one 16 B load) and scans that cell's points (contiguous float4, L1-resident
+// after the first touch) into a private sorted top-K.  After a shell the 32 private lists are merged with
+// warp reductions; the search stops when the K-th distance is below the distance to the faces of the cube
+// visited so far (nothing outside can be closer), or when that face distance exceeds the search radius.
+#pragma once
+#include "common.cuh"
+
+namespace mloam {
+
+#define MLOAM_KEY_NONE 0xffffffffffffffffull
+
+template <int K>
+struct TopK {
+  unsigned long long key[K];  // (float bits of d2) << 32 | original index
+  int pos[K];                 // position in MapView::sorted
+};
+
+template <int K>
+__device__ __forceinline__ void topk_reset(TopK<K> &t) {
+#pragma unroll
+  for (int i = 0; i < K; i++) t.key[i] = MLOAM_KEY_NONE, t.pos[i] = -1;
+}
+
+template <int K>
+__device__ __forceinline__ void topk_insert(TopK<K> &t, unsigned long long key, int pos) {
+  if (key < t.key[K - 1]) {
+    t.key[K - 1] = key;
+    t.pos[K - 1] = pos;
+#pragma unroll
+    for (int i = K - 1; i > 0; --i) {
+      if (t.key[i] < t.key[i - 1]) {
+        unsigned long long tk = t.key[i];
+        t.key[i] = t.key[i - 1];
+        t.key[i - 1] = tk;
+        int tp = t.pos[i];
+        t.pos[i] = t.pos[i - 1];
+        t.pos[i - 1] = tp;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  unsigned hi = (unsigned)(v >> 32);
+  unsigned mh = __reduce_min_sync(MLOAM_FULL_MASK, hi);
+  unsigned lo = (hi == mh) ? (unsigned)v : 0xffffffffu;
+  unsigned ml = __reduce_min_sync(MLOAM_FULL_MASK, lo);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
+// Merge the 32 private lists into the warp-wide top-K.  On return lane 0 holds the merged list and every
+// other lane an empty one (the union of private lists stays the best K seen so far); `out` is replicated.
+template <int K>
+__device__ __forceinline__ void warp_merge(TopK<K> &mine, TopK<K> &out, int lane) {
+#pragma unroll
+  for (int r = 0; r < K; r++) {
+    unsigned long long cur = mine.key[0];
+    unsigned long long m = warp_min_u64(cur);
+    unsigned owners = __ballot_sync(MLOAM_FULL_MASK, cur == m);
+    int src = __ffs(owners) - 1;
+    int p = __shfl_sync(MLOAM_FULL_MASK, mine.pos[0], src);
+    out.key[r] = m;
+    out.pos[r] = (m == MLOAM_KEY_NONE) ? -1 : p;
+    if (lane == src && m != MLOAM_KEY_NONE) {  // pop
+#pragma unroll
+      for (int i = 0; i < K - 1; i++) mine.key[i] = mine.key[i + 1], mine.pos[i] = mine.pos[i + 1];
+      mine.key[K - 1] = MLOAM_KEY_NONE;
+      mine.pos[K - 1] = -1;
+    }
+  }
+  if (lane == 0) mine = out;
+  else topk_reset(mine);
+}
+
+__device__ __forceinline__ HashEntry hash_lookup(const MapView &map, unsigned long long key) {
+  unsigned h = hash_cell(key) & map.mask;
+  while (true) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(map.table + h));
+    unsigned long long k = ((unsigned long long)raw.y << 32) | raw.x;
+    if (k == key) {
+      HashEntry e;
+      e.key = k, e.start = (int)raw.z, e.count = (int)raw.w;
+      return e;
+    }
+    if (k == MLOAM_EMPTY_KEY) {
+      HashEntry e;
+      e.key = k, e.start = 0, e.count = 0;
+      return e;
+    }
+    h = (h + 1) & map.mask;
+  }
+}
+
+// Warp-cooperative search.  All lanes pass the same query; `out` is replicated in every lane.
+template <int K>
+__device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy, float qz, float max_sqdist, int lane,
+                                         TopK<K> &out) {
+  TopK<K> mine;
+  topk_reset(mine);
+  topk_reset(out);
+  const int cx = (int)floorf(qx * map.inv_cell), cy = (int)floorf(qy * map.inv_cell), cz = (int)floorf(qz * map.inv_cell);
+  const float eps = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 8.0f * map.cell) + 1e-6f;
+  const float radius = sqrtf(max_sqdist);
+  int rmax = (int)ceilf(radius * map.inv_cell) + 1;
+  if (rmax > 16) rmax = 16;
+  for (int r = 1; r <= rmax; r++) {
+    const int s = 2 * r + 1;
+    const int ncell = s * s * s;
+    for (int base = 0; base < ncell; base += 32) {
+      const int c = base + lane;
+      if (c < ncell) {
+        const int dz = c / (s * s) - r;
+        const int rem = c % (s * s);
+        const int dy = rem / s - r;
+        const int dx = rem % s - r;
+        const int cheb = max(max(abs(dx), abs(dy)), abs(dz));
+        if (r == 1 || cheb == r) {  // shells r >= 2 skip the cube already visited
+          const HashEntry e = hash_lookup(map, pack_cell(cx + dx, cy + dy, cz + dz));
+          const float4 *p = map.sorted + e.start;
+          for (int j = 0; j < e.count; j++) {
+            const float4 v = __ldg(p + j);
+            const float ex = v.x - qx, ey = v.y - qy, ez = v.z - qz;
+            const float d2 = ex * ex + ey * ey + ez * ez;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(v.w);
+            topk_insert(mine, key, e.start + j);
+          }
+        }
+      }
+    }
+    warp_merge(mine, out, lane);
+    // distance from the query to the nearest face of the visited cube [c-r, c+r+1) * cell
+    float g = qx - (float)(cx - r) * map.cell;
+    g = fminf(g, (float)(cx + r + 1) * map.cell - qx);
+    g = fminf(g, qy - (float)(cy - r) * map.cell);
+    g = fminf(g, (float)(cy + r + 1) * map.cell - qy);
+    g = fminf(g, qz - (float)(cz - r) * map.cell);
+    g = fminf(g, (float)(cz + r + 1) * map.cell - qz);
+    g = g - eps;
+    if (g > 0.0f) {
+      const float g2 = g * g;
+      if (g2 >= max_sqdist) break;
+      if (out.key[K - 1] != MLOAM_KEY_NONE && __uint_as_float((unsigned)(out.key[K - 1] >> 32)) < g2) break;
+    }
+  }
+}
+
+}  // namespace mloam

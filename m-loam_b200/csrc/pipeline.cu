@@ -1,0 +1,312 @@
+// pipeline.cu — the orchestrators of the hot path as kernel sequences on the context stream:
+//   scan2MapOptimization  (lidar_mapper_keyframe.cpp:423-639, gf_method wo_gf)
+//   the per-sweep frame   (extractCloud -> downsampleCurrentScan -> scan2MapOptimization)
+// plus the host-buffer entry points of extraction and the voxel filters.
+//
+// Feature counts produced on the device (extraction, voxel filters) are consumed on the device: kernels are
+// sized for the host-known upper bound and read the true count from HBM, so a frame with max_inner == 1 runs
+// without a single host round trip until the final pose read-back.
+#include <cstdio>
+#include <cstring>
+
+#include "ctx.h"
+#include "host_util.h"
+
+using namespace mloam;
+
+namespace {
+
+struct ScanRef {
+  const float4 *surf;
+  int n_surf;            // count or upper bound
+  const int *d_n_surf;   // nullable
+  const float4 *corner;
+  int n_corner;
+  const int *d_n_corner;
+};
+
+int scan2map_run(Ctx *c, const ScanRef &S, const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+  const mloam_params_t &P = c->params;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  for (int k = 0; k < 7; k++) pose_out7[k] = pose_init7[k];
+  const MapStorage &MS = c->maps[MLOAM_MAP_SURF], &MC = c->maps[MLOAM_MAP_CORNER];
+  if (!MS.built || !MC.built) return fail(c, MLOAM_E_STATE, "scan2map: build MLOAM_MAP_SURF and MLOAM_MAP_CORNER first");
+  if (!((MS.m > 50) && (MC.m > 10))) return MLOAM_OK;  // lidar_mapper_keyframe.cpp:429 ("Map surf num is not enough")
+  int rc = reserve_feat(c, 0, S.n_corner);
+  if (rc) return rc;
+  rc = reserve_feat(c, 1, S.n_surf);
+  if (rc) return rc;
+  rc = lm_init_state(c, pose_init7, P.max_inner, P.eig_thre);
+  if (rc) return rc;
+  LMState *st = c->lm_state.as<LMState>();
+  const double *d_pose = st->x;  // first member
+  const double sinfo = map_sqrt_info(P.cov_trace);
+  const MatchCfg cfg = match_cfg(c);
+  int *h_done = reinterpret_cast<int *>(reinterpret_cast<char *>(c->pinned) + 2048);
+  const int nc_use = P.point_edge_factor ? S.n_corner : 0, ns_use = P.point_plane_factor ? S.n_surf : 0;
+  FeatSet sets[2] = {
+      FeatSet{S.corner, c->feat_valid[0].as<unsigned char>(), c->feat_coeff[0].as<float>(), nc_use, 0, S.d_n_corner},
+      FeatSet{S.surf, c->feat_valid[1].as<unsigned char>(), c->feat_coeff[1].as<float>(), ns_use, 1, S.d_n_surf}};
+  for (int outer = 0; outer < P.max_outer; outer++) {
+    // :503-532  match corner then surf at pose_wmap_curr (wo_gf: every feature)
+    if (nc_use > 0) {
+      rc = match_from_map_device(c, MLOAM_MAP_CORNER, 'c', S.corner, nc_use, S.d_n_corner, d_pose, cfg,
+                                 c->feat_valid[0].as<unsigned char>(), c->feat_coeff[0].as<float>(), nullptr);
+      if (rc) return rc;
+    }
+    if (ns_use > 0) {
+      rc = match_from_map_device(c, MLOAM_MAP_SURF, 's', S.surf, ns_use, S.d_n_surf, d_pose, cfg,
+                                 c->feat_valid[1].as<unsigned char>(), c->feat_coeff[1].as<float>(), nullptr);
+      if (rc) return rc;
+    }
+    // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve
+    rc = linearize_device(c, sets, 2, sinfo, P.huber_a, nullptr, 1, 1, nullptr);
+    if (rc) return rc;
+    // :586-596 ceres::Solve, at most max_inner LM iterations; the device raises `done`
+    for (int it = 0; it < P.max_inner; it++) {
+      rc = linearize_device(c, sets, 2, sinfo, P.huber_a, nullptr, 2, 2, nullptr);
+      if (rc) return rc;
+      if (P.max_inner > 1) {
+        MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        MLOAM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        if (*h_done) break;
+      }
+    }
+  }
+  char *pin = reinterpret_cast<char *>(c->pinned);
+  LMState *hs = reinterpret_cast<LMState *>(pin + 4096);
+  int *h_cnt = reinterpret_cast<int *>(pin + 3072);
+  h_cnt[0] = S.n_surf, h_cnt[1] = S.n_corner;
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(hs, st, sizeof(LMState), cudaMemcpyDeviceToHost, c->stream));
+  if (S.d_n_surf) MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_cnt, S.d_n_surf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (S.d_n_corner) MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_cnt + 1, S.d_n_corner, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 7; k++) pose_out7[k] = hs->x[k];
+  if (stats) {
+    stats->ran = 1;
+    stats->n_corner = hs->n_valid[0], stats->n_surf = hs->n_valid[1];
+    stats->lm_iterations = hs->total_iterations;
+    stats->degenerate = hs->is_degenerate;
+    stats->termination = hs->termination;
+    stats->final_cost = hs->cost;
+    memcpy(stats->eig, hs->eig, sizeof(stats->eig));
+    memcpy(stats->H, hs->H0, sizeof(stats->H));
+    stats->n_surf_in = h_cnt[0], stats->n_corner_in = h_cnt[1];
+  }
+  return MLOAM_OK;
+}
+
+// Device buffers of one frame: feature sets of extractCloud + the down-sampled scans fed to matching.
+struct FrameBufs {
+  ExtractOut ex;
+  float4 *corner_ds, *surf_ds;
+  int *n_corner_ds, *n_surf_ds;  // device counts
+};
+int frame_bufs(Ctx *c, int n, FrameBufs *F) {
+  DevBuf &B = c->scratch[6];
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t N1 = (size_t)n + 16;
+  const size_t o_sharp = take(16 * N1), o_less = take(16 * N1), o_flat = take(16 * N1), o_lflat = take(16 * N1);
+  const size_t o_cds = take(16 * N1), o_sds = take(16 * N1), o_cnt = take(64);
+  MLOAM_CUDA_OK(c, B.reserve(off));
+  char *p = B.as<char>();
+  F->ex.sharp = reinterpret_cast<float4 *>(p + o_sharp), F->ex.less_sharp = reinterpret_cast<float4 *>(p + o_less);
+  F->ex.flat = reinterpret_cast<float4 *>(p + o_flat), F->ex.less_flat = reinterpret_cast<float4 *>(p + o_lflat);
+  F->corner_ds = reinterpret_cast<float4 *>(p + o_cds), F->surf_ds = reinterpret_cast<float4 *>(p + o_sds);
+  int *cnt = reinterpret_cast<int *>(p + o_cnt);
+  F->ex.counts = cnt;  // [0..3]
+  F->n_corner_ds = cnt + 4, F->n_surf_ds = cnt + 5;
+  return MLOAM_OK;
+}
+
+int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
+              const float4 *d_surf_map, int n_surf_map, const float4 *d_corner_map, int n_corner_map, int rebuild_maps,
+              const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+  const mloam_params_t &P = c->params;
+  int rc;
+  if (rebuild_maps) {  // lidar_mapper_keyframe.cpp:433-434 (every frame in the reference)
+    rc = map_build_device(c, MLOAM_MAP_SURF, d_surf_map, n_surf_map, pick_cell(c, 0.f));
+    if (rc) return rc;
+    rc = map_build_device(c, MLOAM_MAP_CORNER, d_corner_map, n_corner_map, pick_cell(c, 0.f));
+    if (rc) return rc;
+  }
+  FrameBufs F;
+  rc = frame_bufs(c, n, &F);
+  if (rc) return rc;
+  rc = extract_device(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, F.ex, nullptr, nullptr);
+  if (rc) return rc;
+  // downsampleCurrentScan, lidar_mapper_keyframe.cpp:356-364 (VoxelGridCovarianceMLOAM<PointI>: xyz mean, last intensity)
+  const int less_cap = n < 120 * n_scans ? n : 120 * n_scans;  // <= 20 less-sharp picks x 6 sectors per ring
+  rc = voxel_downsample_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, P.corner_leaf, 1, F.corner_ds, F.n_corner_ds, 5);
+  if (rc) return rc;
+  rc = voxel_downsample_device(c, F.ex.less_flat, n, F.ex.counts + 3, P.surf_leaf, 1, F.surf_ds, F.n_surf_ds, 5);
+  if (rc) return rc;
+  ScanRef S{F.surf_ds, n, F.n_surf_ds, F.corner_ds, less_cap, F.n_corner_ds};
+  return scan2map_run(c, S, pose_init7, pose_out7, stats);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------ scan2map
+int mloam_scan2map_device(mloam_ctx_t *h, const mloam_point_t *d_surf_scan, int n_surf, const mloam_point_t *d_corner_scan,
+                          int n_corner, const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+  if (!h || !pose_init7 || !pose_out7 || n_surf < 0 || n_corner < 0) return MLOAM_E_INVALID;
+  cudaSetDevice(h->c.device);
+  ScanRef S{reinterpret_cast<const float4 *>(d_surf_scan), n_surf, nullptr, reinterpret_cast<const float4 *>(d_corner_scan), n_corner,
+            nullptr};
+  return scan2map_run(&h->c, S, pose_init7, pose_out7, stats);
+}
+
+int mloam_scan2map(mloam_ctx_t *h, const mloam_point_t *h_surf_scan, int n_surf, const mloam_point_t *h_corner_scan, int n_corner,
+                   const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+  if (!h || !pose_init7 || !pose_out7 || n_surf < 0 || n_corner < 0) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  MLOAM_CUDA_OK(c, c->scan_pts[0].reserve(sizeof(float4) * (size_t)(n_corner + 1)));
+  MLOAM_CUDA_OK(c, c->scan_pts[1].reserve(sizeof(float4) * (size_t)(n_surf + 1)));
+  if (n_corner > 0)
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(c->scan_pts[0].p, h_corner_scan, sizeof(float4) * (size_t)n_corner, cudaMemcpyHostToDevice, c->stream));
+  if (n_surf > 0)
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(c->scan_pts[1].p, h_surf_scan, sizeof(float4) * (size_t)n_surf, cudaMemcpyHostToDevice, c->stream));
+  ScanRef S{c->scan_pts[1].as<float4>(), n_surf, nullptr, c->scan_pts[0].as<float4>(), n_corner, nullptr};
+  return scan2map_run(c, S, pose_init7, pose_out7, stats);
+}
+
+// ------------------------------------------------------------------------------------------ extractCloud
+int mloam_extract_features(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *h_scan_start, const int *h_scan_end,
+                           int n_scans, mloam_features_t *out) {
+  if (!h || !out || n < 0 || n_scans <= 0 || n_scans > 128 || (n > 0 && !h_cloud) || !h_scan_start || !h_scan_end)
+    return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  out->n_sharp = out->n_less_sharp = out->n_flat = out->n_less_flat = 0;
+  if (n == 0) return MLOAM_OK;
+  FrameBufs F;
+  int rc = frame_bufs(c, n, &F);
+  if (rc) return rc;
+  DevBuf &in = c->scratch[0];
+  MLOAM_CUDA_OK(c, in.reserve(sizeof(float4) * (size_t)n + 1024 + 8 * (size_t)n_scans));
+  float4 *d_cloud = in.as<float4>();
+  int *d_ss = reinterpret_cast<int *>(in.as<char>() + sizeof(float4) * (size_t)n + 256);
+  int *d_se = d_ss + n_scans;
+  cudaStream_t st = c->stream;
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_cloud, h_cloud, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ss, h_scan_start, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_se, h_scan_end, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
+  rc = extract_device(c, d_cloud, n, d_ss, d_se, n_scans, F.ex, nullptr, nullptr);
+  if (rc) return rc;
+  int *hc = reinterpret_cast<int *>(reinterpret_cast<char *>(c->pinned) + 3072);
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(hc, F.ex.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(hc + 4, c->d_extract_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(st));
+  if (hc[4] != 0)
+    return fail(c, MLOAM_E_INVALID, "extract: a ring exceeds the on-chip window (12288 points) or ScanInfo is out of range");
+  if (hc[0] > out->cap || hc[1] > out->cap || hc[2] > out->cap || hc[3] > out->cap)
+    return fail(c, MLOAM_E_INVALID, "extract: output capacity too small");
+  out->n_sharp = hc[0], out->n_less_sharp = hc[1], out->n_flat = hc[2], out->n_less_flat = hc[3];
+  if (out->corner_points_sharp && hc[0])
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(out->corner_points_sharp, F.ex.sharp, sizeof(float4) * hc[0], cudaMemcpyDeviceToHost, st));
+  if (out->corner_points_less_sharp && hc[1])
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(out->corner_points_less_sharp, F.ex.less_sharp, sizeof(float4) * hc[1], cudaMemcpyDeviceToHost, st));
+  if (out->surf_points_flat && hc[2])
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(out->surf_points_flat, F.ex.flat, sizeof(float4) * hc[2], cudaMemcpyDeviceToHost, st));
+  if (out->surf_points_less_flat && hc[3])
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(out->surf_points_less_flat, F.ex.less_flat, sizeof(float4) * hc[3], cudaMemcpyDeviceToHost, st));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(st));
+  return MLOAM_OK;
+}
+
+int mloam_extract_debug(mloam_ctx_t *h, float *h_curvature, int *h_label, int n) {
+  if (!h || n < 0) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  // layout of extract_device(): curvature at offset 0, label after it (both 4*(n+16) rounded to 256)
+  const size_t blk = (4 * ((size_t)n + 16) + 255) & ~(size_t)255;
+  if (c->scratch[4].cap < 2 * blk) return fail(c, MLOAM_E_STATE, "extract_debug: no extraction of this size has run");
+  const char *p = c->scratch[4].as<char>();
+  if (h_curvature) MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_curvature, p, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (h_label) MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_label, p + blk, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  return MLOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ voxel grid
+int mloam_voxel_downsample(mloam_ctx_t *h, const mloam_point_t *h_in, int n, float leaf, int intensity_last, mloam_point_t *h_out,
+                           int *n_out) {
+  if (!h || n < 0 || !n_out || (n > 0 && (!h_in || !h_out)) || !(leaf > 0.f)) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  *n_out = 0;
+  if (n == 0) return MLOAM_OK;
+  DevBuf &in = c->scratch[0], &outb = c->scratch[1];
+  MLOAM_CUDA_OK(c, in.reserve(sizeof(float4) * (size_t)n));
+  MLOAM_CUDA_OK(c, outb.reserve(sizeof(float4) * (size_t)n + 256));
+  cudaStream_t st = c->stream;
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(in.p, h_in, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  int *d_cnt = reinterpret_cast<int *>(outb.as<char>() + sizeof(float4) * (size_t)n);
+  int rc = voxel_downsample_device(c, in.as<float4>(), n, nullptr, leaf, intensity_last, outb.as<float4>(), d_cnt, 5);
+  if (rc) return rc;
+  int *hc = reinterpret_cast<int *>(reinterpret_cast<char *>(c->pinned) + 3072);
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(hc, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(st));
+  *n_out = hc[0];
+  if (hc[0] > 0) MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_out, outb.p, sizeof(float4) * (size_t)hc[0], cudaMemcpyDeviceToHost, st));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(st));
+  return MLOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ frame
+int mloam_frame_device(mloam_ctx_t *h, const mloam_point_t *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
+                       const mloam_point_t *d_surf_map, int n_surf_map, const mloam_point_t *d_corner_map, int n_corner_map,
+                       int rebuild_maps, const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+  if (!h || !pose_init7 || !pose_out7 || n <= 0 || !d_cloud || !d_scan_start || !d_scan_end) return MLOAM_E_INVALID;
+  cudaSetDevice(h->c.device);
+  return frame_run(&h->c, reinterpret_cast<const float4 *>(d_cloud), n, d_scan_start, d_scan_end, n_scans,
+                   reinterpret_cast<const float4 *>(d_surf_map), n_surf_map, reinterpret_cast<const float4 *>(d_corner_map),
+                   n_corner_map, rebuild_maps, pose_init7, pose_out7, stats);
+}
+
+int mloam_frame(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *h_scan_start, const int *h_scan_end, int n_scans,
+                const mloam_point_t *h_surf_map, int n_surf_map, const mloam_point_t *h_corner_map, int n_corner_map, int rebuild_maps,
+                const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+  if (!h || !pose_init7 || !pose_out7 || n <= 0 || !h_cloud || !h_scan_start || !h_scan_end || n_scans <= 0 || n_scans > 128)
+    return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  DevBuf &in = c->scratch[0];
+  MLOAM_CUDA_OK(c, in.reserve(sizeof(float4) * (size_t)n + 1024 + 8 * (size_t)n_scans));
+  float4 *d_cloud = in.as<float4>();
+  int *d_ss = reinterpret_cast<int *>(in.as<char>() + sizeof(float4) * (size_t)n + 256);
+  int *d_se = d_ss + n_scans;
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_cloud, h_cloud, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ss, h_scan_start, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_se, h_scan_end, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
+  const float4 *d_sm = nullptr, *d_cm = nullptr;
+  if (rebuild_maps) {
+    if (!h_surf_map || !h_corner_map || n_surf_map < 0 || n_corner_map < 0) return MLOAM_E_INVALID;
+    DevBuf &ms = c->scratch[1], &mc = c->scratch[2];
+    MLOAM_CUDA_OK(c, ms.reserve(sizeof(float4) * (size_t)(n_surf_map + 1)));
+    MLOAM_CUDA_OK(c, mc.reserve(sizeof(float4) * (size_t)(n_corner_map + 1)));
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(ms.p, h_surf_map, sizeof(float4) * (size_t)n_surf_map, cudaMemcpyHostToDevice, st));
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(mc.p, h_corner_map, sizeof(float4) * (size_t)n_corner_map, cudaMemcpyHostToDevice, st));
+    d_sm = ms.as<float4>(), d_cm = mc.as<float4>();
+  }
+  return frame_run(c, d_cloud, n, d_ss, d_se, n_scans, d_sm, n_surf_map, d_cm, n_corner_map, rebuild_maps, pose_init7, pose_out7, stats);
+}
+
+// ------------------------------------------------------------------------------------------ tracker (scan-to-scan)
+int mloam_track_cloud(mloam_ctx_t *h, const mloam_point_t *, int, const mloam_point_t *, int, const mloam_point_t *, int,
+                      const mloam_point_t *, int, const double *, double *, mloam_solve_stats_t *) {
+  if (!h) return MLOAM_E_INVALID;
+  return fail(&h->c, MLOAM_E_STATE, "track_cloud: scan-to-scan matcher not built in this revision");
+}
+
+}  // extern "C"

@@ -1,0 +1,499 @@
+// solve_kernels.cu — residual/Jacobian evaluation, J^T J / J^T r reduction and the device-resident
+// Levenberg-Marquardt state machine that replaces ceres::Solve for the single-pose problems of the path
+// (lidar_mapper_keyframe.cpp:537-596, lidar_tracker.cpp:70-120).
+//
+//   k_linearize : one thread per feature -> (r, 1x6 row) in double, Huber corrector, per-thread packed
+//                 upper-triangular J^T J (21) + J^T r (6) + cost + row counts, warp-shuffle tree ->
+//                 shared-memory cross-warp sum -> one partial per block (deterministic: no atomics).
+//   k_lm        : one warp sums the block partials in fixed order; lane 0 advances the LM state machine
+//                 (Jacobi scaling, LM diagonal, 6x6 Cholesky, step acceptance, radius update, tolerances,
+//                 degeneracy remap) entirely in device memory — the host only polls a done flag.
+#include "ctx.h"
+#include "factors.cuh"
+
+namespace mloam {
+
+constexpr int NE_H = 21, NE_G = 6;
+constexpr int NE_PACK = 30;  // 21 H upper | 6 g | cost | rows(set 0) | rows(set 1)
+constexpr int LIN_THREADS = 256;
+
+struct FeatSetDev {
+  const float4 *pts;
+  const unsigned char *valid;
+  const float *coeff;
+  int n;
+  int is_plane;
+  const int *d_n;
+};
+struct LinArgs {
+  FeatSetDev set[2];
+  int n_sets;
+  double sqrt_info, huber_a;
+  const double *pose;      // explicit pose (7 doubles) or null
+  const LMState *state;    // state->x (use_state 1) / state->xc (use_state 2)
+  int use_state;
+  int respect_done;
+};
+
+__global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__restrict__ partials) {
+  __shared__ double sm[LIN_THREADS / 32][NE_PACK];
+  const double *px = a.use_state == 1 ? a.state->x : (a.use_state == 2 ? a.state->xc : a.pose);
+  if (a.respect_done && a.state && a.state->done) return;  // Solve already terminated: nothing to evaluate
+  const PoseR P = make_poser(px);
+  double acc[NE_PACK];
+#pragma unroll
+  for (int k = 0; k < NE_PACK; k++) acc[k] = 0.0;
+  for (int s = 0; s < a.n_sets; s++) {
+    const FeatSetDev fs = a.set[s];
+    const int fn = fs.d_n ? min(fs.n, *fs.d_n) : fs.n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fn; i += gridDim.x * blockDim.x) {
+      if (!fs.valid[i]) continue;
+      const float4 pf = __ldg(fs.pts + i);
+      const D3 p{(double)pf.x, (double)pf.y, (double)pf.z};
+      const float *cf = fs.coeff + (size_t)i * 6;
+      double J[6];
+      double r;
+      if (fs.is_plane) {
+        r = plane_factor(P, p, D3{(double)cf[0], (double)cf[1], (double)cf[2]}, (double)cf[3], a.sqrt_info, J, true);
+      } else {
+        r = edge_factor(P, p, D3{(double)cf[0], (double)cf[1], (double)cf[2]}, D3{(double)cf[3], (double)cf[4], (double)cf[5]},
+                        a.sqrt_info, J, true);
+      }
+      double rho, rho1;
+      huber(a.huber_a, r * r, &rho, &rho1);
+      const double sc = sqrt(rho1);
+      r = sc * r;
+#pragma unroll
+      for (int k = 0; k < 6; k++) J[k] = sc * J[k];
+      int q = 0;
+#pragma unroll
+      for (int i0 = 0; i0 < 6; i0++)
+#pragma unroll
+        for (int j0 = i0; j0 < 6; j0++) acc[q++] += J[i0] * J[j0];
+#pragma unroll
+      for (int k = 0; k < 6; k++) acc[NE_H + k] += J[k] * r;
+      acc[NE_H + NE_G] += 0.5 * rho;
+      if (s == 0) acc[NE_H + NE_G + 1] += 1.0;
+      else acc[NE_H + NE_G + 2] += 1.0;
+    }
+  }
+  // warp tree
+#pragma unroll
+  for (int k = 0; k < NE_PACK; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(MLOAM_FULL_MASK, v, o);
+    acc[k] = v;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NE_PACK; k++) sm[wid][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NE_PACK) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < LIN_THREADS / 32; w++) v += sm[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * NE_PACK + threadIdx.x] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------- small dense (device)
+__device__ void eig_sym6(const double *Ain, double *w, double *V) {
+  const int N = 6;
+  double a[36], v[36];
+  for (int i = 0; i < 36; i++) a[i] = Ain[i], v[i] = (i % 7 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < N; i++) {
+      diag += fabs(a[i * N + i]);
+      for (int j = i + 1; j < N; j++) off += fabs(a[i * N + j]);
+    }
+    if (off <= 1e-22 * diag || off == 0.0) break;
+    for (int p = 0; p < N - 1; p++)
+      for (int q = p + 1; q < N; q++) {
+        const double apq = a[p * N + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q * N + q] - a[p * N + p]) / (2.0 * apq);
+        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+        if (theta < 0.0) t = -t;
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        a[p * N + p] -= t * apq;
+        a[q * N + q] += t * apq;
+        a[p * N + q] = a[q * N + p] = 0.0;
+        for (int r = 0; r < N; r++) {
+          if (r == p || r == q) continue;
+          const double arp = a[r * N + p], arq = a[r * N + q];
+          a[r * N + p] = a[p * N + r] = c * arp - s * arq;
+          a[r * N + q] = a[q * N + r] = s * arp + c * arq;
+        }
+        for (int k = 0; k < N; k++) {
+          const double vkp = v[k * N + p], vkq = v[k * N + q];
+          v[k * N + p] = c * vkp - s * vkq;
+          v[k * N + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  int idx[6] = {0, 1, 2, 3, 4, 5};
+  for (int i = 1; i < N; i++) {  // stable insertion sort, ascending
+    int k = idx[i], j = i - 1;
+    while (j >= 0 && a[idx[j] * N + idx[j]] > a[k * N + k]) idx[j + 1] = idx[j], j--;
+    idx[j + 1] = k;
+  }
+  for (int j = 0; j < N; j++) {
+    w[j] = a[idx[j] * N + idx[j]];
+    for (int k = 0; k < N; k++) V[k * N + j] = v[k * N + idx[j]];
+  }
+}
+
+__device__ bool chol6(double *A) {
+  const int N = 6;
+  for (int j = 0; j < N; j++) {
+    double d = A[j * N + j];
+    for (int k = 0; k < j; k++) d -= A[j * N + k] * A[j * N + k];
+    if (!(d > 0.0)) return false;
+    d = sqrt(d);
+    A[j * N + j] = d;
+    for (int i = j + 1; i < N; i++) {
+      double s = A[i * N + j];
+      for (int k = 0; k < j; k++) s -= A[i * N + k] * A[j * N + k];
+      A[i * N + j] = s / d;
+    }
+  }
+  return true;
+}
+__device__ void chol6_solve(const double *L, const double *b, double *x) {
+  const int N = 6;
+  double y[6];
+  for (int i = 0; i < N; i++) {
+    double s = b[i];
+    for (int k = 0; k < i; k++) s -= L[i * N + k] * y[k];
+    y[i] = s / L[i * N + i];
+  }
+  for (int i = N - 1; i >= 0; i--) {
+    double s = y[i];
+    for (int k = i + 1; k < N; k++) s -= L[k * N + i] * x[k];
+    x[i] = s / L[i * N + i];
+  }
+}
+
+// Ceres defaults the reference relies on (never overridden in-tree)
+__device__ constexpr double kMinDiag = 1e-6, kMaxDiag = 1e32, kMaxRadius = 1e16;
+__device__ constexpr double kFuncTol = 1e-6, kParamTol = 1e-8, kGradTol = 1e-10, kMinRelDecrease = 1e-3;
+
+__device__ double gradient_max_norm(const LMState *st) {
+  double neg[6], xp[7];
+  for (int j = 0; j < 6; j++) neg[j] = -st->g[j];
+  pose_plus(st->x, neg, st->V_update, xp);
+  double m = 0;
+  for (int k = 0; k < 7; k++) m = fmax(m, fabs(st->x[k] - xp[k]));
+  return m;
+}
+
+// LevenbergMarquardtStrategy::ComputeStep + the invalid-step loop of TrustRegionMinimizer.
+__device__ void lm_compute_step(LMState *st) {
+  while (true) {
+    if (st->iteration >= st->max_inner) {
+      st->done = 1, st->termination = 0;
+      return;
+    }
+    double Hs[36], gs[6], A[36], step[6];
+    for (int a = 0; a < 6; a++) {
+      gs[a] = st->scale[a] * st->g[a];
+      for (int b = 0; b < 6; b++) Hs[a * 6 + b] = st->scale[a] * st->H[a * 6 + b] * st->scale[b];
+    }
+    if (!st->reuse_diagonal)
+      for (int j = 0; j < 6; j++) st->diag[j] = fmin(fmax(Hs[j * 6 + j], kMinDiag), kMaxDiag);
+    for (int i = 0; i < 36; i++) A[i] = Hs[i];
+    for (int j = 0; j < 6; j++) {
+      const double l = sqrt(st->diag[j] / st->radius);
+      A[j * 6 + j] += l * l;
+    }
+    bool ok = chol6(A);
+    if (ok) {
+      chol6_solve(A, gs, step);
+      for (int j = 0; j < 6; j++) {
+        step[j] = -step[j];
+        if (!isfinite(step[j])) ok = false;
+      }
+    }
+    st->reuse_diagonal = 1;
+    st->iteration++;
+    st->total_iterations++;
+    double mcc = 0;
+    if (ok) {
+      double sg = 0, sHs = 0;
+      for (int a = 0; a < 6; a++) {
+        sg += step[a] * gs[a];
+        double t = 0;
+        for (int b = 0; b < 6; b++) t += Hs[a * 6 + b] * step[b];
+        sHs += step[a] * t;
+      }
+      mcc = -(sg + 0.5 * sHs);
+      if (mcc < 0) ok = false;
+    }
+    if (!ok) {
+      if (++st->num_invalid >= 5) {
+        st->done = 1, st->termination = 4;
+        return;
+      }
+      st->radius *= 0.5;
+      st->reuse_diagonal = 1;
+      continue;
+    }
+    st->num_invalid = 0;
+    double delta[6];
+    for (int j = 0; j < 6; j++) delta[j] = step[j] * st->scale[j];
+    pose_plus(st->x, delta, st->V_update, st->xc);
+    st->model_cost_change = mcc;
+    return;
+  }
+}
+
+__device__ void unpack_ne(const double *ne, double *H, double *g) {
+  int q = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++) {
+      H[i * 6 + j] = ne[q];
+      H[j * 6 + i] = ne[q];
+      q++;
+    }
+  for (int k = 0; k < 6; k++) g[k] = ne[NE_H + k];
+}
+
+// mode 1: begin a Solve with the evaluation at x.  mode 2: digest the evaluation at xc.
+__global__ void k_lm(const double *__restrict__ partials, int n_blocks, LMState *st, int mode, double eig_thre,
+                     double *__restrict__ out_ne) {
+  __shared__ double ne[NE_PACK];
+  if (threadIdx.x < NE_PACK) {
+    double v = 0.0;
+    for (int b = 0; b < n_blocks; b++) v += partials[(size_t)b * NE_PACK + threadIdx.x];
+    ne[threadIdx.x] = v;
+    if (out_ne) out_ne[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0 || mode == 0) return;
+  double H[36], g[6];
+  unpack_ne(ne, H, g);
+  const double cost = ne[NE_H + NE_G];
+  if (mode == 1) {
+    for (int i = 0; i < 36; i++) st->H[i] = H[i], st->H0[i] = H[i];
+    for (int i = 0; i < 6; i++) st->g[i] = g[i];
+    st->cost = cost;
+    st->initial_cost = cost;
+    st->n_valid[0] = (int)ne[NE_H + NE_G + 1];
+    st->n_valid[1] = (int)ne[NE_H + NE_G + 2];
+    st->rows = st->n_valid[0] + st->n_valid[1];
+    // PoseLocalParameterization::setParameter + evalDegenracy (lidar_mapper_keyframe.cpp:1172-1204)
+    for (int i = 0; i < 36; i++) st->V_update[i] = (i % 7 == 0) ? 1.0 : 0.0;
+    st->is_degenerate = 0;
+    for (int i = 0; i < 6; i++) st->eig[i] = 0.0;
+    if (st->rows > 0 && eig_thre > 0.0) {
+      double w[6], Vf[36], Vp[36];
+      eig_sym6(H, w, Vf);
+      for (int i = 0; i < 36; i++) Vp[i] = Vf[i];
+      for (int j = 0; j < 6; j++) {
+        if (w[j] < eig_thre) {
+          for (int k = 0; k < 6; k++) Vp[k * 6 + j] = 0.0;
+          st->is_degenerate = 1;
+        } else {
+          break;
+        }
+      }
+      for (int i = 0; i < 6; i++) st->eig[i] = w[i];
+      if (st->is_degenerate)
+        for (int i = 0; i < 6; i++)
+          for (int j = 0; j < 6; j++) {
+            double s = 0;
+            for (int k = 0; k < 6; k++) s += Vf[i * 6 + k] * Vp[j * 6 + k];
+            st->V_update[i * 6 + j] = s;
+          }
+    }
+    double xn = 0;
+    for (int k = 0; k < 7; k++) xn += st->x[k] * st->x[k];
+    st->x_norm = sqrt(xn);
+    for (int j = 0; j < 6; j++) st->scale[j] = 1.0 / (1.0 + sqrt(H[j * 6 + j]));
+    st->radius = 1e4, st->decrease_factor = 2.0, st->reuse_diagonal = 0;
+    st->iteration = 0, st->num_invalid = 0, st->done = 0, st->termination = 0;
+    for (int k = 0; k < 7; k++) st->xc[k] = st->x[k];
+    if (gradient_max_norm(st) <= kGradTol) {
+      st->done = 1, st->termination = 3;
+      return;
+    }
+    lm_compute_step(st);
+    return;
+  }
+  // mode 2
+  if (st->done) return;
+  double sn = 0;
+  for (int k = 0; k < 7; k++) sn += (st->x[k] - st->xc[k]) * (st->x[k] - st->xc[k]);
+  sn = sqrt(sn);
+  if (sn <= kParamTol * (st->x_norm + kParamTol)) {
+    st->done = 1, st->termination = 2;
+    return;
+  }
+  const double cost_change = st->cost - cost;
+  if (fabs(cost_change) <= kFuncTol * st->cost) {
+    st->done = 1, st->termination = 1;
+    return;
+  }
+  const double rel = cost_change / st->model_cost_change;
+  if (rel > kMinRelDecrease) {
+    const double t = 2.0 * rel - 1.0;
+    st->radius = st->radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
+    st->radius = fmin(kMaxRadius, st->radius);
+    st->decrease_factor = 2.0;
+    st->reuse_diagonal = 0;
+    double xn = 0;
+    for (int k = 0; k < 7; k++) st->x[k] = st->xc[k], xn += st->xc[k] * st->xc[k];
+    st->x_norm = sqrt(xn);
+    for (int i = 0; i < 36; i++) st->H[i] = H[i];
+    for (int i = 0; i < 6; i++) st->g[i] = g[i];
+    st->cost = cost;
+    if (gradient_max_norm(st) <= kGradTol) {
+      st->done = 1, st->termination = 3;
+      return;
+    }
+  } else {
+    st->radius = st->radius / st->decrease_factor;
+    st->decrease_factor *= 2.0;
+    st->reuse_diagonal = 1;
+  }
+  lm_compute_step(st);
+}
+
+__global__ void k_lm_init(LMState *st, const double *pose7, int max_inner) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int k = 0; k < 7; k++) st->x[k] = pose7[k], st->xc[k] = pose7[k];
+    st->max_inner = max_inner;
+    st->done = 0, st->termination = 0, st->total_iterations = 0, st->iteration = 0;
+    st->is_degenerate = 0, st->rows = 0, st->n_valid[0] = st->n_valid[1] = 0;
+    st->cost = 0, st->initial_cost = 0;
+    for (int i = 0; i < 36; i++) st->V_update[i] = (i % 7 == 0) ? 1.0 : 0.0, st->H0[i] = 0, st->H[i] = 0;
+    for (int i = 0; i < 6; i++) st->eig[i] = 0, st->g[i] = 0;
+  }
+}
+
+int lm_init_state(Ctx *c, const double *pose7_host, int max_inner, double eig_thre) {
+  (void)eig_thre;
+  MLOAM_CUDA_OK(c, c->lm_state.reserve(sizeof(LMState) + 64));
+  // stage the pose through pinned memory so the copy is truly asynchronous
+  double *stage = reinterpret_cast<double *>(c->pinned);
+  for (int k = 0; k < 7; k++) stage[k] = pose7_host[k];
+  double *d_stage = c->scratch[7].as<double>();
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_stage, stage, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k_lm_init<<<1, 32, 0, c->stream>>>(c->lm_state.as<LMState>(), d_stage, max_inner);
+  c->launches++;
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  return MLOAM_OK;
+}
+
+int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, double huber_a, const double *d_pose7,
+                     int use_state, int lm_mode, double *d_out30) {
+  LinArgs a;
+  int n_total = 0;
+  for (int s = 0; s < 2; s++) {
+    if (s < n_sets) {
+      a.set[s].pts = sets[s].pts, a.set[s].valid = sets[s].valid, a.set[s].coeff = sets[s].coeff;
+      a.set[s].n = sets[s].n, a.set[s].is_plane = sets[s].is_plane, a.set[s].d_n = sets[s].d_n;
+      n_total = sets[s].n > n_total ? sets[s].n : n_total;
+    } else {
+      a.set[s].pts = nullptr, a.set[s].valid = nullptr, a.set[s].coeff = nullptr, a.set[s].n = 0, a.set[s].is_plane = 0, a.set[s].d_n = nullptr;
+    }
+  }
+  a.n_sets = n_sets, a.sqrt_info = sqrt_info, a.huber_a = huber_a, a.pose = d_pose7;
+  a.state = c->lm_state.as<LMState>();
+  a.use_state = use_state;
+  a.respect_done = (lm_mode == 2) ? 1 : 0;
+  int nb = (n_total + LIN_THREADS - 1) / LIN_THREADS;
+  if (nb < 1) nb = 1;
+  const int max_nb = 2 * c->sm_count;
+  if (nb > max_nb) nb = max_nb;
+  MLOAM_CUDA_OK(c, c->partials.reserve(sizeof(double) * NE_PACK * (size_t)(max_nb + 2)));
+  {
+    ProfScope ps(c, "linearize");
+    k_linearize<<<nb, LIN_THREADS, 0, c->stream>>>(a, c->partials.as<double>());
+    c->launches++;
+  }
+  if (c->nccl_comm && lm_mode != 0) {
+    // multi-GPU: rank-local sum -> NCCL all-reduce of the 30 packed doubles -> identical LM step on every rank
+    double *ne = c->partials.as<double>() + (size_t)NE_PACK * max_nb;
+    {
+      ProfScope ps(c, "lm");
+      k_lm<<<1, 32, 0, c->stream>>>(c->partials.as<double>(), nb, c->lm_state.as<LMState>(), 0, 0.0, ne);
+      c->launches++;
+    }
+    int rc = comm_allreduce_doubles(c, ne, NE_PACK);
+    if (rc) return rc;
+    ProfScope ps(c, "lm");
+    k_lm<<<1, 32, 0, c->stream>>>(ne, 1, c->lm_state.as<LMState>(), lm_mode, c->params.eig_thre, d_out30);
+    c->launches++;
+  } else {
+    ProfScope ps(c, "lm");
+    k_lm<<<1, 32, 0, c->stream>>>(c->partials.as<double>(), nb, c->lm_state.as<LMState>(), lm_mode, c->params.eig_thre,
+                                  d_out30);
+    c->launches++;
+  }
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  return MLOAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------- batched Evaluate
+__global__ void k_factor_evaluate(int kind, int n, const double *__restrict__ points, const double *__restrict__ coeffs,
+                                  const double *__restrict__ sqrt_info, const double *__restrict__ params,
+                                  double *__restrict__ res, double *__restrict__ jac) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const D3 p{points[i * 3], points[i * 3 + 1], points[i * 3 + 2]};
+  const double *cf = coeffs + (size_t)i * 6;
+  const double s = sqrt_info ? sqrt_info[i] : 1.0;
+  const D3 c0{cf[0], cf[1], cf[2]}, c1{cf[3], cf[4], cf[5]};
+  if (kind <= 1) {
+    const PoseR P = make_poser(params);
+    double J[6];
+    const double r = kind == 0 ? plane_factor(P, p, c0, cf[3], s, J, jac != nullptr) : edge_factor(P, p, c0, c1, s, J, jac != nullptr);
+    res[i] = r;
+    if (jac) {
+      for (int k = 0; k < 6; k++) jac[(size_t)i * 7 + k] = J[k];
+      jac[(size_t)i * 7 + 6] = 0.0;
+    }
+  } else if (kind == 2) {
+    const PoseR P = make_poser(params);
+    double r[3], J[18];
+    edge_vector_factor(P, p, c0, c1, r, J, jac != nullptr);
+    for (int k = 0; k < 3; k++) res[(size_t)i * 3 + k] = r[k];
+    if (jac)
+      for (int a = 0; a < 3; a++) {
+        for (int k = 0; k < 6; k++) jac[(size_t)i * 21 + a * 7 + k] = J[a * 6 + k];
+        jac[(size_t)i * 21 + a * 7 + 6] = 0.0;
+      }
+  } else {
+    const Chain c = make_chain(params, params + 7, params + 14);
+    double Jp[6], Ji[6], Je[6];
+    const bool wj = jac != nullptr;
+    const double r = kind == 3 ? odom_plane_factor(c, p, c0, cf[3], s, wj ? Jp : nullptr, wj ? Ji : nullptr, wj ? Je : nullptr)
+                               : odom_edge_factor(c, p, c0, c1, s, wj ? Jp : nullptr, wj ? Ji : nullptr, wj ? Je : nullptr);
+    res[i] = r;
+    if (jac) {
+      double *o = jac + (size_t)i * 21;
+      for (int k = 0; k < 6; k++) o[k] = Jp[k], o[7 + k] = Ji[k], o[14 + k] = Je[k];
+      o[6] = o[13] = o[20] = 0.0;
+    }
+  }
+}
+
+int factor_evaluate_device(Ctx *c, int kind, int n, const double *d_points, const double *d_coeffs, const double *d_sqrt_info,
+                           const double *d_params, double *d_res, double *d_jac) {
+  if (kind < 0 || kind > 4) {
+    c->err = "factor_evaluate: kind must be 0..4";
+    return MLOAM_E_INVALID;
+  }
+  if (n <= 0) return MLOAM_OK;
+  k_factor_evaluate<<<(n + 127) / 128, 128, 0, c->stream>>>(kind, n, d_points, d_coeffs, d_sqrt_info, d_params, d_res, d_jac);
+  c->launches++;
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  return MLOAM_OK;
+}
+
+}  // namespace mloam

@@ -12,6 +12,12 @@ inline double map_sqrt_info(double cov_trace) {
   return s >= 3.0 ? 1.0 : s / 3.0;
 }
 
+// Eigen 3.3 MatrixBase::normalized(): a zero vector is returned unchanged
+inline V3 normalized(const V3 &v) {
+  double n = norm(v);
+  return n > 0.0 ? V3{v.x / n, v.y / n, v.z / n} : v;
+}
+
 inline void set_row(double *J, double s, const V3 &a, const V3 &b) {
   J[0] = s * a.x, J[1] = s * a.y, J[2] = s * a.z, J[3] = s * b.x, J[4] = s * b.y, J[5] = s * b.z, J[6] = 0.0;
 }
@@ -47,7 +53,7 @@ inline void edge_factor(const V3 &p, const double *coeff, double sinfo, const do
   r[0] = sinfo * nun / den;
   if (J) {
     M3 R = qmat(q);
-    V3 eta = (1.0 / den) * V3{nu.x / nun, nu.y / nun, nu.z / nun};  // 1/|de| * nu.normalized()^T
+    V3 eta = (1.0 / den) * normalized(nu);  // 1/|de| * nu.normalized()^T
     M3 S = skew(de);
     V3 eS = vecmat(eta, S);
     V3 jt = -eS;
@@ -132,7 +138,7 @@ inline void odom_edge_factor(const V3 &p, const double *coeff, double sinfo, con
   if (!Jp && !Ji && !Je) return;
   M3 Rp = qmat(Qp), Ri = qmat(Qi), Re = qmat(Qe);
   M3 RpT = transpose(Rp);
-  V3 eta = (1.0 / den) * V3{nu.x / nun, nu.y / nun, nu.z / nun};
+  V3 eta = (1.0 / den) * normalized(nu);
   V3 ba = lp - lpa, bb = lp - lpb;
   V3 eS = vecmat(eta, skew(ba - bb));  // eta [ba-bb]x
   V3 eSRpT = vecmat(eS, RpT);

@@ -1,0 +1,43 @@
+"""CPU tests: the C-ABI library builds for sm_100a, loads, and exports every symbol include/mloam_b200.h declares;
+without a device, context creation fails loudly (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+
+def test_library_loads_and_exports_header_symbols(mloam):
+    mloam.build()
+    lib = mloam.lib()
+    hdr = open(os.path.join(mloam.ROOT, "include", "mloam_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mloam_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/mloam_b200.h but not exported"
+    assert set(declared) == set(mloam.ABI_SYMBOLS)
+    assert b"sm_100a" in lib.mloam_version()
+
+
+def test_struct_layouts_match_defaults(mloam):
+    p = mloam.default_params()
+    assert p.n_neigh == 5 and p.max_outer == 2 and p.max_inner == 30
+    assert abs(p.min_match_sq_dis - 1.0) < 1e-7 and abs(p.min_plane_dis - 0.2) < 1e-7
+    assert abs(p.huber_a - 0.1) < 1e-15 and p.eig_thre == 100.0 and abs(p.cov_trace - 0.0075) < 1e-15
+    assert abs(p.corner_leaf - 0.2) < 1e-7 and abs(p.surf_leaf - 0.4) < 1e-7
+
+
+def test_no_device_fails_loudly(mloam):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(mloam.MloamError):
+        mloam.Context(0)
+
+
+def test_only_sm100a_sass_is_embedded(mloam):
+    import subprocess
+
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", mloam.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs

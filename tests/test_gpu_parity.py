@@ -1,0 +1,351 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs.  Integer / index / gate results are compared exactly; poses within the north-star tolerance
+(1e-4 m / 1e-4 rad)."""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_T = 1e-4  # metres   (BASELINE.json north_star)
+POSE_TOL_R = 1e-4  # radians
+
+
+@pytest.fixture(scope="module")
+def c1():
+    """Config C1: 16-ring x 1024 sweep, 50k-point submap."""
+    scene = syn.make_scene()
+    traj = syn.trajectory(6)
+    surf_map, corner_map = syn.make_submap(scene, 50000)
+    cloud, ss, se = syn.make_sweep(scene, traj[4], 16, 1024, seed=4)
+    f = orc.extract_cloud(cloud, ss, se)
+    cs, _ = orc.voxel_grid(f["corner_points_less_sharp"], 0.2, True)
+    sf, _ = orc.voxel_grid(f["surf_points_less_flat"], 0.4, True)
+    init = syn.perturb_pose(traj[4], np.random.Generator(np.random.PCG64(11)))
+    return dict(scene=scene, truth=traj[4], surf_map=surf_map, corner_map=corner_map, cloud=cloud, ss=ss, se=se, feat=f,
+                corner_scan=cs, surf_scan=sf, init=init)
+
+
+def _rand_cloud(rng, n, lo=-20, hi=20):
+    return np.concatenate([rng.uniform(lo, hi, (n, 3)), np.zeros((n, 1))], 1).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("k", [1, 5, 10])
+@pytest.mark.parametrize("cell", [0.25, 0.5, 1.0])
+def test_knn_index_exact(ctx, k, cell):
+    rng = np.random.default_rng(100 + k)
+    m = _rand_cloud(rng, 200000, -10, 10)  # dense: most queries have k neighbours within 1 m
+    q = _rand_cloud(rng, 4000, -11, 11)    # some outside the map
+    ctx.map_build(2, m, cell)
+    idx, sqd = ctx.knn(2, q, k, 1.0)
+    ridx, rsqd = orc.knn(m, q, k)
+    inside = rsqd < 1.0
+    assert np.array_equal(idx[inside], ridx[inside])
+    assert np.array_equal(sqd[inside], rsqd[inside])  # bit-exact float distances
+    assert np.all(idx[~inside] == -1) and np.all(np.isinf(sqd[~inside]))
+    # sortedness / recomputation properties
+    ok = idx >= 0
+    d = ((m[np.where(ok, idx, 0)][:, :, :3] - q[:, None, :3]) ** 2)
+    d2 = (d[..., 0] + d[..., 1]) + d[..., 2]
+    assert np.array_equal(d2[ok], sqd[ok])
+    assert np.all(np.diff(np.where(ok, sqd, np.inf), axis=1) >= 0)
+
+
+def test_knn_with_pose_and_large_radius(ctx):
+    rng = np.random.default_rng(7)
+    m = _rand_cloud(rng, 30000, -30, 30)
+    q = _rand_cloud(rng, 1000, -5, 5)
+    pose = syn.pose7([1, -2, 0.5], syn.quat_from_rpy(0.1, 0.2, 0.3))
+    ctx.map_build(3, m, 1.0)
+    idx, sqd = ctx.knn(3, q, 1, 25.0, pose7=pose)  # K=1, DISTANCE_SQ_THRESHOLD radius (feature_extract.hpp:155-158)
+    qt = orc.associate(q, pose)
+    ridx, rsqd = orc.knn(m, qt, 1)
+    inside = rsqd < 25.0
+    assert inside.mean() > 0.9
+    assert np.array_equal(idx[inside], ridx[inside]) and np.array_equal(sqd[inside], rsqd[inside])
+
+
+def test_knn_tiny_and_empty_maps(ctx):
+    m = np.array([[0, 0, 0, 0], [0.5, 0, 0, 0], [0, 0.5, 0, 0]], np.float32)
+    ctx.map_build(2, m, 0.5)
+    idx, sqd = ctx.knn(2, np.array([[0.1, 0, 0, 0]], np.float32), 5, 1.0)
+    assert list(idx[0]) == [0, 1, 2, -1, -1] and np.isinf(sqd[0, 3])
+    ctx.map_build(2, np.zeros((0, 4), np.float32), 0.5)
+    idx, _ = ctx.knn(2, np.array([[0.1, 0, 0, 0]], np.float32), 5, 1.0)
+    assert np.all(idx == -1)
+    idx, _ = ctx.knn(2, np.zeros((0, 4), np.float32), 5, 1.0)
+    assert idx.shape == (0, 5)
+
+
+# ------------------------------------------------------------------------------------------------ matching
+@pytest.mark.parametrize("kind", ["c", "s"])
+def test_match_from_map_exact(ctx, c1, kind):
+    slot = 0 if kind == "c" else 1
+    map_ = c1["corner_map"] if kind == "c" else c1["surf_map"]
+    data = c1["corner_scan"] if kind == "c" else c1["surf_scan"]
+    ctx.map_build(slot, map_, 0.5)
+    valid, coeffs, nn = ctx.match_from_map(slot, kind, data, c1["init"])
+    rvalid, rcoeffs, rnn = orc.match_from_map(kind, map_, data, c1["init"])
+    assert rvalid.sum() > 100
+    assert np.array_equal(valid, rvalid)                      # identical accept/reject at every gate
+    assert np.array_equal(nn[valid], rnn[rvalid])             # identical neighbour sets, same order
+    if kind == "s":
+        assert np.array_equal(coeffs[valid], rcoeffs[rvalid])  # bit-exact plane (n, d)
+    else:
+        a, b = coeffs[valid], rcoeffs[rvalid]
+        same = np.all(a == b, axis=1)
+        swapped = np.all(a[:, [3, 4, 5, 0, 1, 2]] == b, axis=1)  # eigenvector sign is free: [X1;X2] may swap
+        assert np.all(same | swapped)
+        assert same.mean() > 0.99
+
+
+def test_match_fov_gate_and_neigh10(ctx, c1, mloam):
+    ctx.map_build(1, c1["surf_map"], 0.5)
+    ctx.set_params(check_fov=1, n_neigh=10)
+    try:
+        valid, coeffs, nn = ctx.match_from_map(1, "s", c1["surf_scan"], c1["init"])
+        rvalid, rcoeffs, rnn = orc.match_from_map("s", c1["surf_map"], c1["surf_scan"], c1["init"], n_neigh=10, check_fov=True)
+        assert 10 < rvalid.sum() < rvalid.shape[0]
+        assert np.array_equal(valid, rvalid) and np.array_equal(nn[valid], rnn[rvalid])
+        assert np.array_equal(coeffs[valid], rcoeffs[rvalid])
+    finally:
+        ctx.set_params(check_fov=0, n_neigh=5)
+
+
+# ------------------------------------------------------------------------------------------------ factors
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4])
+def test_factor_evaluate_matches_oracle(ctx, kind):
+    rng = np.random.default_rng(40 + kind)
+    n = 257
+    pts = rng.normal(size=(n, 3)) * 5
+    if kind in (0, 3):
+        nrm = rng.normal(size=(n, 3))
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        coeffs = np.concatenate([nrm, rng.normal(size=(n, 1)), np.zeros((n, 2))], 1)
+    else:
+        a = rng.normal(size=(n, 3)) * 5
+        coeffs = np.concatenate([a, a + rng.normal(size=(n, 3))], 1)
+    npar = 3 if kind >= 3 else 1
+    x = np.concatenate([syn.pose7(rng.normal(size=3) * 2, rng.normal(size=4)) for _ in range(npar)])
+    sinfo = rng.uniform(0.3, 1.0, n) if kind != 2 else None
+    res, jac = ctx.factor_evaluate(kind, pts, coeffs, x, sqrt_info=sinfo)
+    rows = 3 if kind == 2 else 1
+    cols = 21 if kind >= 3 else 7
+    for i in range(0, n, 7):
+        r, J = orc.factor_eval(kind, pts[i], coeffs[i], 1.0 if sinfo is None else sinfo[i], x)
+        assert np.allclose(res[i], r[:rows], rtol=1e-12, atol=1e-12)
+        assert np.allclose(jac[i].reshape(-1), J[: rows * cols], rtol=1e-11, atol=1e-11)
+    # null-tolerant on jacobians, like Evaluate(param, residuals, nullptr)
+    res2, _ = ctx.factor_evaluate(kind, pts, coeffs, x, sqrt_info=sinfo, want_jac=False)
+    assert np.array_equal(res, res2)
+
+
+def test_factor_check_convention_fd(ctx):
+    """The reference's check(): forward differences, eps 1e-6, q * deltaQ (lidar_map_factor.hpp:72-120), on the GPU path."""
+    rng = np.random.default_rng(5)
+    x = syn.pose7([0.3, -1, 2], rng.normal(size=4))
+    p = np.array([[1.0, 2.0, -0.5]])
+    w = np.array([0.36, 0.48, 0.8])
+    coeff = np.array([[*w, 0.7, 0, 0]])
+    r, J = ctx.factor_evaluate(0, p, coeff, x)
+    for k in range(6):
+        d = np.zeros(6)
+        d[k] = 1e-6
+        rp, _ = ctx.factor_evaluate(0, p, coeff, ctx.pose_plus(x, d), want_jac=False)
+        assert abs((rp[0, 0] - r[0, 0]) / 1e-6 - J[0, 0, k]) < 1e-4
+    assert J[0, 0, 6] == 0.0
+
+
+def test_pose_plus_matches_oracle(ctx):
+    rng = np.random.default_rng(6)
+    for _ in range(10):
+        x = syn.pose7(rng.normal(size=3), rng.normal(size=4))
+        d = rng.normal(size=6) * 0.1
+        V = rng.normal(size=(6, 6))
+        assert np.allclose(ctx.pose_plus(x, d), orc.plus(x, d), rtol=0, atol=1e-15)
+        assert np.allclose(ctx.pose_plus(x, d, V), orc.plus(x, d, V), rtol=0, atol=1e-15)
+    x = syn.pose7([1, 2, 3], [0, 0, 0, 1])
+    assert np.array_equal(ctx.pose_plus(x, np.zeros(6)), x)  # Plus(x, 0) = x
+
+
+def test_normal_equations_match_oracle(ctx, c1):
+    # features from the oracle's association so both sides reduce the same rows
+    vs, cfs, _ = orc.match_from_map("s", c1["surf_map"], c1["surf_scan"], c1["init"])
+    vc, cfc, _ = orc.match_from_map("c", c1["corner_map"], c1["corner_scan"], c1["init"])
+    pts = np.concatenate([c1["surf_scan"][vs][:, :3], c1["corner_scan"][vc][:, :3]]).astype(np.float64)
+    coeffs = np.concatenate([cfs[vs], cfc[vc]])
+    types = np.array([ord("s")] * int(vs.sum()) + [ord("c")] * int(vc.sum()), np.uint8)
+    for huber_a in (0.1, 1.0):
+        H, g, cost = ctx.normal_equations(types, pts, coeffs, 1.0, huber_a, c1["init"])
+        rH, rg, rcost = orc.normal_eq(types, pts, coeffs, 1.0, huber_a, c1["init"])
+        assert np.allclose(H, rH, rtol=1e-11, atol=1e-9)
+        assert np.allclose(g, rg, rtol=1e-10, atol=1e-10)
+        assert abs(cost - rcost) <= 1e-12 * max(1.0, abs(rcost))
+        assert np.array_equal(H, H.T)
+    # linearity: duplicating the rows doubles H, g, cost
+    H2, g2, cost2 = ctx.normal_equations(np.tile(types, 2), np.tile(pts, (2, 1)), np.tile(coeffs, (2, 1)), 1.0, 0.1, c1["init"])
+    H1, g1, cost1 = ctx.normal_equations(types, pts, coeffs, 1.0, 0.1, c1["init"])
+    assert np.allclose(H2, 2 * H1, rtol=1e-12) and np.allclose(g2, 2 * g1, rtol=1e-11, atol=1e-12) and abs(cost2 - 2 * cost1) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ voxel grid
+@pytest.mark.parametrize("leaf,last", [(0.2, False), (0.4, True), (1.0, False)])
+def test_voxel_downsample_bit_exact(ctx, c1, leaf, last):
+    pts = c1["feat"]["surf_points_less_flat"]
+    out = ctx.voxel_downsample(pts, leaf, last)
+    ref, ok = orc.voxel_grid(pts, leaf, last)
+    assert ok and out.shape == ref.shape
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    # idempotence-like property: filtering the centroids again never increases the count
+    out2 = ctx.voxel_downsample(out, leaf, last)
+    assert out2.shape[0] <= out.shape[0]
+
+
+def test_voxel_downsample_edge_cases(ctx):
+    assert ctx.voxel_downsample(np.zeros((0, 4), np.float32), 0.2).shape[0] == 0
+    one = np.array([[1.5, -2.5, 3.5, 9.0]], np.float32)
+    assert np.array_equal(ctx.voxel_downsample(one, 0.2), one)
+    pts = np.array([[0.1, 0.1, 0.1, 1], [0.3, 0.5, 0.7, 3], [np.nan, 0, 0, 0], [1.5, 0.2, 0.2, 5], [0.2, 1.6, 0.1, 7]], np.float32)
+    out = ctx.voxel_downsample(pts, 1.0)
+    ref, _ = orc.voxel_grid(pts, 1.0)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)) and out.shape[0] == 3
+    # index space overflow: "Leaf size is too small" -> input returned unchanged (voxel_grid_covariance_mloam_impl.hpp:92-101)
+    big = np.array([[0, 0, 0, 1], [1e6, 1e6, 1e6, 2], [5, 5, 5, 3]], np.float32)
+    assert np.array_equal(ctx.voxel_downsample(big, 0.01), big)
+    # large random cloud incl. negative coordinates
+    rng = np.random.default_rng(8)
+    pts = np.concatenate([rng.uniform(-50, 50, (300000, 3)), rng.uniform(0, 64, (300000, 1))], 1).astype(np.float32)
+    out = ctx.voxel_downsample(pts, 0.4, True)
+    ref, _ = orc.voxel_grid(pts, 0.4, True)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------ extractCloud
+@pytest.mark.parametrize("rings,horizon", [(16, 1024), (64, 2048)])
+def test_extract_features_bit_exact(ctx, rings, horizon):
+    scene = syn.make_scene()
+    pose = syn.trajectory(3)[2]
+    cloud, ss, se = syn.make_sweep(scene, pose, rings, horizon, seed=21)
+    out = ctx.extract_features(cloud, ss, se)
+    ref = orc.extract_cloud(cloud, ss, se)
+    curv, label = ctx.extract_debug(cloud.shape[0])
+    assert np.array_equal(curv.view(np.uint32)[5:-5], ref["curvature"].view(np.uint32)[5:-5])
+    assert np.array_equal(label, ref["label"])
+    for k in ("corner_points_sharp", "corner_points_less_sharp", "surf_points_flat", "surf_points_less_flat"):
+        assert out[k].shape == ref[k].shape, k
+        assert np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)), k
+    assert out["corner_points_sharp"].shape[0] <= 2 * 6 * rings
+
+
+def test_extract_ragged_and_short_rings(ctx):
+    scene = syn.make_scene()
+    cloud, ss, se = syn.make_sweep(scene, syn.trajectory(1)[0], 16, 1024, seed=5)
+    # drop points to make rings ragged, including one ring left with < 6 usable points and one empty ring
+    ring = cloud[:, 3].astype(int)
+    rng = np.random.default_rng(3)
+    keep = rng.random(cloud.shape[0]) > 0.3
+    keep &= ~((ring == 3) & (np.cumsum(ring == 3) > 14))  # ring 3: 14 points -> end-start = 3 < 6: skipped
+    keep &= ring != 7                                      # ring 7: empty
+    c2 = np.ascontiguousarray(cloud[keep])
+    s2, e2 = syn.scan_info_from_cloud(c2, 16)
+    out = ctx.extract_features(c2, s2, e2)
+    ref = orc.extract_cloud(c2, s2, e2)
+    for k in ("corner_points_sharp", "corner_points_less_sharp", "surf_points_flat", "surf_points_less_flat"):
+        assert np.array_equal(out[k].view(np.uint32), ref[k].view(np.uint32)), k
+    assert not np.any(out["surf_points_flat"][:, 3].astype(int) == 3)
+
+
+# ------------------------------------------------------------------------------------------------ scan2map / frame
+@pytest.mark.parametrize("outer,inner", [(2, 30), (5, 1), (10, 1)])
+def test_scan2map_pose_parity(ctx, c1, outer, inner):
+    ctx.map_build(1, c1["surf_map"], 0.5)
+    ctx.map_build(0, c1["corner_map"], 0.5)
+    ctx.set_params(max_outer=outer, max_inner=inner)
+    try:
+        pose, st = ctx.scan2map(c1["surf_scan"], c1["corner_scan"], c1["init"])
+    finally:
+        ctx.set_params(max_outer=2, max_inner=30)
+    o = orc.default_opts()
+    o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = outer, inner
+    ref, rst = orc.scan2map(c1["surf_map"], c1["corner_map"], c1["surf_scan"], c1["corner_scan"], c1["init"], o)
+    dt, dr = syn.pose_err(pose, ref)
+    assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+    assert st["ran"] == 1 and st["n_surf"] == int(rst["n_surf"]) and st["n_corner"] == int(rst["n_corner"])
+    assert st["lm_iterations"] == int(rst["lm_iterations"])
+    assert st["degenerate"] == int(rst["degenerate"])
+    assert np.allclose(st["eig"], rst["eig"], rtol=1e-8)
+    assert np.allclose(st["H"], rst["H"], rtol=1e-9, atol=1e-7)
+    # and it actually localises: closer to the truth than the initial guess
+    assert syn.pose_err(pose, c1["truth"])[0] < syn.pose_err(c1["init"], c1["truth"])[0]
+
+
+def test_scan2map_gates_and_degeneracy(ctx, c1):
+    # map-size gate (lidar_mapper_keyframe.cpp:429): pose returned unchanged, ran = 0
+    ctx.map_build(1, c1["surf_map"][:40], 0.5)
+    ctx.map_build(0, c1["corner_map"], 0.5)
+    pose, st = ctx.scan2map(c1["surf_scan"], c1["corner_scan"], c1["init"])
+    assert st["ran"] == 0 and np.array_equal(pose, c1["init"])
+    # degenerate geometry: a floor-only surf map and no usable corners -> evalDegenracy remaps the update
+    floor = c1["surf_map"][np.abs(c1["surf_map"][:, 2]) < 0.05]
+    ctx.map_build(1, floor, 0.5)
+    far = c1["corner_map"].copy()
+    far[:, :3] += 500.0
+    ctx.map_build(0, far, 0.5)
+    pose, st = ctx.scan2map(c1["surf_scan"], c1["corner_scan"], c1["init"])
+    ref, rst = orc.scan2map(floor, far, c1["surf_scan"], c1["corner_scan"], c1["init"])
+    assert st["degenerate"] == 1 and int(rst["degenerate"]) == 1 and st["n_corner"] == 0
+    dt, dr = syn.pose_err(pose, ref)
+    assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+    # empty scans
+    ctx.map_build(1, c1["surf_map"], 0.5)
+    ctx.map_build(0, c1["corner_map"], 0.5)
+    pose, st = ctx.scan2map(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32), c1["init"])
+    assert st["n_surf"] == 0 and st["n_corner"] == 0 and np.allclose(pose, c1["init"])
+
+
+@pytest.mark.parametrize("outer,inner", [(2, 30), (5, 1)])
+def test_frame_pose_parity_c1(ctx, c1, mloam, outer, inner):
+    ctx.set_params(max_outer=outer, max_inner=inner, n_scans=16, map_cell=0.5)
+    try:
+        pose, st = ctx.frame(c1["cloud"], c1["ss"], c1["se"], c1["surf_map"], c1["corner_map"], c1["init"])
+    finally:
+        ctx.set_params(max_outer=2, max_inner=30, n_scans=64, map_cell=0.0)
+    o = orc.default_opts()
+    o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = outer, inner
+    ref, rst = orc.scan2map(c1["surf_map"], c1["corner_map"], c1["surf_scan"], c1["corner_scan"], c1["init"], o)
+    assert st["n_surf_in"] == c1["surf_scan"].shape[0] and st["n_corner_in"] == c1["corner_scan"].shape[0]
+    assert st["n_surf"] == int(rst["n_surf"]) and st["n_corner"] == int(rst["n_corner"])
+    dt, dr = syn.pose_err(pose, ref)
+    assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+
+
+def test_frame_c2_full_size(ctx):
+    """Config C2 at full size: 64 x 2048 sweep, 1M-point submap, 10 GN iterations; pose parity against the oracle
+    plus size-independent properties."""
+    scene = syn.make_scene()
+    traj = syn.trajectory(8)
+    surf_map, corner_map = syn.make_submap(scene, 1_000_000)
+    cloud, ss, se = syn.make_sweep(scene, traj[7], 64, 2048, seed=7)
+    init = syn.perturb_pose(traj[7], np.random.Generator(np.random.PCG64(17)))
+    ctx.set_params(max_outer=10, max_inner=1, n_scans=64, map_cell=0.25)
+    try:
+        pose, st = ctx.frame(cloud, ss, se, surf_map, corner_map, init)
+        pose_b, st_b = ctx.frame(cloud, ss, se, surf_map, corner_map, init)
+    finally:
+        ctx.set_params(max_outer=2, max_inner=30, map_cell=0.0)
+    assert np.array_equal(pose, pose_b)  # deterministic: no atomics in the reductions
+    f = orc.extract_cloud(cloud, ss, se)
+    cs, _ = orc.voxel_grid(f["corner_points_less_sharp"], 0.2, True)
+    sf, _ = orc.voxel_grid(f["surf_points_less_flat"], 0.4, True)
+    assert st["n_surf_in"] == sf.shape[0] and st["n_corner_in"] == cs.shape[0]
+    o = orc.default_opts()
+    o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = 10, 1
+    ref, rst = orc.scan2map(surf_map, corner_map, sf, cs, init, o)
+    assert st["n_surf"] == int(rst["n_surf"]) and st["n_corner"] == int(rst["n_corner"])
+    dt, dr = syn.pose_err(pose, ref)
+    assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+    et, er = syn.pose_err(pose, traj[7])
+    assert et < 0.02 and er < 2e-3
