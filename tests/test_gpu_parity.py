@@ -51,7 +51,7 @@ def test_knn_index_exact(ctx, k, cell):
     d = ((m[np.where(ok, idx, 0)][:, :, :3] - q[:, None, :3]) ** 2)
     d2 = (d[..., 0] + d[..., 1]) + d[..., 2]
     assert np.array_equal(d2[ok], sqd[ok])
-    assert np.all(np.diff(np.where(ok, sqd, np.inf), axis=1) >= 0)
+    assert np.all(np.diff(np.where(ok, sqd, np.float32(3e38)), axis=1) >= 0)
 
 
 def test_knn_with_pose_and_large_radius(ctx):
