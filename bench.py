@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — M-LOAM per-scan hot path on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+A "step" is one pass of the hot path over one synthetic LiDAR sweep per GPU:
+    setInputCloud on the surf + corner submaps (rebuilt every frame like lidar_mapper_keyframe.cpp:433-434)
+    -> FeatureExtract::extractCloud -> downsampleCurrentScan -> scan2MapOptimization with GN_ITERS re-association
+    iterations (kNN + line/plane fit + residual/Jacobian + J^T J reduction + LM step each).
+N = 1 workload: BASELINE.json configs[1] (1 LiDAR, 64 x 2048 sweep, 1M-point edge+surf submap, 10 GN iterations).
+N > 1: one LiDAR per GPU (its own extrinsic), the submap replicated on every GPU (1M / 2M / 5M / 10M points for
+N = 1 / 2 / 4 / 8), one NCCL all-reduce of the 30 packed normal-equation doubles per LM evaluation.
+
+value      : LiDAR sweeps through the whole hot path per second, summed over GPUs, inputs resident in HBM.
+e2e        : the same through the C-ABI call a user makes (mloam_frame) with HOST buffers (pinned), H2D of the
+             sweep + both submaps and D2H of the pose inside the timed region.
+roofline   : the dominant kernel (k_match: kNN + fit, one warp per feature), algorithmic bytes / CUDA-event time.
+cpu_baseline: the oracle (CPU restatement of the reference path) on the same frame, reference threading.
+--impl reference: that CPU path as the timed arm (all host cores tried, best kept).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GN_ITERS = 10
+MAP_POINTS = {1: 1_000_000, 2: 2_000_000, 4: 5_000_000, 8: 10_000_000}
+RINGS, HORIZON = 64, 2048
+MATCH_BYTES_PER_FEATURE = 16 + 5 * 16 + 24 + 1  # query float4 + 5 neighbour float4 + 6 float coeffs + valid flag
+METRIC = "scan_to_map_lidar_frames_per_sec"
+
+
+def load_mloam():
+    spec = importlib.util.spec_from_file_location("mloam_b200", os.path.join(ROOT, "m-loam_b200", "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["mloam_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def lidar_extrinsic(syn, rank: int, n: int) -> np.ndarray | None:
+    """LiDAR 0 = identity; the others sit on a 1.2 m ring with +-20 deg tilt."""
+    if rank == 0:
+        return None
+    import math
+    a = 2 * math.pi * rank / max(n, 2)
+    tilt = math.radians(20.0) * (1 if rank % 2 else -1)
+    return syn.pose7([0.6 * math.cos(a), 0.6 * math.sin(a), 0.0], syn.quat_from_rpy(tilt * math.sin(a), tilt * math.cos(a), a))
+
+
+def make_workload(syn, n_gpus: int, rank: int, n_frames: int):
+    scene = syn.make_scene()
+    traj = syn.trajectory(n_frames + 2)
+    m_total = MAP_POINTS.get(n_gpus, 1_000_000 * n_gpus)
+    surf_map, corner_map = syn.make_submap(scene, m_total)
+    ext = lidar_extrinsic(syn, rank, n_gpus)
+    frames = []
+    rng = np.random.Generator(np.random.PCG64(1234))
+    for k in range(n_frames):
+        truth = traj[k + 1]
+        cloud, ss, se = syn.make_sweep(scene, truth, RINGS, HORIZON, seed=100 + k, lidar_id=rank, ext=ext)
+        init = syn.perturb_pose(truth, rng)  # BASE pose guess, identical on every rank (shared state of the all-reduced LM)
+        frames.append(dict(cloud=cloud, ss=ss, se=se, init=init, truth=truth))
+    return surf_map, corner_map, frames, ext
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(syn, orc, surf_map, corner_map, frames, steps, warmup, try_all_cores=True):
+    """The reference's CPU path (oracle restatement) on the same frames.  Returns (frames/s, cores used, ms list)."""
+    o = orc.default_opts()
+    o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = GN_ITERS, 1
+    ncores = os.cpu_count() or 1
+
+    def run(fr):
+        t = time.perf_counter()
+        pose, st = orc.frame(fr["cloud"], fr["ss"], fr["se"], surf_map, corner_map, fr["init"], o)
+        return time.perf_counter() - t, pose, st
+
+    best_threads = 1
+    if try_all_cores and ncores > 1:
+        # the mapper is single-threaded in the reference; give it every core for feature matching if that is faster
+        orc.set_threads(1)
+        t1 = run(frames[0])[0]
+        orc.set_threads(ncores)
+        tn = run(frames[0])[0]
+        best_threads = ncores if tn < t1 else 1
+    orc.set_threads(best_threads)
+    for w in range(warmup):
+        run(frames[w % len(frames)])
+    times, last = [], None
+    for k in range(steps):
+        dt, pose, st = run(frames[k % len(frames)])
+        times.append(dt)
+        last = (pose, st)
+    orc.set_threads(1)
+    return len(times) / sum(times), best_threads, times, last
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=12, help="frames of CPU work for cpu_baseline (~10-30 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = args.gpus
+    import synthetic as syn
+
+    config = {"workload": f"C2-like: {n_gpus} LiDAR(s) x {RINGS}-ring x {HORIZON} sweep, {MAP_POINTS.get(n_gpus, n_gpus * 10**6)}-pt "
+                          f"edge+surf submap (1:9) rebuilt every frame, {GN_ITERS} GN iterations (re-association each)",
+              "rings": RINGS, "horizon": HORIZON, "map_points": MAP_POINTS.get(n_gpus, n_gpus * 10**6), "gn_iters": GN_ITERS,
+              "parallelism": f"lidar-per-gpu x{n_gpus}", "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import oracle_lib as orc
+        surf_map, corner_map, frames, _ = make_workload(syn, n_gpus, 0, max(2, min(args.steps, 4)))
+        steps = max(1, min(args.steps, 8))  # bounded sample: ~0.7 s of CPU work per step at N=1
+        warm = max(1, min(args.warmup, 2))
+        fps, cores, times, _ = cpu_reference_arm(syn, orc, surf_map, corner_map, frames, steps, warm)
+        fps_total = fps  # one process handles the LiDARs serially as the mapper does; report per-LiDAR-sweep rate
+        line = {"metric": METRIC, "value": fps_total, "unit": "frames/s", "n_gpus": n_gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": fps_total, "unit": "frames/s", "cores": cores, "kind": "port",
+                                 "sample": f"{steps} frames of the N=1 workload (one LiDAR sweep each), oracle restatement of the "
+                                           f"reference CPU path; host has {os.cpu_count()} logical cores"},
+                "e2e": {"value": fps_total, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this framework has no CPU path"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    m = load_mloam()
+    p = m.default_params()
+    p.n_scans, p.max_outer, p.max_inner, p.map_cell = RINGS, GN_ITERS, 1, 0.25
+    ctx = m.Context(local_rank, p)
+    if world > 1:
+        uid = [m.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+
+    n_frames = 8
+    surf_map, corner_map, frames, ext = make_workload(syn, n_gpus, rank, n_frames)
+    ctx.set_extrinsic(ext)  # this GPU's LiDAR -> base
+    dev = torch.device("cuda", local_rank)
+    d_surf = torch.from_numpy(surf_map).to(dev)
+    d_corner = torch.from_numpy(corner_map).to(dev)
+    d_frames = [dict(cloud=torch.from_numpy(f["cloud"]).to(dev), ss=torch.from_numpy(f["ss"]).to(dev),
+                     se=torch.from_numpy(f["se"]).to(dev)) for f in frames]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    # pinned host copies for the e2e arm
+    h_surf = torch.from_numpy(surf_map).pin_memory()
+    h_corner = torch.from_numpy(corner_map).pin_memory()
+    h_frames = [dict(cloud=torch.from_numpy(f["cloud"]).pin_memory(), ss=f["ss"], se=f["se"]) for f in frames]
+
+    def step_device(k):
+        f, d = frames[k % n_frames], d_frames[k % n_frames]
+        return ctx.frame_device(d["cloud"].data_ptr(), f["cloud"].shape[0], d["ss"].data_ptr(), d["se"].data_ptr(), RINGS,
+                                d_surf.data_ptr(), surf_map.shape[0], d_corner.data_ptr(), corner_map.shape[0], f["init"], True)
+
+    def step_host(k):
+        f, hf = frames[k % n_frames], h_frames[k % n_frames]
+        return ctx.frame(hf["cloud"].numpy(), hf["ss"], hf["se"], h_surf.numpy(), h_corner.numpy(), f["init"], True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- value: inputs resident in HBM, per-step CUDA events on the launching stream, L2 flushed between steps
+    for k in range(args.warmup):
+        step_device(k)
+    ctx.profile(True)
+    ctx.profile_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = ctx.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    last = None
+    feats = 0
+    with torch.cuda.stream(stream):
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)  # not timed: evict the previous step's lines from L2
+            if world > 1:
+                dist.barrier()
+            evs[k][0].record(stream)
+            last = step_device(args.warmup + k)
+            evs[k][1].record(stream)
+            feats += last[1]["n_surf_in"] + last[1]["n_corner_in"]
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    ms_steps = [a.elapsed_time(b) for a, b in evs]
+    t_local = sum(ms_steps) / 1e3
+    prof = {name: ctx.profile_get(name) for name in ("map_build", "extract", "voxel", "match", "linearize", "lm")}
+    ctx.profile(False)
+    t_max = t_local
+    if world > 1:
+        tt = torch.tensor([t_local], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_max = float(tt.item())
+    value = world * args.steps / t_max
+
+    # ---- e2e: HOST buffers through the C ABI (H2D sweep + both submaps, D2H pose) — wall clock around synchronous calls
+    for k in range(2):
+        step_host(k)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 20))
+    for k in range(e2e_steps):
+        step_host(args.warmup + k)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+    e2e_value = world * e2e_steps / t_e2e
+    h2d = int(frames[0]["cloud"].nbytes + 2 * RINGS * 4 + surf_map.nbytes + corner_map.nbytes + 7 * 8)
+    d2h = int(7 * 8 + 4 * 2 + 1272)  # pose + counts + LM state read-back
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    match_ms, match_launches = prof["match"]
+    # every match launch processes all surf or all corner features of the frame: GN_ITERS launches of each per step
+    alg_bytes_total = feats * GN_ITERS * MATCH_BYTES_PER_FEATURE
+    achieved = (alg_bytes_total / 1e9) / (match_ms / 1e3) if match_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_match_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_match<5,*> (kNN + line/plane fit, one warp per feature)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_feature": MATCH_BYTES_PER_FEATURE,
+                "avg_launch_us": 1e3 * match_ms / max(1, match_launches), "launches": match_launches,
+                "note": "submap (16 MB points + 32 MB hash) is L2-resident: the kernel is latency/L2-bound, not HBM-bound"}
+    stage_ms = {k: v[0] / args.steps for k, v in prof.items()}
+
+    # ---- cpu_baseline: the oracle on the same frames, reference threading (mapper is single-threaded)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        import oracle_lib as orc
+        n_cpu = max(2, args.cpu_sample)
+        fps, cores, times, ref_last = cpu_reference_arm(syn, orc, surf_map, corner_map, frames, n_cpu, 1, try_all_cores=False)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} frames of this workload ({sum(times):.1f} s of CPU work), oracle restatement, reference threading "
+                         f"(single-threaded mapper); host has {os.cpu_count()} logical cores"}
+        # parity of the last timed GPU frame against the oracle on the same frame
+        k_last = (args.warmup + args.steps - 1) % n_frames
+        o = orc.default_opts()
+        o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = GN_ITERS, 1
+        ref_pose, _ = orc.frame(frames[k_last]["cloud"], frames[k_last]["ss"], frames[k_last]["se"], surf_map, corner_map,
+                                frames[k_last]["init"], o)
+        dt, dr = syn.pose_err(last[0], ref_pose)
+        config["pose_err_vs_oracle"] = {"m": dt, "rad": dr}
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
+            "data": "synthetic", "config": config, "ms_per_gn_iter": 1e3 * t_max / args.steps / GN_ITERS,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stage_ms_per_step": stage_ms,
+            "features_per_step": feats / args.steps}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

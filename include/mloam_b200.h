@@ -183,6 +183,12 @@ int mloam_frame_device(mloam_ctx_t *ctx, const mloam_point_t *d_cloud, int n, co
                        const mloam_point_t *d_corner_map, int n_corner_map, int rebuild_maps,
                        const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats);
 
+/* Extrinsic of this context's LiDAR (sensor -> base), applied to the extracted features before scan down-sampling
+ * and matching in mloam_frame*, as the odometry node does before handing features to the mapper
+ * (features reach scan2MapOptimization in the base frame, laser id in intensity; visualization.cpp:48,94-100).
+ * NULL resets to identity (no transform). */
+int mloam_set_extrinsic(mloam_ctx_t *ctx, const double *ext7);
+
 /* ---- LidarTracker::trackCloud (lidar_tracker.cpp:23-129). */
 int mloam_track_cloud(mloam_ctx_t *ctx, const mloam_point_t *h_prev_less_sharp, int n_pls,
                       const mloam_point_t *h_prev_less_flat, int n_plf, const mloam_point_t *h_cur_sharp, int n_cs,

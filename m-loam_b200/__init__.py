@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
-    "mloam_frame_device", "mloam_track_cloud", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy",
+    "mloam_frame_device", "mloam_set_extrinsic", "mloam_track_cloud", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy",
 ]
 
 
@@ -295,6 +295,10 @@ class Context:
                                           C.c_void_p(d_surf_map), n_surf_map, C.c_void_p(d_corner_map), n_corner_map,
                                           int(rebuild_maps), _p(pi), _p(out), C.byref(st)))
         return out, st.as_dict()
+
+    def set_extrinsic(self, ext7=None):
+        e = None if ext7 is None else np.ascontiguousarray(ext7, np.float64)
+        self._ck(lib().mloam_set_extrinsic(self._h, _p(e)))
 
     # ---- multi-GPU
     @staticmethod

@@ -99,6 +99,8 @@ struct Ctx {
 
   // NCCL (multi-GPU); opaque here
   int *d_extract_status = nullptr;  // device flag of the last extraction (1: ring window overflow / bad ScanInfo)
+  bool has_ext = false;             // sensor -> base extrinsic applied to extracted features (frame path)
+  double ext[7] = {0, 0, 0, 0, 0, 0, 1};
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;
 };
@@ -149,6 +151,9 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
 int lm_init_state(Ctx *c, const double *pose7_host, int max_inner, double eig_thre);
 int factor_evaluate_device(Ctx *c, int kind, int n, const double *d_points, const double *d_coeffs, const double *d_sqrt_info,
                            const double *d_params, double *d_res, double *d_jac);
+
+// in place: p <- T * p for the first min(n, *d_n) points (pointAssociateToMap, utility.h:103-117); d_pose7 on device
+int transform_points_device(Ctx *c, float4 *d_pts, int n, const int *d_n, const double *d_pose7);
 
 // comm.cu: in-place sum over ranks on the context stream (no-op without a communicator)
 int comm_allreduce_doubles(Ctx *c, double *d_buf, int count);

@@ -563,6 +563,22 @@ __global__ void k_less_flat_gather(const float4 *__restrict__ P, const int *__re
   }
 }
 
+__global__ void k_transform_points(float4 *pts, int n, const int *__restrict__ d_n, const double *__restrict__ pose7) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_n) n = min(n, *d_n);
+  if (i >= n) return;
+  float4 p = pts[i];
+  const float3 q = associate(pose_from_param(pose7), p.x, p.y, p.z);
+  pts[i] = make_float4(q.x, q.y, q.z, p.w);
+}
+int transform_points_device(Ctx *c, float4 *d_pts, int n, const int *d_n, const double *d_pose7) {
+  if (n <= 0) return MLOAM_OK;
+  k_transform_points<<<(n + 255) / 256, 256, 0, c->stream>>>(d_pts, n, d_n, d_pose7);
+  c->launches++;
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  return MLOAM_OK;
+}
+
 int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
                    ExtractOut out, float *d_curv_or_null, int *d_label_or_null) {
   if (n < 0 || n_scans <= 0 || n_scans > 128) {

@@ -140,8 +140,18 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
   if (rc) return rc;
   rc = extract_device(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, F.ex, nullptr, nullptr);
   if (rc) return rc;
-  // downsampleCurrentScan, lidar_mapper_keyframe.cpp:356-364 (VoxelGridCovarianceMLOAM<PointI>: xyz mean, last intensity)
   const int less_cap = n < 120 * n_scans ? n : 120 * n_scans;  // <= 20 less-sharp picks x 6 sectors per ring
+  if (c->has_ext) {  // features are handed to the mapper in the base frame
+    double *stage = reinterpret_cast<double *>(c->pinned) + 32;
+    for (int k = 0; k < 7; k++) stage[k] = c->ext[k];
+    double *d_ext = c->scratch[7].as<double>() + 32;
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ext, stage, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    rc = transform_points_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, d_ext);
+    if (rc) return rc;
+    rc = transform_points_device(c, F.ex.less_flat, n, F.ex.counts + 3, d_ext);
+    if (rc) return rc;
+  }
+  // downsampleCurrentScan, lidar_mapper_keyframe.cpp:356-364 (VoxelGridCovarianceMLOAM<PointI>: xyz mean, last intensity)
   rc = voxel_downsample_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, P.corner_leaf, 1, F.corner_ds, F.n_corner_ds, 5);
   if (rc) return rc;
   rc = voxel_downsample_device(c, F.ex.less_flat, n, F.ex.counts + 3, P.surf_leaf, 1, F.surf_ds, F.n_surf_ds, 5);
@@ -300,6 +310,14 @@ int mloam_frame(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *
     d_sm = ms.as<float4>(), d_cm = mc.as<float4>();
   }
   return frame_run(c, d_cloud, n, d_ss, d_se, n_scans, d_sm, n_surf_map, d_cm, n_corner_map, rebuild_maps, pose_init7, pose_out7, stats);
+}
+
+int mloam_set_extrinsic(mloam_ctx_t *h, const double *ext7) {
+  if (!h) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  c->has_ext = ext7 != nullptr;
+  for (int k = 0; k < 7; k++) c->ext[k] = ext7 ? ext7[k] : (k == 6 ? 1.0 : 0.0);
+  return MLOAM_OK;
 }
 
 // ------------------------------------------------------------------------------------------ tracker (scan-to-scan)

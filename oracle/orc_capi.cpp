@@ -214,6 +214,33 @@ void orc_scan2map(const float *surf_map, int n_sm, const float *corner_map, int 
   if (H36) std::memcpy(H36, r.H_last, sizeof(r.H_last));
 }
 
+// ---- the whole per-sweep hot path on the CPU: extractCloud -> downsampleCurrentScan -> scan2MapOptimization
+// (the bench's cpu_baseline / --impl reference step).  stats[20]: [0..15] as orc_scan2map, [16] t_extract,
+// [17] t_downsample, [18] n_surf_in, [19] n_corner_in
+void orc_frame(const float *cloud, int n, const int *scan_start, const int *scan_end, int n_scans, const float *surf_map,
+               int n_sm, const float *corner_map, int n_cm, float corner_leaf, float surf_leaf, const double *pose_init7,
+               const double *opts, double *pose_out7, double *stats) {
+  Cloud c = to_cloud(cloud, n);
+  ScanInfo si;
+  si.scan_start_ind.assign(scan_start, scan_start + n_scans);
+  si.scan_end_ind.assign(scan_end, scan_end + n_scans);
+  double t0 = now_s();
+  CloudFeature f;
+  extract_cloud(c, si, n_scans, f);
+  double t1 = now_s();
+  Cloud cs, ss;
+  voxel_grid(f.corner_points_less_sharp, corner_leaf, cs, true);  // lidar_mapper_keyframe.cpp:359-364
+  voxel_grid(f.surf_points_less_flat, surf_leaf, ss, true);
+  double t2 = now_s();
+  double st16[16];
+  orc_scan2map(surf_map, n_sm, corner_map, n_cm, ss.empty() ? nullptr : &ss[0].x, (int)ss.size(),
+               cs.empty() ? nullptr : &cs[0].x, (int)cs.size(), pose_init7, opts, pose_out7, st16, nullptr);
+  if (stats) {
+    for (int i = 0; i < 16; i++) stats[i] = st16[i];
+    stats[16] = t1 - t0, stats[17] = t2 - t1, stats[18] = (double)ss.size(), stats[19] = (double)cs.size();
+  }
+}
+
 // ---- LidarTracker::trackCloud. stats[3]: n_corner, n_surf, lm_iterations
 void orc_track_cloud(const float *prev_less_sharp, int n_pls, const float *prev_less_flat, int n_plf,
                      const float *cur_sharp, int n_cs, const float *cur_flat, int n_cf, const double *pose_ini7,
@@ -226,6 +253,15 @@ void orc_track_cloud(const float *prev_less_sharp, int n_pls, const float *prev_
   TrackResult r = track_cloud(a, b, c, d, to_pose(pose_ini7), o);
   pose_to_param(r.pose, pose_out7);
   if (stats) stats[0] = r.n_corner, stats[1] = r.n_surf, stats[2] = r.lm_iterations;
+}
+
+// OpenMP threads used by the parallel sections (1 = the reference's serial behaviour; tests always use 1).
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n < 1 ? 1 : n);
+#else
+  (void)n;
+#endif
 }
 
 int orc_max_threads() {

@@ -46,11 +46,11 @@ class KdTree {
   // nearestKSearch (call sites feature_extract.hpp:155,293,406,570,666,813).  Writes min(K, size) hits and
   // returns that count.
   int nearestKSearch(float qx, float qy, float qz, int K, int *idx, float *sqd) const {
-    std::vector<KnnHit> best;
-    best.reserve(K + 1);
-    if (!nodes_.empty()) search(0, qx, qy, qz, K, best);
-    for (size_t i = 0; i < best.size(); i++) idx[i] = best[i].idx, sqd[i] = best[i].d2;
-    return (int)best.size();
+    Best best;
+    best.K = K < kMaxK ? K : kMaxK;
+    if (!nodes_.empty()) search(0, qx, qy, qz, best);
+    for (int i = 0; i < best.n; i++) idx[i] = best.h[i].idx, sqd[i] = best.h[i].d2;
+    return best.n;
   }
   size_t size() const { return cloud_ ? cloud_->size() : 0; }
 
@@ -64,6 +64,18 @@ class KdTree {
   std::vector<int> order_;
   std::vector<Node> nodes_;
   static constexpr int kLeaf = 15;
+  static constexpr int kMaxK = 64;
+  struct Best {  // fixed-capacity sorted result set (no heap traffic per query)
+    KnnHit h[kMaxK + 1];
+    int n = 0, K = 0;
+    void offer(const KnnHit &x) {
+      if (n == K && !hit_less(x, h[n - 1])) return;
+      int i = n < K ? n : K - 1;
+      while (i > 0 && hit_less(x, h[i - 1])) h[i] = h[i - 1], i--;
+      h[i] = x;
+      if (n < K) n++;
+    }
+  };
 
   static float coord(const PointI &p, int d) { return d == 0 ? p.x : (d == 1 ? p.y : p.z); }
 
@@ -110,27 +122,20 @@ class KdTree {
     }
     return s * (1.0 - 1e-5);
   }
-  void search(int id, float qx, float qy, float qz, int K, std::vector<KnnHit> &best) const {
+  void search(int id, float qx, float qy, float qz, Best &best) const {
     const Node &nd = nodes_[id];
-    if ((int)best.size() == K && boxdist(nd, qx, qy, qz) > (double)best.back().d2) return;
+    if (best.n == best.K && boxdist(nd, qx, qy, qz) > (double)best.h[best.n - 1].d2) return;
     if (nd.left < 0) {
-      for (int i = nd.lo; i < nd.hi; i++) {
-        KnnHit h{dist2f((*cloud_)[order_[i]], qx, qy, qz), order_[i]};
-        if ((int)best.size() < K || hit_less(h, best.back())) {
-          auto it = std::upper_bound(best.begin(), best.end(), h, hit_less);
-          best.insert(it, h);
-          if ((int)best.size() > K) best.pop_back();
-        }
-      }
+      for (int i = nd.lo; i < nd.hi; i++) best.offer(KnnHit{dist2f((*cloud_)[order_[i]], qx, qy, qz), order_[i]});
       return;
     }
     double dl = boxdist(nodes_[nd.left], qx, qy, qz), dr = boxdist(nodes_[nd.right], qx, qy, qz);
     if (dl <= dr) {
-      search(nd.left, qx, qy, qz, K, best);
-      search(nd.right, qx, qy, qz, K, best);
+      search(nd.left, qx, qy, qz, best);
+      search(nd.right, qx, qy, qz, best);
     } else {
-      search(nd.right, qx, qy, qz, K, best);
-      search(nd.left, qx, qy, qz, K, best);
+      search(nd.right, qx, qy, qz, best);
+      search(nd.left, qx, qy, qz, best);
     }
   }
 };

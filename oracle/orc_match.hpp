@@ -116,12 +116,21 @@ inline bool match_surf_point_from_map(const KdTree &tree, const Cloud &map, cons
 inline void match_from_map(char type, const KdTree &tree, const Cloud &map, const Cloud &data, const Pose &pose,
                            std::vector<Feature> &features, int n_neigh, bool check_fov, const MatchParams &mp) {
   features.clear();
-  Feature f;
-  for (size_t i = 0; i < data.size(); i++) {
-    bool ok = type == 'c' ? match_corner_point_from_map(tree, map, data[i], pose, f, i, n_neigh, check_fov, mp)
-                          : match_surf_point_from_map(tree, map, data[i], pose, f, i, n_neigh, check_fov, mp);
-    if (ok) features.push_back(f);
+  const int n = (int)data.size();
+  // The reference loop is serial (the mapper has no OpenMP).  With more than one OpenMP thread
+  // configured (bench "all host cores" arm only) queries are matched in parallel and compacted in query order,
+  // which yields the identical feature list.
+  std::vector<unsigned char> ok(n, 0);
+  std::vector<Feature> all(n);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (int i = 0; i < n; i++) {
+    ok[i] = (type == 'c' ? match_corner_point_from_map(tree, map, data[i], pose, all[i], i, n_neigh, check_fov, mp)
+                         : match_surf_point_from_map(tree, map, data[i], pose, all[i], i, n_neigh, check_fov, mp))
+                ? 1
+                : 0;
   }
+  for (int i = 0; i < n; i++)
+    if (ok[i]) features.push_back(all[i]);
 }
 
 // matchCornerFromScan, feature_extract.hpp:131-271.  cloud_scan must be ring-sorted; int(intensity)=ring.

@@ -46,6 +46,7 @@ def lib():
         _lib.orc_logdet.restype = C.c_double
         _lib.orc_map_sqrt_info.restype = C.c_double
         _lib.orc_map_sqrt_info.argtypes = [C.c_double]
+        _lib.orc_set_threads(1)  # serial, like the reference's mapper; bench's all-cores arm raises it explicitly
     return _lib
 
 
@@ -58,6 +59,10 @@ def ref_lib():
             return None
         _ref = C.CDLL(p)
     return _ref
+
+
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(int(n))
 
 
 def cloud(a) -> np.ndarray:
@@ -240,6 +245,23 @@ def scan2map(surf_map, corner_map, surf_scan, corner_scan, pose_init, opts=None)
     st = {k: stats[i] for i, k in enumerate(names)}
     st["eig"] = stats[9:15].copy()
     st["H"] = H
+    return out, st
+
+
+def frame(cloud_, scan_start, scan_end, surf_map, corner_map, pose_init, opts=None, corner_leaf=0.2, surf_leaf=0.4):
+    """extractCloud -> downsampleCurrentScan -> scan2MapOptimization on the CPU (one LiDAR sweep)."""
+    pts, sm, cm = cloud(cloud_), cloud(surf_map), cloud(corner_map)
+    ss = np.ascontiguousarray(scan_start, np.int32)
+    se = np.ascontiguousarray(scan_end, np.int32)
+    opts = default_opts() if opts is None else np.ascontiguousarray(opts, np.float64)
+    pose_init = np.ascontiguousarray(pose_init, np.float64)
+    out = np.empty(7)
+    stats = np.zeros(20)
+    lib().orc_frame(_p(pts), pts.shape[0], _p(ss), _p(se), ss.shape[0], _p(sm), sm.shape[0], _p(cm), cm.shape[0],
+                    C.c_float(corner_leaf), C.c_float(surf_leaf), _p(pose_init), _p(opts), _p(out), _p(stats))
+    names = ["ran", "n_surf", "n_corner", "lm_iterations", "final_cost", "degenerate", "t_kdtree", "t_match", "t_solver"]
+    st = {k: stats[i] for i, k in enumerate(names)}
+    st.update(t_extract=stats[16], t_downsample=stats[17], n_surf_in=int(stats[18]), n_corner_in=int(stats[19]))
     return out, st
 
 
