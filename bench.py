@@ -205,7 +205,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     m = load_mloam()
     p = m.default_params()
-    p.n_scans, p.max_outer, p.max_inner, p.map_cell = RINGS, GN_ITERS, 1, 0.25
+    p.n_scans, p.max_outer, p.max_inner, p.map_cell = RINGS, GN_ITERS, 1, 0.26
     ctx = m.Context(local_rank, p)
     if world > 1:
         uid = [m.Context.comm_unique_id() if rank == 0 else None]

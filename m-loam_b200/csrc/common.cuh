@@ -128,6 +128,12 @@ __host__ __device__ inline unsigned long long pack_cell(int ix, int iy, int iz) 
          ((unsigned long long)((unsigned)(iy + MLOAM_CELL_BIAS) & 0x1fffffu) << 21) |
          (unsigned long long)((unsigned)(iz + MLOAM_CELL_BIAS) & 0x1fffffu);
 }
+// Coarse occupancy: blocks of 4x4x4 cells share one tagged record (bit 63) holding their point count.
+#define MLOAM_COARSE_SHIFT 2
+#define MLOAM_COARSE_TAG 0x8000000000000000ull
+__host__ __device__ inline unsigned long long coarse_key(int cx, int cy, int cz) {
+  return pack_cell(cx, cy, cz) | MLOAM_COARSE_TAG;
+}
 __host__ __device__ inline unsigned hash_cell(unsigned long long k) {
   k ^= k >> 33;
   k *= 0xff51afd7ed558ccdull;

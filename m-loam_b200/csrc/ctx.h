@@ -99,7 +99,8 @@ struct Ctx {
 
   // NCCL (multi-GPU); opaque here
   int *d_extract_status = nullptr;  // device flag of the last extraction (1: ring window overflow / bad ScanInfo)
-  bool has_ext = false;             // sensor -> base extrinsic applied to extracted features (frame path)
+  int want_eig = 1;                 // k_lm mode 1: always run the 6x6 eigen-solver (1) or only when degenerate (0)
+  bool has_ext = false;            // sensor -> base extrinsic applied to extracted features (frame path)
   double ext[7] = {0, 0, 0, 0, 0, 0, 1};
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;

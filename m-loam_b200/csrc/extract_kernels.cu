@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(RING_THREADS)
   __shared__ unsigned char gap[RING_MAX + 16];
   const int ring = blockIdx.x;
   RingStage &S = stage[ring];
-  if (threadIdx.x == 0) S.n_sharp = S.n_less = S.n_flat = 0;
+  if (threadIdx.x == 0) S.n_sharp = S.n_less = S.n_flat = 0;  // rings that return early emit nothing
   const int s = scan_start[ring], e = scan_end[ring];
   if (e - s < 6) return;  // :155
   // on-chip window [lo, hi) = [s-5, e+5): every index the picks can touch (ind +- 5, ind in [s, e-1])
@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(RING_THREADS)
   }
   for (int k = s + threadIdx.x; k < e; k += RING_THREADS) ring_of[k] = ring;  // :258 range [sp_0, ep_5] = [s, e-1]
   __syncthreads();
+  int n_sharp = 0, n_less = 0, n_flat = 0;  // warp 0 keeps the running pick counts (uniform across its lanes)
   for (int j = 0; j < 6; j++) {
     const int sp = s + (e - s) * j / 6;            // :160
     const int ep = s + (e - s) * (j + 1) / 6 - 1;  // :161
@@ -459,26 +460,42 @@ __global__ void __launch_bounds__(RING_THREADS)
         __syncthreads();
       }
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+      // The picks are inherently sequential (each one suppresses its +-5 neighbours), but finding the NEXT
+      // unsuppressed candidate is not: warp 0 inspects 32 sorted candidates per step and ballots for the first
+      // one that is still unpicked; lane 0 applies the pick.  Same visiting order as the reference's loops.
+      const int lane = threadIdx.x;
       // :165-215 edge points, largest curvature first
       int largest = 0;
-      for (int k = len - 1; k >= 0; k--) {
-        const unsigned long long kk = keys[k];
+      int k = len - 1;
+      while (k >= 0) {
+        const int idx = k - lane;
+        const bool inb = idx >= 0;
+        const unsigned long long kk = inb ? keys[idx] : 0ull;
         const float cv = __uint_as_float((unsigned)(kk >> 32));
-        if (!((double)cv > 0.1)) break;  // sorted: nothing below can pass `curvature > 0.1`
         const int ind = (int)(unsigned)(kk & 0xffffffffu);
-        const int o = ind - lo;
-        if (picked[o] == 0) {
-          largest++;
+        const bool pass = inb && ((double)cv > 0.1);  // sorted: once one fails, everything after it fails
+        const unsigned m_fail = __ballot_sync(MLOAM_FULL_MASK, !pass);
+        const unsigned before_fail = m_fail ? ((1u << (__ffs(m_fail) - 1)) - 1u) : 0xffffffffu;
+        const unsigned m_unp = __ballot_sync(MLOAM_FULL_MASK, pass && picked[ind - lo] == 0) & before_fail;
+        if (m_unp == 0) {
+          if (m_fail) break;
+          k -= 32;
+          continue;
+        }
+        const int sel = __ffs(m_unp) - 1;
+        const int pind = __shfl_sync(MLOAM_FULL_MASK, ind, sel);
+        largest++;
+        if (largest > 20) break;
+        if (lane == 0) {
+          const int o = pind - lo;
           if (largest <= 2) {
-            label[ind] = 2;
-            S.sharp[S.n_sharp++] = ind;
-            S.less[S.n_less++] = ind;
-          } else if (largest <= 20) {
-            label[ind] = 1;
-            S.less[S.n_less++] = ind;
+            label[pind] = 2;
+            S.sharp[n_sharp] = pind;
+            S.less[n_less] = pind;
           } else {
-            break;
+            label[pind] = 1;
+            S.less[n_less] = pind;
           }
           picked[o] = 1;
           for (int l = 1; l <= 5; l++) {
@@ -490,20 +507,40 @@ __global__ void __launch_bounds__(RING_THREADS)
             picked[o + l] = 1;
           }
         }
+        if (largest <= 2) n_sharp++;
+        n_less++;
+        __syncwarp();
+        k = k - sel - 1;
       }
       // :218-256 flat points, smallest curvature first; the 4th pick breaks before any marking (:227-231)
       int smallest = 0;
-      for (int k = 0; k < len; k++) {
-        const unsigned long long kk = keys[k];
+      k = 0;
+      while (k < len) {
+        const int idx = k + lane;
+        const bool inb = idx < len;
+        const unsigned long long kk = inb ? keys[idx] : 0ull;
         const float cv = __uint_as_float((unsigned)(kk >> 32));
-        if (!((double)cv < 0.1)) break;
         const int ind = (int)(unsigned)(kk & 0xffffffffu);
-        const int o = ind - lo;
-        if (picked[o] == 0) {
-          label[ind] = -1;
-          S.flat[S.n_flat++] = ind;
-          smallest++;
-          if (smallest >= 4) break;
+        const bool pass = inb && ((double)cv < 0.1);
+        const unsigned m_fail = __ballot_sync(MLOAM_FULL_MASK, !pass);
+        const unsigned before_fail = m_fail ? ((1u << (__ffs(m_fail) - 1)) - 1u) : 0xffffffffu;
+        const unsigned m_unp = __ballot_sync(MLOAM_FULL_MASK, pass && picked[ind - lo] == 0) & before_fail;
+        if (m_unp == 0) {
+          if (m_fail) break;
+          k += 32;
+          continue;
+        }
+        const int sel = __ffs(m_unp) - 1;
+        const int pind = __shfl_sync(MLOAM_FULL_MASK, ind, sel);
+        smallest++;
+        if (lane == 0) {
+          label[pind] = -1;
+          S.flat[n_flat] = pind;
+        }
+        n_flat++;
+        if (smallest >= 4) break;
+        if (lane == 0) {
+          const int o = pind - lo;
           picked[o] = 1;
           for (int l = 1; l <= 5; l++) {
             if (!gap[o + l - 1]) break;
@@ -514,31 +551,33 @@ __global__ void __launch_bounds__(RING_THREADS)
             picked[o + l] = 1;
           }
         }
+        __syncwarp();
+        k = k + sel + 1;
       }
     }
     __syncthreads();
   }
+  if (threadIdx.x == 0) S.n_sharp = n_sharp, S.n_less = n_less, S.n_flat = n_flat;
 }
 
 // Emit the staged picks in ring order (the order the reference's push_backs produce).
 __global__ void k_emit_picks(const float4 *__restrict__ P, const RingStage *__restrict__ stage, int n_scans, float4 *__restrict__ sharp,
                              float4 *__restrict__ less, float4 *__restrict__ flat, int *__restrict__ counts) {
-  __shared__ int off[3][129];
-  if (threadIdx.x == 0) {
-    int a = 0, b = 0, c = 0;
-    for (int r = 0; r < n_scans; r++) {
-      off[0][r] = a, off[1][r] = b, off[2][r] = c;
-      a += stage[r].n_sharp, b += stage[r].n_less, c += stage[r].n_flat;
-    }
-    counts[0] = a, counts[1] = b, counts[2] = c;
+  // one CTA per ring: offsets = counts of the rings before it (<= 127 small reads), then a parallel gather
+  __shared__ int off[3];
+  const int r = blockIdx.x;
+  if (threadIdx.x < 3) {
+    int a = 0;
+    for (int q = 0; q < r; q++) a += threadIdx.x == 0 ? stage[q].n_sharp : (threadIdx.x == 1 ? stage[q].n_less : stage[q].n_flat);
+    off[threadIdx.x] = a;
+    if (r == n_scans - 1)
+      counts[threadIdx.x] = a + (threadIdx.x == 0 ? stage[r].n_sharp : (threadIdx.x == 1 ? stage[r].n_less : stage[r].n_flat));
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < n_scans; r += blockDim.x) {
-    const RingStage &S = stage[r];
-    for (int k = 0; k < S.n_sharp; k++) sharp[off[0][r] + k] = P[S.sharp[k]];
-    for (int k = 0; k < S.n_less; k++) less[off[1][r] + k] = P[S.less[k]];
-    for (int k = 0; k < S.n_flat; k++) flat[off[2][r] + k] = P[S.flat[k]];
-  }
+  const RingStage &S = stage[r];
+  for (int k = threadIdx.x; k < S.n_sharp; k += blockDim.x) sharp[off[0] + k] = P[S.sharp[k]];
+  for (int k = threadIdx.x; k < S.n_less; k += blockDim.x) less[off[1] + k] = P[S.less[k]];
+  for (int k = threadIdx.x; k < S.n_flat; k += blockDim.x) flat[off[2] + k] = P[S.flat[k]];
 }
 
 __global__ void k_ring_of_init(int *ring_of, int n) {
@@ -623,7 +662,7 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
   k_curvature<<<(n + CURV_THREADS - 1) / CURV_THREADS, CURV_THREADS, 0, st>>>(d_cloud, n, curv, gap, label);
   k_ring_of_init<<<nb, 256, 0, st>>>(ring_of, n);
   k_ring_pick<<<n_scans, RING_THREADS, 0, st>>>(curv, gap, n, d_scan_start, d_scan_end, label, ring_of, stage, status);
-  k_emit_picks<<<1, 128, 0, st>>>(d_cloud, stage, n_scans, out.sharp, out.less_sharp, out.flat, out.counts);
+  k_emit_picks<<<n_scans, 128, 0, st>>>(d_cloud, stage, n_scans, out.sharp, out.less_sharp, out.flat, out.counts);
   k_less_flat_flags<<<nb, 256, 0, st>>>(ring_of, label, n, flag);
   c->launches += 5;
   scan_exclusive(c, flag, pos, n, tmp, out.counts + 3 /* provisional: points entering the per-ring voxel grid */);

@@ -101,7 +101,14 @@ __device__ __forceinline__ HashEntry hash_lookup(const MapView &map, unsigned lo
 }
 
 // Warp-cooperative search.  All lanes pass the same query; `out` is replicated in every lane.
-template <int K>
+//
+// Step 0 consults the coarse occupancy records (4x4x4-cell blocks): the 27 blocks around the query's block are
+// probed by 27 lanes at once.  When a block edge is at least the search radius, those 27 blocks contain every
+// point inside the search ball, so (a) fewer than K points in them means no result can exist (the query is
+// rejected after one round), and (b) cells in empty blocks / outside the 27 blocks are never probed.  This is
+// what keeps the worst case (a feature with no map support, which would otherwise walk all shells) cheap.
+// REJECT_PARTIAL: the caller only wants results when K neighbours exist inside the radius (every matcher gate).
+template <int K, bool REJECT_PARTIAL>
 __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy, float qz, float max_sqdist, int lane,
                                          TopK<K> &out) {
   TopK<K> mine;
@@ -112,6 +119,19 @@ __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy,
   const float radius = sqrtf(max_sqdist);
   int rmax = (int)ceilf(radius * map.inv_cell) + 1;
   if (rmax > 16) rmax = 16;
+  const int ccx = cx >> MLOAM_COARSE_SHIFT, ccy = cy >> MLOAM_COARSE_SHIFT, ccz = cz >> MLOAM_COARSE_SHIFT;
+  const bool coarse_ok = map.cell * (float)(1 << MLOAM_COARSE_SHIFT) >= radius * 1.0002f + 64.0f * eps;
+  unsigned occ;
+  {
+    int cnt = 0;
+    if (lane < 27) {
+      const HashEntry e = hash_lookup(map, coarse_key(ccx + lane % 3 - 1, ccy + (lane % 9) / 3 - 1, ccz + lane / 9 - 1));
+      cnt = e.start;  // coarse records keep their point count in `start`
+    }
+    occ = __ballot_sync(MLOAM_FULL_MASK, cnt > 0);
+    const int total = __reduce_add_sync(MLOAM_FULL_MASK, cnt);
+    if (REJECT_PARTIAL && coarse_ok && total < K) return;
+  }
   for (int r = 1; r <= rmax; r++) {
     const int s = 2 * r + 1;
     const int ncell = s * s * s;
@@ -123,15 +143,30 @@ __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy,
         const int dy = rem / s - r;
         const int dx = rem % s - r;
         const int cheb = max(max(abs(dx), abs(dy)), abs(dz));
-        if (r == 1 || cheb == r) {  // shells r >= 2 skip the cube already visited
+        bool probe = (r == 1 || cheb == r);  // shells r >= 2 skip the cube already visited
+        if (probe) {
+          const int bx = ((cx + dx) >> MLOAM_COARSE_SHIFT) - ccx, by = ((cy + dy) >> MLOAM_COARSE_SHIFT) - ccy,
+                    bz = ((cz + dz) >> MLOAM_COARSE_SHIFT) - ccz;
+          if (abs(bx) <= 1 && abs(by) <= 1 && abs(bz) <= 1) probe = (occ >> ((bz + 1) * 9 + (by + 1) * 3 + (bx + 1))) & 1u;
+          else if (coarse_ok) probe = false;  // beyond the 27 blocks: farther than the search radius
+        }
+        if (probe) {
           const HashEntry e = hash_lookup(map, pack_cell(cx + dx, cy + dy, cz + dz));
           const float4 *p = map.sorted + e.start;
-          for (int j = 0; j < e.count; j++) {
-            const float4 v = __ldg(p + j);
-            const float ex = v.x - qx, ey = v.y - qy, ez = v.z - qz;
-            const float d2 = ex * ex + ey * ey + ez * ez;
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(v.w);
-            topk_insert(mine, key, e.start + j);
+          for (int j = 0; j < e.count; j += 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = __ldg(p + (j + u < e.count ? j + u : j));  // 4 independent loads in flight
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              if (j + u < e.count) {
+                const float ex = v[u].x - qx, ey = v[u].y - qy, ez = v[u].z - qz;
+                const float d2 = ex * ex + ey * ey + ez * ez;
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(v[u].w);
+                topk_insert(mine, key, e.start + j + u);
+              }
+            }
           }
         }
       }

@@ -31,8 +31,8 @@ __global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_ce
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const float4 p = pts[i];
-  const unsigned long long key =
-      pack_cell((int)floorf(p.x * inv_cell), (int)floorf(p.y * inv_cell), (int)floorf(p.z * inv_cell));
+  const int fx = (int)floorf(p.x * inv_cell), fy = (int)floorf(p.y * inv_cell), fz = (int)floorf(p.z * inv_cell);
+  const unsigned long long key = pack_cell(fx, fy, fz);
   unsigned h = hash_cell(key) & mask;
   while (true) {
     unsigned long long *kp = &table[h].key;
@@ -43,6 +43,18 @@ __global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_ce
   }
   slot_of[i] = (int)h;
   rank_of[i] = atomicAdd(&table[h].count, 1);
+  // Coarse occupancy record of the 4x4x4-cell block this cell belongs to: same table, tagged key, the point
+  // count lives in `start` (its `count` stays 0 so the start-offset scan ignores it).
+  const unsigned long long ckey = coarse_key(fx >> MLOAM_COARSE_SHIFT, fy >> MLOAM_COARSE_SHIFT, fz >> MLOAM_COARSE_SHIFT);
+  unsigned hc = hash_cell(ckey) & mask;
+  while (true) {
+    unsigned long long *kp = &table[hc].key;
+    unsigned long long prev = *kp;
+    if (prev == MLOAM_EMPTY_KEY) prev = atomicCAS(kp, MLOAM_EMPTY_KEY, ckey);
+    if (prev == MLOAM_EMPTY_KEY || prev == ckey) break;
+    hc = (hc + 1) & mask;
+  }
+  atomicAdd(&table[hc].start, 1);
 }
 
 // Exclusive scan of table[].count into table[].start: block totals -> scan of totals -> apply.
@@ -115,7 +127,8 @@ __global__ void k_scan_apply(HashEntry *table, unsigned cap, const int *tile_sum
   int ex = block_exclusive_scan(s, nullptr) + tile_sums[blockIdx.x];
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; k++) {
-    if (base + k < cap) table[base + k].start = ex;
+    // tagged (coarse) and empty records keep their `start` (bit 63 is set in both)
+    if (base + k < cap && !(table[base + k].key & MLOAM_COARSE_TAG)) table[base + k].start = ex;
     ex += c[k];
   }
 }
@@ -144,7 +157,8 @@ int map_build_device(Ctx *c, int slot, const float4 *d_pts, int m, float cell) {
   }
   MapStorage &M = c->maps[slot];
   ProfScope ps(c, "map_build");
-  const unsigned cap = next_pow2((unsigned)(m > 512 ? 2 * (unsigned)m : 1024u));
+  // fine cells + coarse blocks <= 2m records: keep at least two slots empty so every probe sequence terminates
+  const unsigned cap = next_pow2((unsigned)(m > 511 ? 2 * (unsigned)m + 2 : 1024u));
   MLOAM_CUDA_OK(c, M.sorted.reserve(sizeof(float4) * (size_t)(m + 1)));
   MLOAM_CUDA_OK(c, M.orig.reserve(sizeof(float4) * (size_t)(m + 1)));
   MLOAM_CUDA_OK(c, M.table.reserve(sizeof(HashEntry) * (size_t)cap));
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(QWARPS * 32)
   float3 s = make_float3(p.x, p.y, p.z);
   if (pose7) s = associate(pose_from_param(pose7), p.x, p.y, p.z);
   TopK<K> best;
-  warp_knn<K>(map, s.x, s.y, s.z, max_sqdist, lane, best);
+  warp_knn<K, false>(map, s.x, s.y, s.z, max_sqdist, lane, best);
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -245,7 +259,7 @@ __global__ void __launch_bounds__(QWARPS * 32)
   const PoseD T = pose_from_param(pose7);
   const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
   TopK<K> best;
-  warp_knn<K>(map, sel.x, sel.y, sel.z, min_match_sq_dis, lane, best);
+  warp_knn<K, true>(map, sel.x, sel.y, sel.z, min_match_sq_dis, lane, best);
   bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
             __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
   float out[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

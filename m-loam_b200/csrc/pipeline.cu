@@ -59,8 +59,11 @@ int scan2map_run(Ctx *c, const ScanRef &S, const double *pose_init7, double *pos
                                  c->feat_valid[1].as<unsigned char>(), c->feat_coeff[1].as<float>(), nullptr);
       if (rc) return rc;
     }
-    // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve
+    // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve.  The
+    // eigenvalue report is only produced for the last outer iteration (earlier ones just need the decision).
+    c->want_eig = (outer == P.max_outer - 1) ? 1 : 0;
     rc = linearize_device(c, sets, 2, sinfo, P.huber_a, nullptr, 1, 1, nullptr);
+    c->want_eig = 1;
     if (rc) return rc;
     // :586-596 ceres::Solve, at most max_inner LM iterations; the device raises `done`
     for (int it = 0; it < P.max_inner; it++) {

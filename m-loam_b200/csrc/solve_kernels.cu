@@ -16,6 +16,7 @@ namespace mloam {
 constexpr int NE_H = 21, NE_G = 6;
 constexpr int NE_PACK = 30;  // 21 H upper | 6 g | cost | rows(set 0) | rows(set 1)
 constexpr int LIN_THREADS = 256;
+constexpr int LM_THREADS = 256;
 
 struct FeatSetDev {
   const float4 *pts;
@@ -263,14 +264,26 @@ __device__ void unpack_ne(const double *ne, double *H, double *g) {
 }
 
 // mode 1: begin a Solve with the evaluation at x.  mode 2: digest the evaluation at xc.
-__global__ void k_lm(const double *__restrict__ partials, int n_blocks, LMState *st, int mode, double eig_thre,
+__global__ void __launch_bounds__(LM_THREADS) k_lm(const double *__restrict__ partials, int n_blocks, LMState *st, int mode, double eig_thre, int want_eig,
                      double *__restrict__ out_ne) {
+  // block partials -> packed normal equations, in a fixed order (deterministic): warp w sums blocks w, w+8, ...
+  // for component `lane`, then the 8 warp sums are added in warp order.
   __shared__ double ne[NE_PACK];
-  if (threadIdx.x < NE_PACK) {
+  __shared__ double wsum[LM_THREADS / 32][32];
+  {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double v = 0.0;
-    for (int b = 0; b < n_blocks; b++) v += partials[(size_t)b * NE_PACK + threadIdx.x];
-    ne[threadIdx.x] = v;
-    if (out_ne) out_ne[threadIdx.x] = v;
+    if (lane < NE_PACK)
+      for (int b = w; b < n_blocks; b += LM_THREADS / 32) v += partials[(size_t)b * NE_PACK + lane];
+    wsum[w][lane] = v;
+    __syncthreads();
+    if (threadIdx.x < NE_PACK) {
+      double t = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < LM_THREADS / 32; ww++) t += wsum[ww][threadIdx.x];
+      ne[threadIdx.x] = t;
+      if (out_ne) out_ne[threadIdx.x] = t;
+    }
   }
   __syncthreads();
   if (threadIdx.x != 0 || mode == 0) return;
@@ -289,7 +302,16 @@ __global__ void k_lm(const double *__restrict__ partials, int n_blocks, LMState 
     for (int i = 0; i < 36; i++) st->V_update[i] = (i % 7 == 0) ? 1.0 : 0.0;
     st->is_degenerate = 0;
     for (int i = 0; i < 6; i++) st->eig[i] = 0.0;
-    if (st->rows > 0 && eig_thre > 0.0) {
+    // lambda_min(H) > eig_thre  <=>  H - eig_thre*I is positive definite: one 6x6 Cholesky decides the common,
+    // non-degenerate case; the Jacobi eigen-solver only runs when a direction is (nearly) degenerate or when the
+    // caller asked for the eigenvalue report (want_eig: last outer iteration).
+    bool need_eig = st->rows > 0 && eig_thre > 0.0;
+    if (need_eig && !want_eig) {
+      double S[36];
+      for (int i = 0; i < 36; i++) S[i] = H[i] - ((i % 7 == 0) ? eig_thre : 0.0);
+      if (chol6(S)) need_eig = false;
+    }
+    if (need_eig) {
       double w[6], Vf[36], Vp[36];
       eig_sym6(H, w, Vf);
       for (int i = 0; i < 36; i++) Vp[i] = Vf[i];
@@ -402,13 +424,14 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
       a.set[s].pts = nullptr, a.set[s].valid = nullptr, a.set[s].coeff = nullptr, a.set[s].n = 0, a.set[s].is_plane = 0, a.set[s].d_n = nullptr;
     }
   }
+  const int want_eig = c->want_eig;
   a.n_sets = n_sets, a.sqrt_info = sqrt_info, a.huber_a = huber_a, a.pose = d_pose7;
   a.state = c->lm_state.as<LMState>();
   a.use_state = use_state;
   a.respect_done = (lm_mode == 2) ? 1 : 0;
   int nb = (n_total + LIN_THREADS - 1) / LIN_THREADS;
   if (nb < 1) nb = 1;
-  const int max_nb = 2 * c->sm_count;
+  const int max_nb = c->sm_count;
   if (nb > max_nb) nb = max_nb;
   MLOAM_CUDA_OK(c, c->partials.reserve(sizeof(double) * NE_PACK * (size_t)(max_nb + 2)));
   {
@@ -421,17 +444,17 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
     double *ne = c->partials.as<double>() + (size_t)NE_PACK * max_nb;
     {
       ProfScope ps(c, "lm");
-      k_lm<<<1, 32, 0, c->stream>>>(c->partials.as<double>(), nb, c->lm_state.as<LMState>(), 0, 0.0, ne);
+      k_lm<<<1, LM_THREADS, 0, c->stream>>>(c->partials.as<double>(), nb, c->lm_state.as<LMState>(), 0, 0.0, 0, ne);
       c->launches++;
     }
     int rc = comm_allreduce_doubles(c, ne, NE_PACK);
     if (rc) return rc;
     ProfScope ps(c, "lm");
-    k_lm<<<1, 32, 0, c->stream>>>(ne, 1, c->lm_state.as<LMState>(), lm_mode, c->params.eig_thre, d_out30);
+    k_lm<<<1, LM_THREADS, 0, c->stream>>>(ne, 1, c->lm_state.as<LMState>(), lm_mode, c->params.eig_thre, want_eig, d_out30);
     c->launches++;
   } else {
     ProfScope ps(c, "lm");
-    k_lm<<<1, 32, 0, c->stream>>>(c->partials.as<double>(), nb, c->lm_state.as<LMState>(), lm_mode, c->params.eig_thre,
+    k_lm<<<1, LM_THREADS, 0, c->stream>>>(c->partials.as<double>(), nb, c->lm_state.as<LMState>(), lm_mode, c->params.eig_thre, want_eig,
                                   d_out30);
     c->launches++;
   }
