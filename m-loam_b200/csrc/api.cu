@@ -113,7 +113,7 @@ void mloam_ctx_destroy(mloam_ctx_t *h) {
   prof_collect(c);
   for (auto e : c->evt_pool) cudaEventDestroy(e);
   for (auto &m : c->maps) {
-    m.sorted.release(), m.orig.release(), m.table.release(), m.slot_of.release(), m.rank_of.release(), m.scan_tmp.release();
+    m.sorted.release(), m.orig.release(), m.table.release(), m.block_mask.release(), m.slot_of.release(), m.rank_of.release(), m.scan_tmp.release();
   }
   for (int i = 0; i < 2; i++) c->scan_pts[i].release(), c->feat_valid[i].release(), c->feat_coeff[i].release(), c->feat_nn[i].release();
   c->partials.release(), c->lm_state.release();

@@ -115,6 +115,7 @@ struct MapView {
   const float4 *sorted;    // cell-major points: xyz + original index (int bits) in w
   const float4 *orig;      // original order (ring walks of the scan-to-scan matcher)
   const HashEntry *table;
+  const unsigned long long *block_mask;  // per table slot: occupied cells of a 4x4x4 block (valid for block records)
   unsigned mask;           // capacity - 1 (power of two)
   float cell, inv_cell;
   int m;

@@ -36,7 +36,7 @@ struct DevBuf {
 };
 
 struct MapStorage {
-  DevBuf sorted, orig, table, slot_of, rank_of, scan_tmp;
+  DevBuf sorted, orig, table, block_mask, slot_of, rank_of, scan_tmp;
   unsigned capacity = 0;  // hash slots (power of two)
   int m = 0;
   float cell = 0.f;
@@ -46,6 +46,7 @@ struct MapStorage {
     v.sorted = sorted.as<float4>();
     v.orig = orig.as<float4>();
     v.table = table.as<HashEntry>();
+    v.block_mask = block_mask.as<unsigned long long>();
     v.mask = capacity - 1;
     v.cell = cell;
     v.inv_cell = 1.0f / cell;

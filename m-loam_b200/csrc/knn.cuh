@@ -81,7 +81,8 @@ __device__ __forceinline__ void warp_merge(TopK<K> &mine, TopK<K> &out, int lane
   else topk_reset(mine);
 }
 
-__device__ __forceinline__ HashEntry hash_lookup(const MapView &map, unsigned long long key) {
+// Probe the open-addressing table.  *slot (optional) receives the record's slot (or -1).
+__device__ __forceinline__ HashEntry hash_lookup(const MapView &map, unsigned long long key, int *slot = nullptr) {
   unsigned h = hash_cell(key) & map.mask;
   while (true) {
     const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(map.table + h));
@@ -89,25 +90,52 @@ __device__ __forceinline__ HashEntry hash_lookup(const MapView &map, unsigned lo
     if (k == key) {
       HashEntry e;
       e.key = k, e.start = (int)raw.z, e.count = (int)raw.w;
+      if (slot) *slot = (int)h;
       return e;
     }
     if (k == MLOAM_EMPTY_KEY) {
       HashEntry e;
       e.key = k, e.start = 0, e.count = 0;
+      if (slot) *slot = -1;
       return e;
     }
     h = (h + 1) & map.mask;
   }
 }
 
+// Scan one cell's points (contiguous float4 run) into a private top-K, 4 independent loads in flight.
+template <int K>
+__device__ __forceinline__ void scan_cell(const MapView &map, const HashEntry &e, float qx, float qy, float qz, TopK<K> &mine) {
+  const float4 *p = map.sorted + e.start;
+  for (int j = 0; j < e.count; j += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = __ldg(p + (j + u < e.count ? j + u : j));
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (j + u < e.count) {
+        const float ex = v[u].x - qx, ey = v[u].y - qy, ez = v[u].z - qz;
+        const float d2 = ex * ex + ey * ey + ez * ez;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(v[u].w);
+        topk_insert(mine, key, e.start + j + u);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int cell_bit(int fx, int fy, int fz) { return ((fz & 3) << 4) | ((fy & 3) << 2) | (fx & 3); }
+
 // Warp-cooperative search.  All lanes pass the same query; `out` is replicated in every lane.
 //
-// Step 0 consults the coarse occupancy records (4x4x4-cell blocks): the 27 blocks around the query's block are
-// probed by 27 lanes at once.  When a block edge is at least the search radius, those 27 blocks contain every
-// point inside the search ball, so (a) fewer than K points in them means no result can exist (the query is
-// rejected after one round), and (b) cells in empty blocks / outside the 27 blocks are never probed.  This is
-// what keeps the worst case (a feature with no map support, which would otherwise walk all shells) cheap.
-// REJECT_PARTIAL: the caller only wants results when K neighbours exist inside the radius (every matcher gate).
+// Step 0: 27 lanes fetch the occupancy records of the 27 blocks (4x4x4 cells) around the query's block: point
+//   count + a 64-bit mask of occupied cells.  When a block edge is at least the search radius those blocks
+//   contain every point of the search ball, so fewer than K points in them means no result can exist
+//   (REJECT_PARTIAL callers stop after this one round — the fate of a feature with no map support).
+// Ring 1: the 27 cells around the query's cell, one lane per cell, probing only cells whose mask bit is set;
+//   warp-merge; stop if the K-th distance is inside the visited cube (the common case on a dense map).
+// Otherwise: each lane walks the set bits of its own block's mask and visits the cells whose box is closer than
+//   the current bound min(radius^2, K-th distance) — never an empty cell, never a cell outside the ball.
+// If blocks are smaller than the radius (caller chose a tiny cell) the search falls back to plain shells.
 template <int K, bool REJECT_PARTIAL>
 __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy, float qz, float max_sqdist, int lane,
                                          TopK<K> &out) {
@@ -117,22 +145,85 @@ __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy,
   const int cx = (int)floorf(qx * map.inv_cell), cy = (int)floorf(qy * map.inv_cell), cz = (int)floorf(qz * map.inv_cell);
   const float eps = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 8.0f * map.cell) + 1e-6f;
   const float radius = sqrtf(max_sqdist);
-  int rmax = (int)ceilf(radius * map.inv_cell) + 1;
-  if (rmax > 16) rmax = 16;
   const int ccx = cx >> MLOAM_COARSE_SHIFT, ccy = cy >> MLOAM_COARSE_SHIFT, ccz = cz >> MLOAM_COARSE_SHIFT;
   const bool coarse_ok = map.cell * (float)(1 << MLOAM_COARSE_SHIFT) >= radius * 1.0002f + 64.0f * eps;
-  unsigned occ;
+  // ---- step 0: block occupancy
+  unsigned long long bmask = 0ull;
   {
     int cnt = 0;
     if (lane < 27) {
-      const HashEntry e = hash_lookup(map, coarse_key(ccx + lane % 3 - 1, ccy + (lane % 9) / 3 - 1, ccz + lane / 9 - 1));
-      cnt = e.start;  // coarse records keep their point count in `start`
+      int slot;
+      const HashEntry e = hash_lookup(map, coarse_key(ccx + lane % 3 - 1, ccy + (lane % 9) / 3 - 1, ccz + lane / 9 - 1), &slot);
+      cnt = e.start;  // block records keep their point count in `start`
+      if (slot >= 0) bmask = __ldg(map.block_mask + slot);
     }
-    occ = __ballot_sync(MLOAM_FULL_MASK, cnt > 0);
     const int total = __reduce_add_sync(MLOAM_FULL_MASK, cnt);
     if (REJECT_PARTIAL && coarse_ok && total < K) return;
   }
-  for (int r = 1; r <= rmax; r++) {
+  // ---- ring 1
+  {
+    const int dx = lane % 3 - 1, dy = (lane % 9) / 3 - 1, dz = lane / 9 - 1;  // lanes 27..31 idle
+    const int fx = cx + dx, fy = cy + dy, fz = cz + dz;
+    const int bl = ((fz >> MLOAM_COARSE_SHIFT) - ccz + 1) * 9 + ((fy >> MLOAM_COARSE_SHIFT) - ccy + 1) * 3 +
+                   ((fx >> MLOAM_COARSE_SHIFT) - ccx + 1);
+    const unsigned long long m = __shfl_sync(MLOAM_FULL_MASK, bmask, lane < 27 ? bl : 0);
+    if (lane < 27 && ((m >> cell_bit(fx, fy, fz)) & 1ull)) {
+      const HashEntry e = hash_lookup(map, pack_cell(fx, fy, fz));
+      scan_cell<K>(map, e, qx, qy, qz, mine);
+    }
+    warp_merge(mine, out, lane);
+  }
+  auto face_gap = [&](int r) {  // distance from the query to the nearest face of the visited cube [c-r, c+r+1) * cell
+    float g = qx - (float)(cx - r) * map.cell;
+    g = fminf(g, (float)(cx + r + 1) * map.cell - qx);
+    g = fminf(g, qy - (float)(cy - r) * map.cell);
+    g = fminf(g, (float)(cy + r + 1) * map.cell - qy);
+    g = fminf(g, qz - (float)(cz - r) * map.cell);
+    g = fminf(g, (float)(cz + r + 1) * map.cell - qz);
+    return g - eps;
+  };
+  auto kth = [&]() { return __uint_as_float((unsigned)(out.key[K - 1] >> 32)); };
+  {
+    const float g = face_gap(1);
+    if (g > 0.0f) {
+      const float g2 = g * g;
+      if (g2 >= max_sqdist) return;
+      if (out.key[K - 1] != MLOAM_KEY_NONE && kth() < g2) return;
+    }
+  }
+  if (coarse_ok) {
+    // ---- mask-guided completion: lane = block; visit occupied cells closer than the bound
+    float bound = max_sqdist;
+    if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
+    if (lane < 27) {
+      const int B = 1 << MLOAM_COARSE_SHIFT;
+      const int b0x = (ccx + lane % 3 - 1) * B, b0y = (ccy + (lane % 9) / 3 - 1) * B, b0z = (ccz + lane / 9 - 1) * B;
+      unsigned long long m = bmask;
+      while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int fx = b0x + (b & 3), fy = b0y + ((b >> 2) & 3), fz = b0z + (b >> 4);
+        if (abs(fx - cx) <= 1 && abs(fy - cy) <= 1 && abs(fz - cz) <= 1) continue;  // ring 1 already did it
+        // squared distance from q to the cell box (conservative by eps)
+        const float lox = (float)fx * map.cell, loy = (float)fy * map.cell, loz = (float)fz * map.cell;
+        const float gx = fmaxf(fmaxf(lox - qx, qx - (lox + map.cell)) - eps, 0.0f);
+        const float gy = fmaxf(fmaxf(loy - qy, qy - (loy + map.cell)) - eps, 0.0f);
+        const float gz = fmaxf(fmaxf(loz - qz, qz - (loz + map.cell)) - eps, 0.0f);
+        const float md2 = gx * gx + gy * gy + gz * gz;
+        float lb = bound;
+        if (mine.key[K - 1] != MLOAM_KEY_NONE) lb = fminf(lb, __uint_as_float((unsigned)(mine.key[K - 1] >> 32)));
+        if (md2 > lb) continue;  // nothing in this cell can enter the K best (ties at equal distance are kept)
+        const HashEntry e = hash_lookup(map, pack_cell(fx, fy, fz));
+        scan_cell<K>(map, e, qx, qy, qz, mine);
+      }
+    }
+    warp_merge(mine, out, lane);
+    return;
+  }
+  // ---- fallback: plain Chebyshev shells (blocks do not cover the search ball)
+  int rmax = (int)ceilf(radius * map.inv_cell) + 1;
+  if (rmax > 16) rmax = 16;
+  for (int r = 2; r <= rmax; r++) {
     const int s = 2 * r + 1;
     const int ncell = s * s * s;
     for (int base = 0; base < ncell; base += 32) {
@@ -142,48 +233,18 @@ __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy,
         const int rem = c % (s * s);
         const int dy = rem / s - r;
         const int dx = rem % s - r;
-        const int cheb = max(max(abs(dx), abs(dy)), abs(dz));
-        bool probe = (r == 1 || cheb == r);  // shells r >= 2 skip the cube already visited
-        if (probe) {
-          const int bx = ((cx + dx) >> MLOAM_COARSE_SHIFT) - ccx, by = ((cy + dy) >> MLOAM_COARSE_SHIFT) - ccy,
-                    bz = ((cz + dz) >> MLOAM_COARSE_SHIFT) - ccz;
-          if (abs(bx) <= 1 && abs(by) <= 1 && abs(bz) <= 1) probe = (occ >> ((bz + 1) * 9 + (by + 1) * 3 + (bx + 1))) & 1u;
-          else if (coarse_ok) probe = false;  // beyond the 27 blocks: farther than the search radius
-        }
-        if (probe) {
+        if (max(max(abs(dx), abs(dy)), abs(dz)) == r) {
           const HashEntry e = hash_lookup(map, pack_cell(cx + dx, cy + dy, cz + dz));
-          const float4 *p = map.sorted + e.start;
-          for (int j = 0; j < e.count; j += 4) {
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = __ldg(p + (j + u < e.count ? j + u : j));  // 4 independent loads in flight
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              if (j + u < e.count) {
-                const float ex = v[u].x - qx, ey = v[u].y - qy, ez = v[u].z - qz;
-                const float d2 = ex * ex + ey * ey + ez * ez;
-                const unsigned long long key =
-                    ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(v[u].w);
-                topk_insert(mine, key, e.start + j + u);
-              }
-            }
-          }
+          scan_cell<K>(map, e, qx, qy, qz, mine);
         }
       }
     }
     warp_merge(mine, out, lane);
-    // distance from the query to the nearest face of the visited cube [c-r, c+r+1) * cell
-    float g = qx - (float)(cx - r) * map.cell;
-    g = fminf(g, (float)(cx + r + 1) * map.cell - qx);
-    g = fminf(g, qy - (float)(cy - r) * map.cell);
-    g = fminf(g, (float)(cy + r + 1) * map.cell - qy);
-    g = fminf(g, qz - (float)(cz - r) * map.cell);
-    g = fminf(g, (float)(cz + r + 1) * map.cell - qz);
-    g = g - eps;
+    const float g = face_gap(r);
     if (g > 0.0f) {
       const float g2 = g * g;
       if (g2 >= max_sqdist) break;
-      if (out.key[K - 1] != MLOAM_KEY_NONE && __uint_as_float((unsigned)(out.key[K - 1] >> 32)) < g2) break;
+      if (out.key[K - 1] != MLOAM_KEY_NONE && kth() < g2) break;
     }
   }
 }

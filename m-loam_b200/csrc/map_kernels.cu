@@ -15,19 +15,20 @@
 namespace mloam {
 
 // ------------------------------------------------------------------------------------------- build
-__global__ void k_table_clear(HashEntry *table, unsigned cap) {
+__global__ void k_table_clear(HashEntry *table, unsigned long long *block_mask, unsigned cap) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cap) {
     uint4 v;
     v.x = 0xffffffffu, v.y = 0xffffffffu, v.z = 0u, v.w = 0u;
     reinterpret_cast<uint4 *>(table)[i] = v;
+    block_mask[i] = 0ull;
   }
 }
 
 // Pass 1: cell key per point, insert-or-find its slot, count.  rank_of = arrival order inside the cell
 // (only the order of points inside a cell depends on it; results never do — kNN ties break on the index).
-__global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_cell, HashEntry *table, unsigned mask,
-                             int *__restrict__ slot_of, int *__restrict__ rank_of) {
+__global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_cell, HashEntry *table, unsigned long long *block_mask,
+                             unsigned mask, int *__restrict__ slot_of, int *__restrict__ rank_of) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const float4 p = pts[i];
@@ -55,6 +56,8 @@ __global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_ce
     hc = (hc + 1) & mask;
   }
   atomicAdd(&table[hc].start, 1);
+  const unsigned long long bit = 1ull << (((fz & 3) << 4) | ((fy & 3) << 2) | (fx & 3));
+  if (!(block_mask[hc] & bit)) atomicOr(&block_mask[hc], bit);
 }
 
 // Exclusive scan of table[].count into table[].start: block totals -> scan of totals -> apply.
@@ -162,18 +165,19 @@ int map_build_device(Ctx *c, int slot, const float4 *d_pts, int m, float cell) {
   MLOAM_CUDA_OK(c, M.sorted.reserve(sizeof(float4) * (size_t)(m + 1)));
   MLOAM_CUDA_OK(c, M.orig.reserve(sizeof(float4) * (size_t)(m + 1)));
   MLOAM_CUDA_OK(c, M.table.reserve(sizeof(HashEntry) * (size_t)cap));
+  MLOAM_CUDA_OK(c, M.block_mask.reserve(sizeof(unsigned long long) * (size_t)cap));
   MLOAM_CUDA_OK(c, M.slot_of.reserve(sizeof(int) * (size_t)(m + 1)));
   MLOAM_CUDA_OK(c, M.rank_of.reserve(sizeof(int) * (size_t)(m + 1)));
   const int n_tiles = (int)((cap + SCAN_TILE - 1) / SCAN_TILE);
   MLOAM_CUDA_OK(c, M.scan_tmp.reserve(sizeof(int) * (size_t)n_tiles));
   M.capacity = cap, M.m = m, M.cell = cell, M.built = true;
   cudaStream_t st = c->stream;
-  k_table_clear<<<(cap + 255) / 256, 256, 0, st>>>(M.table.as<HashEntry>(), cap);
+  k_table_clear<<<(cap + 255) / 256, 256, 0, st>>>(M.table.as<HashEntry>(), M.block_mask.as<unsigned long long>(), cap);
   c->launches++;
   if (m > 0) {
     const int nb = (m + 255) / 256;
-    k_map_insert<<<nb, 256, 0, st>>>(d_pts, m, 1.0f / cell, M.table.as<HashEntry>(), cap - 1, M.slot_of.as<int>(),
-                                     M.rank_of.as<int>());
+    k_map_insert<<<nb, 256, 0, st>>>(d_pts, m, 1.0f / cell, M.table.as<HashEntry>(), M.block_mask.as<unsigned long long>(), cap - 1,
+                                     M.slot_of.as<int>(), M.rank_of.as<int>());
     k_scan_tile_sums<<<n_tiles, SCAN_THREADS, 0, st>>>(M.table.as<HashEntry>(), cap, M.scan_tmp.as<int>());
     k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(M.scan_tmp.as<int>(), n_tiles);
     k_scan_apply<<<n_tiles, SCAN_THREADS, 0, st>>>(M.table.as<HashEntry>(), cap, M.scan_tmp.as<int>());
@@ -193,20 +197,20 @@ __global__ void __launch_bounds__(QWARPS * 32)
     k_knn(MapView map, const float4 *__restrict__ q, int nq, const double *__restrict__ pose7, float max_sqdist,
           int *__restrict__ idx, float *__restrict__ sqd) {
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * QWARPS + (threadIdx.x >> 5);
-  if (i >= nq) return;
-  const float4 p = __ldg(q + i);
-  float3 s = make_float3(p.x, p.y, p.z);
-  if (pose7) s = associate(pose_from_param(pose7), p.x, p.y, p.z);
-  TopK<K> best;
-  warp_knn<K, false>(map, s.x, s.y, s.z, max_sqdist, lane, best);
-  if (lane == 0) {
+  for (int i = blockIdx.x * QWARPS + (threadIdx.x >> 5); i < nq; i += gridDim.x * QWARPS) {
+    const float4 p = __ldg(q + i);
+    float3 s = make_float3(p.x, p.y, p.z);
+    if (pose7) s = associate(pose_from_param(pose7), p.x, p.y, p.z);
+    TopK<K> best;
+    warp_knn<K, false>(map, s.x, s.y, s.z, max_sqdist, lane, best);
+    if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-      const float d2 = __uint_as_float((unsigned)(best.key[k] >> 32));
-      const bool ok = best.key[k] != MLOAM_KEY_NONE && d2 < max_sqdist;
-      idx[(size_t)i * K + k] = ok ? (int)(unsigned)(best.key[k] & 0xffffffffu) : -1;
-      sqd[(size_t)i * K + k] = ok ? d2 : INFINITY;
+      for (int k = 0; k < K; k++) {
+        const float d2 = __uint_as_float((unsigned)(best.key[k] >> 32));
+        const bool ok = best.key[k] != MLOAM_KEY_NONE && d2 < max_sqdist;
+        idx[(size_t)i * K + k] = ok ? (int)(unsigned)(best.key[k] & 0xffffffffu) : -1;
+        sqd[(size_t)i * K + k] = ok ? d2 : INFINITY;
+      }
     }
   }
 }
@@ -220,7 +224,8 @@ int knn_device(Ctx *c, int slot, const float4 *d_q, int nq, const double *d_pose
   if (nq <= 0) return MLOAM_OK;
   ProfScope ps(c, "knn");
   MapView mv = c->maps[slot].view();
-  const int nb = (nq + QWARPS - 1) / QWARPS;
+  int nb = (nq + QWARPS - 1) / QWARPS;
+  if (nb > 8 * c->sm_count) nb = 8 * c->sm_count;  // warps stride over the queries
   cudaStream_t st = c->stream;
   switch (k) {
     case 1: k_knn<1><<<nb, QWARPS * 32, 0, st>>>(mv, d_q, nq, d_pose7, max_sqdist, d_idx, d_sqd); break;
@@ -252,11 +257,11 @@ __global__ void __launch_bounds__(QWARPS * 32)
             float min_match_sq_dis, float min_plane_dis, int check_fov, unsigned char *__restrict__ valid,
             float *__restrict__ coeff, int *__restrict__ nn) {
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * QWARPS + (threadIdx.x >> 5);
   if (d_n) n = min(n, *d_n);  // feature count produced on the device (no host round trip)
-  if (i >= n) return;
-  const float4 p = __ldg(pts + i);
   const PoseD T = pose_from_param(pose7);
+  // warps stride over the features: the grid is sized for the SM count, not for the (loose) upper bound
+  for (int i = blockIdx.x * QWARPS + (threadIdx.x >> 5); i < n; i += gridDim.x * QWARPS) {
+  const float4 p = __ldg(pts + i);
   const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
   TopK<K> best;
   warp_knn<K, true>(map, sel.x, sel.y, sel.z, min_match_sq_dis, lane, best);
@@ -319,6 +324,7 @@ __global__ void __launch_bounds__(QWARPS * 32)
         nn[(size_t)i * K + j] = (ok && best.key[j] != MLOAM_KEY_NONE) ? (int)(unsigned)(best.key[j] & 0xffffffffu) : -1;
     }
   }
+  }  // feature loop
 }
 
 int match_from_map_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const int *d_n, const double *d_pose7,
@@ -334,9 +340,10 @@ int match_from_map_device(Ctx *c, int slot, int type, const float4 *d_pts, int n
   if (n <= 0) return MLOAM_OK;
   ProfScope ps(c, "match");
   MapView mv = c->maps[slot].view();
-  const int nb = (n + QWARPS - 1) / QWARPS;
+  int nb = (n + QWARPS - 1) / QWARPS;
+  if (nb > 8 * c->sm_count) nb = 8 * c->sm_count;  // 8 CTAs x 8 warps per SM; warps stride over the features
   cudaStream_t st = c->stream;
-#define MLOAM_LAUNCH_MATCH(KK, PL)                                                                                      \
+#define MLOAM_LAUNCH_MATCH(KK, PL)                                                                                     \
   k_match<KK, PL><<<nb, QWARPS * 32, 0, st>>>(mv, d_pts, n, d_n, d_pose7, cfg.min_match_sq_dis, cfg.min_plane_dis, cfg.check_fov, \
                                               d_valid, d_coeff, d_nn)
   if (cfg.n_neigh == 5) {
