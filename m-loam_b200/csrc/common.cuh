@@ -136,12 +136,13 @@ __host__ __device__ inline unsigned long long coarse_key(int cx, int cy, int cz)
   return pack_cell(cx, cy, cz) | MLOAM_COARSE_TAG;
 }
 __host__ __device__ inline unsigned hash_cell(unsigned long long k) {
-  k ^= k >> 33;
-  k *= 0xff51afd7ed558ccdull;
-  k ^= k >> 33;
-  k *= 0xc4ceb9fe1a85ec53ull;
-  k ^= k >> 33;
-  return (unsigned)k;
+  // classic 3-prime spatial hash on the 21-bit cell coordinates (3 IMAD + folds; the table load is <= 0.5 so
+  // linear probing stays short), block records are displaced by the tag bit
+  const unsigned x = (unsigned)(k >> 42) & 0x1fffffu, y = (unsigned)(k >> 21) & 0x1fffffu, z = (unsigned)k & 0x1fffffu;
+  unsigned h = (x * 73856093u) ^ (y * 19349663u) ^ (z * 83492791u);
+  h ^= (unsigned)(k >> 63) * 0x9e3779b9u;
+  h ^= h >> 15;
+  return h;
 }
 
 // ------------------------------------------------------------------ LM state (device resident)

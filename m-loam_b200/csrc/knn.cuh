@@ -195,26 +195,47 @@ __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy,
     // ---- mask-guided completion: lane = block; visit occupied cells closer than the bound
     float bound = max_sqdist;
     if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
-    if (lane < 27) {
-      const int B = 1 << MLOAM_COARSE_SHIFT;
+    const int B = 1 << MLOAM_COARSE_SHIFT;
+    // (a) each lane (= block) selects, with ALU work only, its occupied cells whose box is within the bound
+    unsigned long long cand = 0ull;
+    if (lane < 27 && bmask) {
       const int b0x = (ccx + lane % 3 - 1) * B, b0y = (ccy + (lane % 9) / 3 - 1) * B, b0z = (ccz + lane / 9 - 1) * B;
-      unsigned long long m = bmask;
+      const float bw = map.cell * (float)B;
+      const float bgx = fmaxf(fmaxf((float)b0x * map.cell - qx, qx - ((float)b0x * map.cell + bw)) - eps, 0.0f);
+      const float bgy = fmaxf(fmaxf((float)b0y * map.cell - qy, qy - ((float)b0y * map.cell + bw)) - eps, 0.0f);
+      const float bgz = fmaxf(fmaxf((float)b0z * map.cell - qz, qz - ((float)b0z * map.cell + bw)) - eps, 0.0f);
+      if (bgx * bgx + bgy * bgy + bgz * bgz <= bound) {  // the block itself reaches into the ball
+        unsigned long long m = bmask;
+        while (m) {
+          const int b = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          const int fx = b0x + (b & 3), fy = b0y + ((b >> 2) & 3), fz = b0z + (b >> 4);
+          if (abs(fx - cx) <= 1 && abs(fy - cy) <= 1 && abs(fz - cz) <= 1) continue;  // ring 1 already did it
+          // squared distance from q to the cell box (conservative by eps)
+          const float lox = (float)fx * map.cell, loy = (float)fy * map.cell, loz = (float)fz * map.cell;
+          const float gx = fmaxf(fmaxf(lox - qx, qx - (lox + map.cell)) - eps, 0.0f);
+          const float gy = fmaxf(fmaxf(loy - qy, qy - (loy + map.cell)) - eps, 0.0f);
+          const float gz = fmaxf(fmaxf(loz - qz, qz - (loz + map.cell)) - eps, 0.0f);
+          if (gx * gx + gy * gy + gz * gz <= bound) cand |= 1ull << b;  // ties at equal distance are kept
+        }
+      }
+    }
+    // (b) the warp walks the blocks; the selected cells of a block are spread over the lanes (one cell per lane)
+    const unsigned nonempty = __ballot_sync(MLOAM_FULL_MASK, cand != 0ull);
+    for (unsigned todo = nonempty; todo; todo &= todo - 1) {
+      const int bl = __ffs(todo) - 1;
+      unsigned long long m = __shfl_sync(MLOAM_FULL_MASK, cand, bl);
+      const int b0x = (ccx + bl % 3 - 1) * B, b0y = (ccy + (bl % 9) / 3 - 1) * B, b0z = (ccz + bl / 9 - 1) * B;
       while (m) {
-        const int b = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const int fx = b0x + (b & 3), fy = b0y + ((b >> 2) & 3), fz = b0z + (b >> 4);
-        if (abs(fx - cx) <= 1 && abs(fy - cy) <= 1 && abs(fz - cz) <= 1) continue;  // ring 1 already did it
-        // squared distance from q to the cell box (conservative by eps)
-        const float lox = (float)fx * map.cell, loy = (float)fy * map.cell, loz = (float)fz * map.cell;
-        const float gx = fmaxf(fmaxf(lox - qx, qx - (lox + map.cell)) - eps, 0.0f);
-        const float gy = fmaxf(fmaxf(loy - qy, qy - (loy + map.cell)) - eps, 0.0f);
-        const float gz = fmaxf(fmaxf(loz - qz, qz - (loz + map.cell)) - eps, 0.0f);
-        const float md2 = gx * gx + gy * gy + gz * gz;
-        float lb = bound;
-        if (mine.key[K - 1] != MLOAM_KEY_NONE) lb = fminf(lb, __uint_as_float((unsigned)(mine.key[K - 1] >> 32)));
-        if (md2 > lb) continue;  // nothing in this cell can enter the K best (ties at equal distance are kept)
-        const HashEntry e = hash_lookup(map, pack_cell(fx, fy, fz));
-        scan_cell<K>(map, e, qx, qy, qz, mine);
+        const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+        const int nlo = __popc(lo), cnt = nlo + __popc(hi);
+        if (lane < cnt) {
+          const int b = lane < nlo ? (int)__fns(lo, 0, lane + 1) : 32 + (int)__fns(hi, 0, lane - nlo + 1);
+          const HashEntry e = hash_lookup(map, pack_cell(b0x + (b & 3), b0y + ((b >> 2) & 3), b0z + (b >> 4)));
+          scan_cell<K>(map, e, qx, qy, qz, mine);
+        }
+        if (cnt <= 32) break;
+        for (int t = 0; t < 32; t++) m &= m - 1;  // drop the 32 cells just handled
       }
     }
     warp_merge(mine, out, lane);
