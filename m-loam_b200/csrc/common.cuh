@@ -176,6 +176,7 @@ struct LMState {
   int n_valid[2];          // matched corner / surf features
   int max_inner;
   int pad;
+  int work[2];             // dynamic work-queue heads of the corner / surf match launches (reset by k_lm)
 };
 
 }  // namespace mloam

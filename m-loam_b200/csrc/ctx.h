@@ -134,7 +134,7 @@ int knn_device(Ctx *c, int slot, const float4 *d_q, int nq, const double *d_pose
 // type 'c' / 's'.  d_pose7 device pointer to 7 doubles.  Outputs: valid[n], coeff[n*6] float, nn[n*n_neigh] (nullable)
 // d_n (nullable): device-side feature count, n is then the launch upper bound.
 int match_from_map_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const int *d_n, const double *d_pose7,
-                          const MatchCfg &cfg, unsigned char *d_valid, float *d_coeff, int *d_nn);
+                          const MatchCfg &cfg, unsigned char *d_valid, float *d_coeff, int *d_nn, int *d_work = nullptr);
 
 // solve_kernels.cu
 struct FeatSet {

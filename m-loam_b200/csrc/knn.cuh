@@ -6,11 +6,21 @@
 // to points with d2 < max_sqdist — which is all the callers look at: every reference caller rejects the
 // query unless sqdist[K-1] < MIN_MATCH_SQ_DIS (or sqdist[0] < DISTANCE_SQ_THRESHOLD for K=1).
 //
-// Search: cells are visited in Chebyshev shells around the query's cell.  In a shell each lane owns one
-// cell: it probes the hash (one 16 B load) and scans that cell's points (contiguous float4, L1-resident
-// after the first touch) into a private sorted top-K.  After a shell the 32 private lists are merged with
-// warp reductions; the search stops when the K-th distance is below the distance to the faces of the cube
-// visited so far (nothing outside can be closer), or when that face distance exceeds the search radius.
+// Search plan per query (all 32 lanes cooperate, `out` is the warp-wide best K, replicated in every lane):
+//   step 0  27 lanes fetch the occupancy records of the 27 blocks (4x4x4 cells) around the query's block: point
+//           count + 64-bit mask of occupied cells.  When a block edge is at least the search radius those blocks
+//           contain every point of the search ball, so fewer than K points in them means no result can exist
+//           (REJECT_PARTIAL callers stop here: the fate of a feature with no map support).
+//   ring 1  the 27 cells around the query's cell, one lane per cell, probing only cells whose mask bit is set.
+//           The cells' point runs (start, count) go to a per-warp shared-memory run table; the points of ALL runs
+//           are then scanned as one flat list, 4 per lane per step (independent 16 B loads, perfectly balanced),
+//           and reduced with a warp-wide K-selection (no per-lane sorted lists, no divergent insertion sort).
+//           Stop if the K-th distance is inside the visited cube — the common case on a dense map.
+//   finish  otherwise walk the non-empty blocks whose box reaches into the current bound min(radius^2, K-th):
+//           lanes test cells l and l+32 of the block's mask against the bound, probe the survivors, pack their
+//           runs into the run table (flushed through the same flat scan) — never an empty cell, never a cell
+//           outside the ball.
+// If blocks are smaller than the radius (caller chose a tiny cell) the finish falls back to plain shells.
 #pragma once
 #include "common.cuh"
 
@@ -20,7 +30,7 @@ namespace mloam {
 
 template <int K>
 struct TopK {
-  unsigned long long key[K];  // (float bits of d2) << 32 | original index
+  unsigned long long key[K];  // (float bits of d2) << 32 | original index, ascending
   int pos[K];                 // position in MapView::sorted
 };
 
@@ -30,24 +40,12 @@ __device__ __forceinline__ void topk_reset(TopK<K> &t) {
   for (int i = 0; i < K; i++) t.key[i] = MLOAM_KEY_NONE, t.pos[i] = -1;
 }
 
-template <int K>
-__device__ __forceinline__ void topk_insert(TopK<K> &t, unsigned long long key, int pos) {
-  if (key < t.key[K - 1]) {
-    t.key[K - 1] = key;
-    t.pos[K - 1] = pos;
-#pragma unroll
-    for (int i = K - 1; i > 0; --i) {
-      if (t.key[i] < t.key[i - 1]) {
-        unsigned long long tk = t.key[i];
-        t.key[i] = t.key[i - 1];
-        t.key[i - 1] = tk;
-        int tp = t.pos[i];
-        t.pos[i] = t.pos[i - 1];
-        t.pos[i - 1] = tp;
-      }
-    }
-  }
-}
+// Per-warp run table (shared memory): run r = points [start[r], start[r] + count) with pref[r] = points before it.
+constexpr int KNN_RUNS = 64;
+struct RunBuf {
+  int start[KNN_RUNS];
+  int pref[KNN_RUNS];
+};
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
   unsigned hi = (unsigned)(v >> 32);
@@ -57,28 +55,85 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   return ((unsigned long long)mh << 32) | ml;
 }
 
-// Merge the 32 private lists into the warp-wide top-K.  On return lane 0 holds the merged list and every
-// other lane an empty one (the union of private lists stays the best K seen so far); `out` is replicated.
-template <int K>
-__device__ __forceinline__ void warp_merge(TopK<K> &mine, TopK<K> &out, int lane) {
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int *total) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(MLOAM_FULL_MASK, inc, o);
+    if (lane >= o) inc += t;
+  }
+  *total = __shfl_sync(MLOAM_FULL_MASK, inc, 31);
+  return inc - v;
+}
+
+// Warp-wide selection: new best K = the K smallest of (current best) U (NC candidates per lane).
+template <int K, int NC>
+__device__ __forceinline__ void warp_select(unsigned long long (&ck)[NC], int (&cp)[NC], TopK<K> &out, int lane) {
+  // cheap exit: nothing beats the current K-th
+  unsigned long long cmin = ck[0];
+#pragma unroll
+  for (int u = 1; u < NC; u++) cmin = ck[u] < cmin ? ck[u] : cmin;
+  if (!__any_sync(MLOAM_FULL_MASK, cmin < out.key[K - 1])) return;
+  // the current best joins as one extra candidate in lanes 0..K-1
+  unsigned long long ek = MLOAM_KEY_NONE;
+  int ep = -1;
+#pragma unroll
+  for (int i = 0; i < K; i++)
+    if (lane == i) ek = out.key[i], ep = out.pos[i];
 #pragma unroll
   for (int r = 0; r < K; r++) {
-    unsigned long long cur = mine.key[0];
-    unsigned long long m = warp_min_u64(cur);
-    unsigned owners = __ballot_sync(MLOAM_FULL_MASK, cur == m);
-    int src = __ffs(owners) - 1;
-    int p = __shfl_sync(MLOAM_FULL_MASK, mine.pos[0], src);
+    unsigned long long lm = ek;
+    int lp = ep, which = NC;
+#pragma unroll
+    for (int u = 0; u < NC; u++)
+      if (ck[u] < lm) lm = ck[u], lp = cp[u], which = u;
+    const unsigned long long m = warp_min_u64(lm);
+    const unsigned owners = __ballot_sync(MLOAM_FULL_MASK, lm == m);
+    const int src = __ffs(owners) - 1;
+    const int p = __shfl_sync(MLOAM_FULL_MASK, lp, src);
     out.key[r] = m;
     out.pos[r] = (m == MLOAM_KEY_NONE) ? -1 : p;
-    if (lane == src && m != MLOAM_KEY_NONE) {  // pop
+    if (lane == src && m != MLOAM_KEY_NONE) {  // keys are unique (they embed the point index): one owner
+      if (which == NC) ek = MLOAM_KEY_NONE;
 #pragma unroll
-      for (int i = 0; i < K - 1; i++) mine.key[i] = mine.key[i + 1], mine.pos[i] = mine.pos[i + 1];
-      mine.key[K - 1] = MLOAM_KEY_NONE;
-      mine.pos[K - 1] = -1;
+      for (int u = 0; u < NC; u++)
+        if (which == u) ck[u] = MLOAM_KEY_NONE;
     }
   }
-  if (lane == 0) mine = out;
-  else topk_reset(mine);
+}
+
+// Scan the flat concatenation of the runs in `rb` (N = padded table size, 32 or 64; `total` points) into `out`.
+template <int K, int N>
+__device__ __forceinline__ void scan_runs(const MapView &map, const RunBuf &rb, int total, float qx, float qy, float qz,
+                                          int lane, TopK<K> &out) {
+  for (int base = 0; base < total; base += 128) {
+    unsigned long long ck[4];
+    int cp[4];
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int t = base + u * 32 + lane;
+      cp[u] = -1;
+      if (t < total) {
+        int r = 0;
+#pragma unroll
+        for (int step = N / 2; step > 0; step >>= 1)
+          if (rb.pref[r + step] <= t) r += step;  // largest r with pref[r] <= t (empty runs share a prefix value)
+        cp[u] = rb.start[r] + (t - rb.pref[r]);
+        v[u] = __ldg(map.sorted + cp[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      ck[u] = MLOAM_KEY_NONE;
+      if (cp[u] >= 0) {
+        const float ex = v[u].x - qx, ey = v[u].y - qy, ez = v[u].z - qz;
+        const float d2 = ex * ex + ey * ey + ez * ez;
+        ck[u] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(v[u].w);
+      }
+    }
+    warp_select<K, 4>(ck, cp, out, lane);
+  }
 }
 
 // Probe the open-addressing table.  *slot (optional) receives the record's slot (or -1).
@@ -103,50 +158,20 @@ __device__ __forceinline__ HashEntry hash_lookup(const MapView &map, unsigned lo
   }
 }
 
-// Scan one cell's points (contiguous float4 run) into a private top-K, 4 independent loads in flight.
-template <int K>
-__device__ __forceinline__ void scan_cell(const MapView &map, const HashEntry &e, float qx, float qy, float qz, TopK<K> &mine) {
-  const float4 *p = map.sorted + e.start;
-  for (int j = 0; j < e.count; j += 4) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) v[u] = __ldg(p + (j + u < e.count ? j + u : j));
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (j + u < e.count) {
-        const float ex = v[u].x - qx, ey = v[u].y - qy, ez = v[u].z - qz;
-        const float d2 = ex * ex + ey * ey + ez * ez;
-        const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(v[u].w);
-        topk_insert(mine, key, e.start + j + u);
-      }
-    }
-  }
-}
-
 __device__ __forceinline__ int cell_bit(int fx, int fy, int fz) { return ((fz & 3) << 4) | ((fy & 3) << 2) | (fx & 3); }
 
-// Warp-cooperative search.  All lanes pass the same query; `out` is replicated in every lane.
-//
-// Step 0: 27 lanes fetch the occupancy records of the 27 blocks (4x4x4 cells) around the query's block: point
-//   count + a 64-bit mask of occupied cells.  When a block edge is at least the search radius those blocks
-//   contain every point of the search ball, so fewer than K points in them means no result can exist
-//   (REJECT_PARTIAL callers stop after this one round — the fate of a feature with no map support).
-// Ring 1: the 27 cells around the query's cell, one lane per cell, probing only cells whose mask bit is set;
-//   warp-merge; stop if the K-th distance is inside the visited cube (the common case on a dense map).
-// Otherwise: each lane walks the set bits of its own block's mask and visits the cells whose box is closer than
-//   the current bound min(radius^2, K-th distance) — never an empty cell, never a cell outside the ball.
-// If blocks are smaller than the radius (caller chose a tiny cell) the search falls back to plain shells.
+// REJECT_PARTIAL: the caller only wants results when K neighbours exist inside the radius (every matcher gate).
+// rb: this warp's run table in shared memory.
 template <int K, bool REJECT_PARTIAL>
-__device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy, float qz, float max_sqdist, int lane,
+__device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float qx, float qy, float qz, float max_sqdist, int lane,
                                          TopK<K> &out) {
-  TopK<K> mine;
-  topk_reset(mine);
   topk_reset(out);
   const int cx = (int)floorf(qx * map.inv_cell), cy = (int)floorf(qy * map.inv_cell), cz = (int)floorf(qz * map.inv_cell);
   const float eps = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 8.0f * map.cell) + 1e-6f;
   const float radius = sqrtf(max_sqdist);
+  const int B = 1 << MLOAM_COARSE_SHIFT;
   const int ccx = cx >> MLOAM_COARSE_SHIFT, ccy = cy >> MLOAM_COARSE_SHIFT, ccz = cz >> MLOAM_COARSE_SHIFT;
-  const bool coarse_ok = map.cell * (float)(1 << MLOAM_COARSE_SHIFT) >= radius * 1.0002f + 64.0f * eps;
+  const bool coarse_ok = map.cell * (float)B >= radius * 1.0002f + 64.0f * eps;
   // ---- step 0: block occupancy
   unsigned long long bmask = 0ull;
   {
@@ -167,11 +192,18 @@ __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy,
     const int bl = ((fz >> MLOAM_COARSE_SHIFT) - ccz + 1) * 9 + ((fy >> MLOAM_COARSE_SHIFT) - ccy + 1) * 3 +
                    ((fx >> MLOAM_COARSE_SHIFT) - ccx + 1);
     const unsigned long long m = __shfl_sync(MLOAM_FULL_MASK, bmask, lane < 27 ? bl : 0);
+    int start = 0, count = 0;
     if (lane < 27 && ((m >> cell_bit(fx, fy, fz)) & 1ull)) {
       const HashEntry e = hash_lookup(map, pack_cell(fx, fy, fz));
-      scan_cell<K>(map, e, qx, qy, qz, mine);
+      start = e.start, count = e.count;
     }
-    warp_merge(mine, out, lane);
+    int total;
+    const int excl = warp_excl_scan(count, lane, &total);
+    __syncwarp();
+    rb.start[lane] = start;
+    rb.pref[lane] = excl;
+    __syncwarp();
+    scan_runs<K, 32>(map, rb, total, qx, qy, qz, lane, out);
   }
   auto face_gap = [&](int r) {  // distance from the query to the nearest face of the visited cube [c-r, c+r+1) * cell
     float g = qx - (float)(cx - r) * map.cell;
@@ -192,53 +224,72 @@ __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy,
     }
   }
   if (coarse_ok) {
-    // ---- mask-guided completion: lane = block; visit occupied cells closer than the bound
+    // ---- finish with the block masks
     float bound = max_sqdist;
     if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
-    const int B = 1 << MLOAM_COARSE_SHIFT;
-    // (a) each lane (= block) selects, with ALU work only, its occupied cells whose box is within the bound
-    unsigned long long cand = 0ull;
+    // blocks that are non-empty and whose box reaches into the bound (ties at equal distance are kept)
+    bool reach = false;
     if (lane < 27 && bmask) {
-      const int b0x = (ccx + lane % 3 - 1) * B, b0y = (ccy + (lane % 9) / 3 - 1) * B, b0z = (ccz + lane / 9 - 1) * B;
       const float bw = map.cell * (float)B;
-      const float bgx = fmaxf(fmaxf((float)b0x * map.cell - qx, qx - ((float)b0x * map.cell + bw)) - eps, 0.0f);
-      const float bgy = fmaxf(fmaxf((float)b0y * map.cell - qy, qy - ((float)b0y * map.cell + bw)) - eps, 0.0f);
-      const float bgz = fmaxf(fmaxf((float)b0z * map.cell - qz, qz - ((float)b0z * map.cell + bw)) - eps, 0.0f);
-      if (bgx * bgx + bgy * bgy + bgz * bgz <= bound) {  // the block itself reaches into the ball
-        unsigned long long m = bmask;
-        while (m) {
-          const int b = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          const int fx = b0x + (b & 3), fy = b0y + ((b >> 2) & 3), fz = b0z + (b >> 4);
-          if (abs(fx - cx) <= 1 && abs(fy - cy) <= 1 && abs(fz - cz) <= 1) continue;  // ring 1 already did it
-          // squared distance from q to the cell box (conservative by eps)
+      const float x0 = (float)((ccx + lane % 3 - 1) * B) * map.cell, y0 = (float)((ccy + (lane % 9) / 3 - 1) * B) * map.cell,
+                  z0 = (float)((ccz + lane / 9 - 1) * B) * map.cell;
+      const float gx = fmaxf(fmaxf(x0 - qx, qx - (x0 + bw)) - eps, 0.0f);
+      const float gy = fmaxf(fmaxf(y0 - qy, qy - (y0 + bw)) - eps, 0.0f);
+      const float gz = fmaxf(fmaxf(z0 - qz, qz - (z0 + bw)) - eps, 0.0f);
+      reach = gx * gx + gy * gy + gz * gz <= bound;
+    }
+    int nr = 0, npts = 0;  // runs / points currently in the table (warp-uniform)
+    __syncwarp();          // ring 1 is done reading the table
+    for (unsigned todo = __ballot_sync(MLOAM_FULL_MASK, reach); todo; todo &= todo - 1) {
+      const int bl = __ffs(todo) - 1;
+      const unsigned long long m = __shfl_sync(MLOAM_FULL_MASK, bmask, bl);
+      const int b0x = (ccx + bl % 3 - 1) * B, b0y = (ccy + (bl % 9) / 3 - 1) * B, b0z = (ccz + bl / 9 - 1) * B;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const int b = lane + 32 * half;  // this lane's cell of the block
+        bool take = (m >> b) & 1ull;
+        const int fx = b0x + (b & 3), fy = b0y + ((b >> 2) & 3), fz = b0z + (b >> 4);
+        if (take && abs(fx - cx) <= 1 && abs(fy - cy) <= 1 && abs(fz - cz) <= 1) take = false;  // ring 1 did it
+        if (take) {
           const float lox = (float)fx * map.cell, loy = (float)fy * map.cell, loz = (float)fz * map.cell;
           const float gx = fmaxf(fmaxf(lox - qx, qx - (lox + map.cell)) - eps, 0.0f);
           const float gy = fmaxf(fmaxf(loy - qy, qy - (loy + map.cell)) - eps, 0.0f);
           const float gz = fmaxf(fmaxf(loz - qz, qz - (loz + map.cell)) - eps, 0.0f);
-          if (gx * gx + gy * gy + gz * gz <= bound) cand |= 1ull << b;  // ties at equal distance are kept
+          take = gx * gx + gy * gy + gz * gz <= bound;
         }
+        const unsigned tk = __ballot_sync(MLOAM_FULL_MASK, take);
+        if (!tk) continue;
+        const int ncell = __popc(tk);
+        if (nr + ncell > KNN_RUNS) {  // flush the table through the flat scan
+          __syncwarp();
+          for (int r = nr + lane; r < KNN_RUNS; r += 32) rb.pref[r] = npts;
+          __syncwarp();
+          scan_runs<K, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
+          if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
+          nr = 0, npts = 0;
+          __syncwarp();
+        }
+        int start = 0, count = 0;
+        if (take) {
+          const HashEntry e = hash_lookup(map, pack_cell(fx, fy, fz));
+          start = e.start, count = e.count;
+        }
+        int tot;
+        const int excl = warp_excl_scan(count, lane, &tot);
+        if (take) {
+          const int slot = nr + __popc(tk & ((1u << lane) - 1u));
+          rb.start[slot] = start;
+          rb.pref[slot] = npts + excl;
+        }
+        nr += ncell, npts += tot;
       }
     }
-    // (b) the warp walks the blocks; the selected cells of a block are spread over the lanes (one cell per lane)
-    const unsigned nonempty = __ballot_sync(MLOAM_FULL_MASK, cand != 0ull);
-    for (unsigned todo = nonempty; todo; todo &= todo - 1) {
-      const int bl = __ffs(todo) - 1;
-      unsigned long long m = __shfl_sync(MLOAM_FULL_MASK, cand, bl);
-      const int b0x = (ccx + bl % 3 - 1) * B, b0y = (ccy + (bl % 9) / 3 - 1) * B, b0z = (ccz + bl / 9 - 1) * B;
-      while (m) {
-        const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
-        const int nlo = __popc(lo), cnt = nlo + __popc(hi);
-        if (lane < cnt) {
-          const int b = lane < nlo ? (int)__fns(lo, 0, lane + 1) : 32 + (int)__fns(hi, 0, lane - nlo + 1);
-          const HashEntry e = hash_lookup(map, pack_cell(b0x + (b & 3), b0y + ((b >> 2) & 3), b0z + (b >> 4)));
-          scan_cell<K>(map, e, qx, qy, qz, mine);
-        }
-        if (cnt <= 32) break;
-        for (int t = 0; t < 32; t++) m &= m - 1;  // drop the 32 cells just handled
-      }
+    if (nr > 0) {
+      __syncwarp();
+      for (int r = nr + lane; r < KNN_RUNS; r += 32) rb.pref[r] = npts;
+      __syncwarp();
+      scan_runs<K, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
     }
-    warp_merge(mine, out, lane);
     return;
   }
   // ---- fallback: plain Chebyshev shells (blocks do not cover the search ball)
@@ -249,6 +300,7 @@ __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy,
     const int ncell = s * s * s;
     for (int base = 0; base < ncell; base += 32) {
       const int c = base + lane;
+      int start = 0, count = 0;
       if (c < ncell) {
         const int dz = c / (s * s) - r;
         const int rem = c % (s * s);
@@ -256,11 +308,18 @@ __device__ __forceinline__ void warp_knn(const MapView &map, float qx, float qy,
         const int dx = rem % s - r;
         if (max(max(abs(dx), abs(dy)), abs(dz)) == r) {
           const HashEntry e = hash_lookup(map, pack_cell(cx + dx, cy + dy, cz + dz));
-          scan_cell<K>(map, e, qx, qy, qz, mine);
+          start = e.start, count = e.count;
         }
       }
+      int total;
+      const int excl = warp_excl_scan(count, lane, &total);
+      if (total == 0) continue;
+      __syncwarp();
+      rb.start[lane] = start;
+      rb.pref[lane] = excl;
+      __syncwarp();
+      scan_runs<K, 32>(map, rb, total, qx, qy, qz, lane, out);
     }
-    warp_merge(mine, out, lane);
     const float g = face_gap(r);
     if (g > 0.0f) {
       const float g2 = g * g;

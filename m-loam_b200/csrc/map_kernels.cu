@@ -196,13 +196,14 @@ template <int K>
 __global__ void __launch_bounds__(QWARPS * 32)
     k_knn(MapView map, const float4 *__restrict__ q, int nq, const double *__restrict__ pose7, float max_sqdist,
           int *__restrict__ idx, float *__restrict__ sqd) {
+  __shared__ RunBuf rbuf[QWARPS];
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * QWARPS + (threadIdx.x >> 5); i < nq; i += gridDim.x * QWARPS) {
     const float4 p = __ldg(q + i);
     float3 s = make_float3(p.x, p.y, p.z);
     if (pose7) s = associate(pose_from_param(pose7), p.x, p.y, p.z);
     TopK<K> best;
-    warp_knn<K, false>(map, s.x, s.y, s.z, max_sqdist, lane, best);
+    warp_knn<K, false>(map, rbuf[threadIdx.x >> 5], s.x, s.y, s.z, max_sqdist, lane, best);
     if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < K; k++) {
@@ -255,16 +256,26 @@ template <int K, bool IS_PLANE>
 __global__ void __launch_bounds__(QWARPS * 32)
     k_match(MapView map, const float4 *__restrict__ pts, int n, const int *__restrict__ d_n, const double *__restrict__ pose7,
             float min_match_sq_dis, float min_plane_dis, int check_fov, unsigned char *__restrict__ valid,
-            float *__restrict__ coeff, int *__restrict__ nn) {
+            float *__restrict__ coeff, int *__restrict__ nn, int *__restrict__ work) {
+  __shared__ RunBuf rbuf[QWARPS];
   const int lane = threadIdx.x & 31;
   if (d_n) n = min(n, *d_n);  // feature count produced on the device (no host round trip)
   const PoseD T = pose_from_param(pose7);
-  // warps stride over the features: the grid is sized for the SM count, not for the (loose) upper bound
-  for (int i = blockIdx.x * QWARPS + (threadIdx.x >> 5); i < n; i += gridDim.x * QWARPS) {
+  // The grid is sized for the SM count, not for the (loose) upper bound.  With a work-queue head (`work`, zeroed
+  // by k_lm between launches) every warp pulls the next feature when it finishes one, so a long query (sparse
+  // neighbourhood) does not stall a whole wave; without one, warps stride statically.
+  int i = blockIdx.x * QWARPS + (threadIdx.x >> 5);
+  while (true) {
+  if (work) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(work, 1);
+    i = __shfl_sync(MLOAM_FULL_MASK, t, 0);
+  }
+  if (i >= n) break;
   const float4 p = __ldg(pts + i);
   const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
   TopK<K> best;
-  warp_knn<K, true>(map, sel.x, sel.y, sel.z, min_match_sq_dis, lane, best);
+  warp_knn<K, true>(map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best);
   bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
             __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
   float out[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -324,11 +335,12 @@ __global__ void __launch_bounds__(QWARPS * 32)
         nn[(size_t)i * K + j] = (ok && best.key[j] != MLOAM_KEY_NONE) ? (int)(unsigned)(best.key[j] & 0xffffffffu) : -1;
     }
   }
+  if (!work) i += gridDim.x * QWARPS;
   }  // feature loop
 }
 
 int match_from_map_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const int *d_n, const double *d_pose7,
-                          const MatchCfg &cfg, unsigned char *d_valid, float *d_coeff, int *d_nn) {
+                          const MatchCfg &cfg, unsigned char *d_valid, float *d_coeff, int *d_nn, int *d_work) {
   if (slot < 0 || slot >= MLOAM_NUM_MAPS || !c->maps[slot].built) {
     c->err = "match_from_map: map slot not built";
     return MLOAM_E_STATE;
@@ -345,7 +357,7 @@ int match_from_map_device(Ctx *c, int slot, int type, const float4 *d_pts, int n
   cudaStream_t st = c->stream;
 #define MLOAM_LAUNCH_MATCH(KK, PL)                                                                                     \
   k_match<KK, PL><<<nb, QWARPS * 32, 0, st>>>(mv, d_pts, n, d_n, d_pose7, cfg.min_match_sq_dis, cfg.min_plane_dis, cfg.check_fov, \
-                                              d_valid, d_coeff, d_nn)
+                                              d_valid, d_coeff, d_nn, d_work)
   if (cfg.n_neigh == 5) {
     if (type == 's') MLOAM_LAUNCH_MATCH(5, true);
     else MLOAM_LAUNCH_MATCH(5, false);

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(LM_THREADS) k_lm(const double *__restrict__ pa
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0 && mode != 0) st->work[0] = 0, st->work[1] = 0;  // re-arm the match work queues
   if (threadIdx.x != 0 || mode == 0) return;
   double H[36], g[6];
   unpack_ne(ne, H, g);
@@ -391,6 +392,7 @@ __global__ void k_lm_init(LMState *st, const double *pose7, int max_inner) {
     st->max_inner = max_inner;
     st->done = 0, st->termination = 0, st->total_iterations = 0, st->iteration = 0;
     st->is_degenerate = 0, st->rows = 0, st->n_valid[0] = st->n_valid[1] = 0;
+    st->work[0] = st->work[1] = 0;
     st->cost = 0, st->initial_cost = 0;
     for (int i = 0; i < 36; i++) st->V_update[i] = (i % 7 == 0) ? 1.0 : 0.0, st->H0[i] = 0, st->H[i] = 0;
     for (int i = 0; i < 6; i++) st->eig[i] = 0, st->g[i] = 0;
