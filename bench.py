@@ -269,7 +269,7 @@ def main():
     launches = ctx.launch_count() - launches0
     ms_steps = [a.elapsed_time(b) for a, b in evs]
     t_local = sum(ms_steps) / 1e3
-    prof = {name: ctx.profile_get(name) for name in ("map_build", "extract", "voxel", "match", "linearize", "lm")}
+    prof = {name: ctx.profile_get(name) for name in ("map_build", "extract", "voxel", "match", "fit", "linearize", "lm")}
     ctx.profile(False)
     t_max = t_local
     if world > 1:

@@ -82,6 +82,7 @@ struct Ctx {
   DevBuf feat_valid[2];           // unsigned char per query
   DevBuf feat_coeff[2];           // float[6] per query
   DevBuf feat_nn[2];              // int[n_neigh] per query (optional)
+  DevBuf knn_pos[2];              // int[n_neigh] per query: neighbour positions handed from k_match_knn to k_match_fit
   DevBuf partials;                // per-block packed normal equations
   DevBuf lm_state;                // LMState
   DevBuf scratch[8];              // general scratch (knn outputs, factor batches, extraction, voxel)
@@ -135,6 +136,19 @@ int knn_device(Ctx *c, int slot, const float4 *d_q, int nq, const double *d_pose
 // d_n (nullable): device-side feature count, n is then the launch upper bound.
 int match_from_map_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const int *d_n, const double *d_pose7,
                           const MatchCfg &cfg, unsigned char *d_valid, float *d_coeff, int *d_nn, int *d_work = nullptr);
+
+// match_kernels.cu: one kNN launch + one fit launch over up to two feature sets
+struct MatchJob {
+  int slot;                 // map slot
+  int type;                 // 'c' (line fit) | 's' (plane fit)
+  const float4 *pts;        // sensor-frame features
+  int n;                    // count / upper bound
+  const int *d_n;           // nullable device-side count
+  unsigned char *valid;     // out
+  float *coeff;             // out, n * 6
+  int *nn;                  // out, nullable, n * n_neigh original indices
+};
+int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_pose7, const MatchCfg &cfg, int *d_work);
 
 // solve_kernels.cu
 struct FeatSet {

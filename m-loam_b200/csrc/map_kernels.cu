@@ -9,7 +9,6 @@
 // original index, so a cell is one contiguous run of 16 B records (a 128 B line holds 8 points).  The hash
 // table is open addressing over 16 B {key,start,count} records: one probe = one 16 B load.
 #include "ctx.h"
-#include "fit.cuh"
 #include "knn.cuh"
 
 namespace mloam {
@@ -234,141 +233,6 @@ int knn_device(Ctx *c, int slot, const float4 *d_q, int nq, const double *d_pose
     case 10: k_knn<10><<<nb, QWARPS * 32, 0, st>>>(mv, d_q, nq, d_pose7, max_sqdist, d_idx, d_sqd); break;
     default: c->err = "knn: k must be 1, 5 or 10"; return MLOAM_E_INVALID;
   }
-  c->launches++;
-  MLOAM_CUDA_OK(c, cudaGetLastError());
-  return MLOAM_OK;
-}
-
-// ------------------------------------------------------------------------------------------- match
-// FOV gate, feature_extract.hpp:696-715 (and :434-458, :599-618, :842-861)
-__device__ __forceinline__ bool in_laser_fov(const PoseD &T, const float3 &sel) {
-  const float3 zt = associate(T, 0.0f, 0.0f, 10.0f);
-  const double ex = T.t.x - (double)sel.x, ey = T.t.y - (double)sel.y, ez = T.t.z - (double)sel.z;
-  const float s1 = (float)(ex * ex + ey * ey + ez * ez);
-  const float ax = zt.x - sel.x, ay = zt.y - sel.y, az = zt.z - sel.z;
-  const float s2 = ax * ax + ay * ay + az * az;
-  const float check1 = 100.0f + s1 - s2 - 10.0f * sqrtf(3.0f) * sqrtf(s1);
-  const float check2 = 100.0f + s1 - s2 + 10.0f * sqrtf(3.0f) * sqrtf(s1);
-  return check1 < 0 && check2 > 0;
-}
-
-template <int K, bool IS_PLANE>
-__global__ void __launch_bounds__(QWARPS * 32)
-    k_match(MapView map, const float4 *__restrict__ pts, int n, const int *__restrict__ d_n, const double *__restrict__ pose7,
-            float min_match_sq_dis, float min_plane_dis, int check_fov, unsigned char *__restrict__ valid,
-            float *__restrict__ coeff, int *__restrict__ nn, int *__restrict__ work) {
-  __shared__ RunBuf rbuf[QWARPS];
-  const int lane = threadIdx.x & 31;
-  if (d_n) n = min(n, *d_n);  // feature count produced on the device (no host round trip)
-  const PoseD T = pose_from_param(pose7);
-  // The grid is sized for the SM count, not for the (loose) upper bound.  With a work-queue head (`work`, zeroed
-  // by k_lm between launches) every warp pulls the next feature when it finishes one, so a long query (sparse
-  // neighbourhood) does not stall a whole wave; without one, warps stride statically.
-  int i = blockIdx.x * QWARPS + (threadIdx.x >> 5);
-  while (true) {
-  if (work) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(work, 1);
-    i = __shfl_sync(MLOAM_FULL_MASK, t, 0);
-  }
-  if (i >= n) break;
-  const float4 p = __ldg(pts + i);
-  const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
-  TopK<K> best;
-  warp_knn<K, true>(map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best);
-  bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
-            __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
-  float out[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (ok) {
-    float X[K][3];
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-      const float4 v = __ldg(map.sorted + best.pos[j]);
-      X[j][0] = v.x, X[j][1] = v.y, X[j][2] = v.z;
-    }
-    if (IS_PLANE) {
-      // :573-594 / :817-837
-      float A[K][3];
-#pragma unroll
-      for (int j = 0; j < K; j++) A[j][0] = X[j][0], A[j][1] = X[j][1], A[j][2] = X[j][2];
-      float nv[3];
-      ok = lsq_plane_dev<K>(A, nv);
-      if (ok) {
-        const float nrm = sqrtf(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
-        const float d = 1 / nrm;
-        nv[0] = nv[0] / nrm, nv[1] = nv[1] / nrm, nv[2] = nv[2] / nrm;
-#pragma unroll
-        for (int j = 0; j < K; j++)
-          if (fabsf(nv[0] * X[j][0] + nv[1] * X[j][1] + nv[2] * X[j][2] + d) > min_plane_dis) ok = false;
-        out[0] = nv[0], out[1] = nv[1], out[2] = nv[2], out[3] = d;
-      }
-    } else {
-      // :410-432 / :670-693
-      float cx = 0.f, cy = 0.f, cz = 0.f;
-#pragma unroll
-      for (int j = 0; j < K; j++) cx = cx + X[j][0], cy = cy + X[j][1], cz = cz + X[j][2];
-      const float kf = (float)K;
-      cx = cx / kf, cy = cy / kf, cz = cz / kf;
-      float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        const float a = X[j][0] - cx, b = X[j][1] - cy, c = X[j][2] - cz;
-        c00 = c00 + a * a, c01 = c01 + a * b, c02 = c02 + a * c;
-        c11 = c11 + b * b, c12 = c12 + b * c, c22 = c22 + c * c;
-      }
-      float w[3], V[3][3];
-      eig3f_dev(c00, c01, c02, c11, c12, c22, w, V);
-      ok = w[2] > 3 * w[1];
-      const float k01 = 0.1f;
-      out[0] = k01 * V[0][2] + cx, out[1] = k01 * V[1][2] + cy, out[2] = k01 * V[2][2] + cz;
-      out[3] = -k01 * V[0][2] + cx, out[4] = -k01 * V[1][2] + cy, out[5] = -k01 * V[2][2] + cz;
-    }
-    if (ok && check_fov) ok = in_laser_fov(T, sel);
-  }
-  if (lane == 0) {
-    valid[i] = ok ? 1 : 0;
-#pragma unroll
-    for (int j = 0; j < 6; j++) coeff[(size_t)i * 6 + j] = ok ? out[j] : 0.f;
-    if (nn) {
-#pragma unroll
-      for (int j = 0; j < K; j++)
-        nn[(size_t)i * K + j] = (ok && best.key[j] != MLOAM_KEY_NONE) ? (int)(unsigned)(best.key[j] & 0xffffffffu) : -1;
-    }
-  }
-  if (!work) i += gridDim.x * QWARPS;
-  }  // feature loop
-}
-
-int match_from_map_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const int *d_n, const double *d_pose7,
-                          const MatchCfg &cfg, unsigned char *d_valid, float *d_coeff, int *d_nn, int *d_work) {
-  if (slot < 0 || slot >= MLOAM_NUM_MAPS || !c->maps[slot].built) {
-    c->err = "match_from_map: map slot not built";
-    return MLOAM_E_STATE;
-  }
-  if (type != 'c' && type != 's') {
-    c->err = "match_from_map: type must be 'c' or 's'";
-    return MLOAM_E_INVALID;
-  }
-  if (n <= 0) return MLOAM_OK;
-  ProfScope ps(c, "match");
-  MapView mv = c->maps[slot].view();
-  int nb = (n + QWARPS - 1) / QWARPS;
-  if (nb > 8 * c->sm_count) nb = 8 * c->sm_count;  // 8 CTAs x 8 warps per SM; warps stride over the features
-  cudaStream_t st = c->stream;
-#define MLOAM_LAUNCH_MATCH(KK, PL)                                                                                     \
-  k_match<KK, PL><<<nb, QWARPS * 32, 0, st>>>(mv, d_pts, n, d_n, d_pose7, cfg.min_match_sq_dis, cfg.min_plane_dis, cfg.check_fov, \
-                                              d_valid, d_coeff, d_nn, d_work)
-  if (cfg.n_neigh == 5) {
-    if (type == 's') MLOAM_LAUNCH_MATCH(5, true);
-    else MLOAM_LAUNCH_MATCH(5, false);
-  } else if (cfg.n_neigh == 10) {
-    if (type == 's') MLOAM_LAUNCH_MATCH(10, true);
-    else MLOAM_LAUNCH_MATCH(10, false);
-  } else {
-    c->err = "match_from_map: n_neigh must be 5 or 10";
-    return MLOAM_E_INVALID;
-  }
-#undef MLOAM_LAUNCH_MATCH
   c->launches++;
   MLOAM_CUDA_OK(c, cudaGetLastError());
   return MLOAM_OK;

@@ -49,14 +49,13 @@ int scan2map_run(Ctx *c, const ScanRef &S, const double *pose_init7, double *pos
       FeatSet{S.surf, c->feat_valid[1].as<unsigned char>(), c->feat_coeff[1].as<float>(), ns_use, 1, S.d_n_surf}};
   for (int outer = 0; outer < P.max_outer; outer++) {
     // :503-532  match corner then surf at pose_wmap_curr (wo_gf: every feature)
-    if (nc_use > 0) {
-      rc = match_from_map_device(c, MLOAM_MAP_CORNER, 'c', S.corner, nc_use, S.d_n_corner, d_pose, cfg,
-                                 c->feat_valid[0].as<unsigned char>(), c->feat_coeff[0].as<float>(), nullptr, &st->work[0]);
-      if (rc) return rc;
-    }
-    if (ns_use > 0) {
-      rc = match_from_map_device(c, MLOAM_MAP_SURF, 's', S.surf, ns_use, S.d_n_surf, d_pose, cfg,
-                                 c->feat_valid[1].as<unsigned char>(), c->feat_coeff[1].as<float>(), nullptr, &st->work[1]);
+    {
+      MatchJob jobs[2] = {
+          MatchJob{MLOAM_MAP_CORNER, 'c', S.corner, nc_use, S.d_n_corner, c->feat_valid[0].as<unsigned char>(),
+                   c->feat_coeff[0].as<float>(), nullptr},
+          MatchJob{MLOAM_MAP_SURF, 's', S.surf, ns_use, S.d_n_surf, c->feat_valid[1].as<unsigned char>(),
+                   c->feat_coeff[1].as<float>(), nullptr}};
+      rc = match_pair_device(c, jobs, 2, d_pose, cfg, &st->work[0]);
       if (rc) return rc;
     }
     // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve.  The
