@@ -189,6 +189,13 @@ int mloam_frame_device(mloam_ctx_t *ctx, const mloam_point_t *d_cloud, int n, co
  * NULL resets to identity (no transform). */
 int mloam_set_extrinsic(mloam_ctx_t *ctx, const double *ext7);
 
+/* ---- FeatureExtract::matchCornerFromScan / matchSurfFromScan (feature_extract.hpp:131-376) against the map slot
+ * built (mloam_map_build, cell ~1.3 m) from the previous sweep's less-sharp / less-flat features, which must be in
+ * the reference's ring-sorted order (int(intensity) = ring).  type 'c': coeffs = [X_closest; X_second];
+ * 's': (w, d, 0, 0).  nn3 (nullable): [closest, ind2, ind3] per query (-1 when absent). */
+int mloam_match_from_scan(mloam_ctx_t *ctx, int slot, int type, const mloam_point_t *h_pts, int n, const double *pose7,
+                          unsigned char *h_valid, double *h_coeffs, int *h_nn3);
+
 /* ---- LidarTracker::trackCloud (lidar_tracker.cpp:23-129). */
 int mloam_track_cloud(mloam_ctx_t *ctx, const mloam_point_t *h_prev_less_sharp, int n_pls,
                       const mloam_point_t *h_prev_less_flat, int n_plf, const mloam_point_t *h_cur_sharp, int n_cs,

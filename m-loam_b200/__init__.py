@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
-    "mloam_frame_device", "mloam_set_extrinsic", "mloam_track_cloud", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy",
+    "mloam_frame_device", "mloam_set_extrinsic", "mloam_match_from_scan", "mloam_track_cloud", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy",
 ]
 
 
@@ -294,6 +294,25 @@ class Context:
         self._ck(lib().mloam_frame_device(self._h, C.c_void_p(d_cloud), n, C.c_void_p(d_scan_start), C.c_void_p(d_scan_end), n_scans,
                                           C.c_void_p(d_surf_map), n_surf_map, C.c_void_p(d_corner_map), n_corner_map,
                                           int(rebuild_maps), _p(pi), _p(out), C.byref(st)))
+        return out, st.as_dict()
+
+    def match_from_scan(self, slot: int, kind: str, pts, pose7):
+        pts = _cloud(pts)
+        n = pts.shape[0]
+        pose = np.ascontiguousarray(pose7, np.float64)
+        valid = np.zeros(n, np.uint8)
+        coeffs = np.zeros((n, 6), np.float64)
+        nn3 = np.zeros((n, 3), np.int32)
+        self._ck(lib().mloam_match_from_scan(self._h, slot, ord(kind), _p(pts), n, _p(pose), _p(valid), _p(coeffs), _p(nn3)))
+        return valid.astype(bool), coeffs, nn3
+
+    def track_cloud(self, prev_less_sharp, prev_less_flat, cur_sharp, cur_flat, pose_ini7):
+        a, b, c, d = _cloud(prev_less_sharp), _cloud(prev_less_flat), _cloud(cur_sharp), _cloud(cur_flat)
+        pi = np.ascontiguousarray(pose_ini7, np.float64)
+        out = np.zeros(7)
+        st = SolveStats()
+        self._ck(lib().mloam_track_cloud(self._h, _p(a), a.shape[0], _p(b), b.shape[0], _p(c), c.shape[0], _p(d), d.shape[0], _p(pi),
+                                         _p(out), C.byref(st)))
         return out, st.as_dict()
 
     def set_extrinsic(self, ext7=None):

@@ -177,6 +177,8 @@ struct LMState {
   int max_inner;
   int pad;
   int work[2];             // dynamic work-queue heads of the corner / surf match launches (reset by k_lm)
+  int min_corr;            // a Solve with fewer matched features is skipped (lidar_tracker.cpp:64-68)
+  int skipped;             // ... and this flag is raised
 };
 
 }  // namespace mloam

@@ -101,7 +101,9 @@ struct Ctx {
 
   // NCCL (multi-GPU); opaque here
   int *d_extract_status = nullptr;  // device flag of the last extraction (1: ring window overflow / bad ScanInfo)
-  int want_eig = 1;                 // k_lm mode 1: always run the 6x6 eigen-solver (1) or only when degenerate (0)
+  int lm_min_corr = 0;              // lm_init_state: minimum matched features for a Solve (tracker: 10)
+  double lm_eig_thre = -1.0;        // < 0: use params.eig_thre; the tracker disables evalDegenracy with 0
+  int want_eig = 1;                // k_lm mode 1: always run the 6x6 eigen-solver (1) or only when degenerate (0)
   bool has_ext = false;            // sensor -> base extrinsic applied to extracted features (frame path)
   double ext[7] = {0, 0, 0, 0, 0, 0, 1};
   void *nccl_comm = nullptr;
@@ -149,6 +151,13 @@ struct MatchJob {
   int *nn;                  // out, nullable, n * n_neigh original indices
 };
 int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_pose7, const MatchCfg &cfg, int *d_work);
+
+// track_kernels.cu
+int match_from_scan_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const double *d_pose7, unsigned char *d_valid,
+                           float *d_coeff, int *d_nn3);
+int track_cloud_device(Ctx *c, const float4 *d_prev_less_sharp, int n_pls, const float4 *d_prev_less_flat, int n_plf,
+                       const float4 *d_cur_sharp, int n_cs, const float4 *d_cur_flat, int n_cf, const double *pose_ini7,
+                       double *pose_out7, mloam_solve_stats_t *stats);
 
 // solve_kernels.cu
 struct FeatSet {

@@ -322,11 +322,4 @@ int mloam_set_extrinsic(mloam_ctx_t *h, const double *ext7) {
   return MLOAM_OK;
 }
 
-// ------------------------------------------------------------------------------------------ tracker (scan-to-scan)
-int mloam_track_cloud(mloam_ctx_t *h, const mloam_point_t *, int, const mloam_point_t *, int, const mloam_point_t *, int,
-                      const mloam_point_t *, int, const double *, double *, mloam_solve_stats_t *) {
-  if (!h) return MLOAM_E_INVALID;
-  return fail(&h->c, MLOAM_E_STATE, "track_cloud: scan-to-scan matcher not built in this revision");
-}
-
 }  // extern "C"

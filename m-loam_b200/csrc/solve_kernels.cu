@@ -54,6 +54,34 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
       const float *cf = fs.coeff + (size_t)i * 6;
       double J[6];
       double r;
+      if (fs.is_plane == 2) {
+        // LidarScanEdgeFactorVector (tracker, lidar_tracker.cpp:89): one 3-row residual BLOCK, the loss acts on
+        // its squared norm (Ceres applies rho per block)
+        double r3[3], J3[18];
+        edge_vector_factor(P, p, D3{(double)cf[0], (double)cf[1], (double)cf[2]}, D3{(double)cf[3], (double)cf[4], (double)cf[5]}, r3,
+                           J3, true);
+        double rho, rho1;
+        huber(a.huber_a, r3[0] * r3[0] + r3[1] * r3[1] + r3[2] * r3[2], &rho, &rho1);
+        const double sc = sqrt(rho1);
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const double rm = sc * r3[m];
+          double Jm[6];
+#pragma unroll
+          for (int k = 0; k < 6; k++) Jm[k] = sc * J3[m * 6 + k];
+          int q = 0;
+#pragma unroll
+          for (int i0 = 0; i0 < 6; i0++)
+#pragma unroll
+            for (int j0 = i0; j0 < 6; j0++) acc[q++] += Jm[i0] * Jm[j0];
+#pragma unroll
+          for (int k = 0; k < 6; k++) acc[NE_H + k] += Jm[k] * rm;
+        }
+        acc[NE_H + NE_G] += 0.5 * rho;
+        if (s == 0) acc[NE_H + NE_G + 1] += 1.0;
+        else acc[NE_H + NE_G + 2] += 1.0;
+        continue;
+      }
       if (fs.is_plane) {
         r = plane_factor(P, p, D3{(double)cf[0], (double)cf[1], (double)cf[2]}, (double)cf[3], a.sqrt_info, J, true);
       } else {
@@ -299,6 +327,12 @@ __global__ void __launch_bounds__(LM_THREADS) k_lm(const double *__restrict__ pa
     st->n_valid[0] = (int)ne[NE_H + NE_G + 1];
     st->n_valid[1] = (int)ne[NE_H + NE_G + 2];
     st->rows = st->n_valid[0] + st->n_valid[1];
+    st->skipped = 0;
+    if (st->rows < st->min_corr) {  // "less correspondence": the outer iteration is skipped, pose untouched
+      st->done = 1, st->termination = 5, st->skipped = 1;
+      for (int k = 0; k < 7; k++) st->xc[k] = st->x[k];
+      return;
+    }
     // PoseLocalParameterization::setParameter + evalDegenracy (lidar_mapper_keyframe.cpp:1172-1204)
     for (int i = 0; i < 36; i++) st->V_update[i] = (i % 7 == 0) ? 1.0 : 0.0;
     st->is_degenerate = 0;
@@ -386,10 +420,11 @@ __global__ void __launch_bounds__(LM_THREADS) k_lm(const double *__restrict__ pa
   lm_compute_step(st);
 }
 
-__global__ void k_lm_init(LMState *st, const double *pose7, int max_inner) {
+__global__ void k_lm_init(LMState *st, const double *pose7, int max_inner, int min_corr) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     for (int k = 0; k < 7; k++) st->x[k] = pose7[k], st->xc[k] = pose7[k];
     st->max_inner = max_inner;
+    st->min_corr = min_corr, st->skipped = 0;
     st->done = 0, st->termination = 0, st->total_iterations = 0, st->iteration = 0;
     st->is_degenerate = 0, st->rows = 0, st->n_valid[0] = st->n_valid[1] = 0;
     st->work[0] = st->work[1] = 0;
@@ -407,7 +442,7 @@ int lm_init_state(Ctx *c, const double *pose7_host, int max_inner, double eig_th
   for (int k = 0; k < 7; k++) stage[k] = pose7_host[k];
   double *d_stage = c->scratch[7].as<double>();
   MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_stage, stage, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  k_lm_init<<<1, 32, 0, c->stream>>>(c->lm_state.as<LMState>(), d_stage, max_inner);
+  k_lm_init<<<1, 32, 0, c->stream>>>(c->lm_state.as<LMState>(), d_stage, max_inner, c->lm_min_corr);
   c->launches++;
   MLOAM_CUDA_OK(c, cudaGetLastError());
   return MLOAM_OK;
@@ -452,11 +487,11 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
     int rc = comm_allreduce_doubles(c, ne, NE_PACK);
     if (rc) return rc;
     ProfScope ps(c, "lm");
-    k_lm<<<1, LM_THREADS, 0, c->stream>>>(ne, 1, c->lm_state.as<LMState>(), lm_mode, c->params.eig_thre, want_eig, d_out30);
+    k_lm<<<1, LM_THREADS, 0, c->stream>>>(ne, 1, c->lm_state.as<LMState>(), lm_mode, (c->lm_eig_thre >= 0.0 ? c->lm_eig_thre : c->params.eig_thre), want_eig, d_out30);
     c->launches++;
   } else {
     ProfScope ps(c, "lm");
-    k_lm<<<1, LM_THREADS, 0, c->stream>>>(c->partials.as<double>(), nb, c->lm_state.as<LMState>(), lm_mode, c->params.eig_thre, want_eig,
+    k_lm<<<1, LM_THREADS, 0, c->stream>>>(c->partials.as<double>(), nb, c->lm_state.as<LMState>(), lm_mode, (c->lm_eig_thre >= 0.0 ? c->lm_eig_thre : c->params.eig_thre), want_eig,
                                   d_out30);
     c->launches++;
   }

@@ -349,3 +349,63 @@ def test_frame_c2_full_size(ctx):
     assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
     et, er = syn.pose_err(pose, traj[7])
     assert et < 0.05 and er < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ scan-to-scan (tracker)
+@pytest.fixture(scope="module")
+def two_sweeps():
+    scene = syn.make_scene()
+    traj = syn.trajectory(4)
+    out = {}
+    for rings, horizon, key in ((16, 1024, "s16"), (64, 2048, "s64")):
+        a, ssa, sea = syn.make_sweep(scene, traj[1], rings, horizon, seed=31)
+        b, ssb, seb = syn.make_sweep(scene, traj[2], rings, horizon, seed=32)
+        out[key] = dict(fa=orc.extract_cloud(a, ssa, sea), fb=orc.extract_cloud(b, ssb, seb),
+                        rel=syn.pose_mul(syn.pose_inv(traj[1]), traj[2]))
+    return out
+
+
+@pytest.mark.parametrize("key", ["s16", "s64"])
+@pytest.mark.parametrize("kind", ["c", "s"])
+def test_match_from_scan_exact(ctx, two_sweeps, key, kind):
+    d = two_sweeps[key]
+    scan = d["fa"]["corner_points_less_sharp" if kind == "c" else "surf_points_less_flat"]
+    data = d["fb"]["corner_points_sharp" if kind == "c" else "surf_points_flat"]
+    guess = syn.pose7([0.05, 0.01, 0.0], syn.quat_from_rpy(0.0, 0.0, 0.005))
+    slot = 2 if kind == "c" else 3
+    ctx.map_build(slot, scan, 1.3)
+    valid, coeffs, nn3 = ctx.match_from_scan(slot, kind, data, guess)
+    fidx, rcoeffs = orc.match_from_scan(kind, scan, data, guess)
+    assert fidx.shape[0] > 20
+    assert np.array_equal(np.nonzero(valid)[0], fidx)      # same features survive, in query order
+    assert np.array_equal(coeffs[valid], rcoeffs)          # bit-exact [X_j; X_l] / (w, d)
+
+
+@pytest.mark.parametrize("key", ["s16", "s64"])
+def test_track_cloud_pose_parity(ctx, two_sweeps, key):
+    d = two_sweeps[key]
+    ident = syn.pose7([0, 0, 0], [0, 0, 0, 1])
+    args = (d["fa"]["corner_points_less_sharp"], d["fa"]["surf_points_less_flat"], d["fb"]["corner_points_sharp"],
+            d["fb"]["surf_points_flat"], ident)
+    pose, st = ctx.track_cloud(*args)
+    ref, rst = orc.track_cloud(*args)
+    dt, dr = syn.pose_err(pose, ref)
+    assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+    assert st["n_corner"] == rst["n_corner"] and st["n_surf"] == rst["n_surf"]
+    assert st["lm_iterations"] == rst["lm_iterations"]
+    et, er = syn.pose_err(pose, d["rel"])
+    assert et < 0.05 and er < 5e-3  # recovers the inter-sweep motion
+
+
+def test_track_cloud_too_few_correspondences(ctx, two_sweeps):
+    """< 10 correspondences: both outer iterations are skipped and the initial pose comes back (lidar_tracker.cpp:64-68)."""
+    d = two_sweeps["s16"]
+    ident = syn.pose7([0.1, 0.2, 0.3], syn.quat_from_rpy(0.01, 0.02, 0.03))
+    far = d["fa"]["corner_points_less_sharp"].copy()
+    far[:, :3] += 1000.0
+    far2 = d["fa"]["surf_points_less_flat"].copy()
+    far2[:, :3] += 1000.0
+    pose, st = ctx.track_cloud(far, far2, d["fb"]["corner_points_sharp"], d["fb"]["surf_points_flat"], ident)
+    ref, rst = orc.track_cloud(far, far2, d["fb"]["corner_points_sharp"], d["fb"]["surf_points_flat"], ident)
+    assert st["n_corner"] + st["n_surf"] < 10 and st["lm_iterations"] == 0 == rst["lm_iterations"]
+    assert np.allclose(pose, ref, atol=1e-15) and np.allclose(pose, ident, atol=1e-15)
