@@ -1,0 +1,86 @@
+"""N > 1 coverage.  CPU (gloo, world_size 2): the property the GPU path relies on — the per-LiDAR normal equations
+summed by an all-reduce equal the normal equations of the merged features — and the bench's rank-invariant workload.
+GPU: tests/multi_gpu_check.py under torch.distributed.run when >= 2 GPUs are visible."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    import synthetic as syn
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    scene = syn.make_scene()
+    truth = syn.trajectory(3)[2]
+    surf_map, corner_map = syn.make_submap(scene, 30000)
+    init = syn.perturb_pose(truth, np.random.Generator(np.random.PCG64(5)))
+    feats = []
+    for r in range(world):
+        cloud, ss, se = syn.make_sweep(scene, truth, 16, 512, seed=60, lidar_id=r)
+        f = orc.extract_cloud(cloud, ss, se)
+        feats.append(orc.voxel_grid(f["surf_points_less_flat"], 0.4, True)[0])
+
+    def ne(sf):
+        v, cf, _ = orc.match_from_map("s", surf_map, sf, init)
+        types = np.full(int(v.sum()), ord("s"), np.uint8)
+        return orc.normal_eq(types, sf[v][:, :3].astype(np.float64), cf[v], 1.0, 0.1, init)
+
+    H, g, cost = ne(feats[rank])  # this rank's LiDAR
+    packed = torch.from_numpy(np.concatenate([H.reshape(-1), g, [cost]]))
+    dist.all_reduce(packed)  # the single collective of the path
+    Hm, gm, costm = ne(np.concatenate(feats))  # merged features on one process
+    merged = np.concatenate([Hm.reshape(-1), gm, [costm]])
+    ok = np.allclose(packed.numpy(), merged, rtol=1e-12, atol=1e-9)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_allreduce_of_per_lidar_normal_equations_equals_merged_gloo():
+    import torch.multiprocessing as mp
+
+    world = 2
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_gloo_worker, args=(world, 29511, ret), nprocs=world, join=True)
+        assert all(ret[r] for r in range(world))
+
+
+def test_bench_workload_is_rank_invariant_where_it_must_be():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    import synthetic as syn
+
+    assert bench.lidar_extrinsic(syn, 0, 4) is None
+    e1, e2 = bench.lidar_extrinsic(syn, 1, 4), bench.lidar_extrinsic(syn, 2, 4)
+    assert abs(np.linalg.norm(e1[3:]) - 1) < 1e-12 and not np.allclose(e1, e2)
+    bench.MAP_POINTS[2] = 20000  # small maps for the test
+    bench.RINGS, bench.HORIZON = 16, 256
+    sm0, cm0, fr0, x0 = bench.make_workload(syn, 2, 0, 2)
+    sm1, cm1, fr1, x1 = bench.make_workload(syn, 2, 1, 2)
+    assert np.array_equal(sm0, sm1) and np.array_equal(cm0, cm1)          # replicated submap
+    assert all(np.array_equal(a["init"], b["init"]) for a, b in zip(fr0, fr1))  # shared LM state starts identical
+    assert not np.array_equal(fr0[0]["cloud"], fr1[0]["cloud"]) and x0 is None and x1 is not None
+
+
+@pytest.mark.gpu
+def test_two_gpu_frame_parity():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run tests/multi_gpu_check.py under torchrun with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
