@@ -36,7 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 GN_ITERS = 10
 MAP_POINTS = {1: 1_000_000, 2: 2_000_000, 4: 5_000_000, 8: 10_000_000}
 RINGS, HORIZON = 64, 2048
-MATCH_BYTES_PER_FEATURE = 16 + 5 * 16 + 24 + 1  # query float4 + 5 neighbour float4 + 6 float coeffs + valid flag
+MATCH_BYTES_PER_FEATURE = 16 + 5 * 16 + 5 * 4  # k_match_knn: query float4 + 5 neighbour float4 + 5 neighbour positions
 METRIC = "scan_to_map_lidar_frames_per_sec"
 
 
@@ -318,7 +318,7 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_match<5,*> (kNN + line/plane fit, one warp per feature)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "k_match_knn<5> (pointAssociateToMap + exact 5-NN in the voxel hash, one warp per feature)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_feature": MATCH_BYTES_PER_FEATURE,
                 "avg_launch_us": 1e3 * match_ms / max(1, match_launches), "launches": match_launches,

@@ -41,3 +41,20 @@ def test_only_sm100a_sass_is_embedded(mloam):
     out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", mloam.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
     assert archs == {"sm_100a"}, archs
+
+
+def test_cpp_host_shim_compiles_links_and_refuses_to_run_without_gpu(mloam):
+    """m-loam_b200/host/mloam_shim.hpp mirrors the reference's class surface over the C ABI; its self-test must build
+    with plain g++ (no CUDA, PCL, Eigen or Ceres headers) and, with no device, fail loudly instead of falling back."""
+    import subprocess
+
+    import torch
+
+    mloam.build()
+    exe = os.path.join(mloam.HERE, "host", "shim_selftest")
+    subprocess.check_call(["make", "-C", mloam.HERE, "host/shim_selftest"], stdout=subprocess.DEVNULL)
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present (the gpu-marked test runs the binary)")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 2 and "no CPU path" in out.stdout

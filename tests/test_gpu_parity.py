@@ -409,3 +409,15 @@ def test_track_cloud_too_few_correspondences(ctx, two_sweeps):
     ref, rst = orc.track_cloud(far, far2, d["fb"]["corner_points_sharp"], d["fb"]["surf_points_flat"], ident)
     assert st["n_corner"] + st["n_surf"] < 10 and st["lm_iterations"] == 0 == rst["lm_iterations"]
     assert np.allclose(pose, ref, atol=1e-15) and np.allclose(pose, ident, atol=1e-15)
+
+
+def test_cpp_host_shim_selftest(mloam):
+    """The reference-shaped C++ surface (FeatureExtract, MapHandle, PoseLocalParameterization, Lidar*Factor::Evaluate with
+    the check() finite-difference convention, scan2MapOptimization) end to end through the C ABI."""
+    import os
+    import subprocess
+
+    exe = os.path.join(mloam.HERE, "host", "shim_selftest")
+    assert os.path.exists(exe), "build() must have produced the host shim self-test"
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "SHIM_SELFTEST OK" in out.stdout, out.stdout[-3000:] + out.stderr[-1000:]
