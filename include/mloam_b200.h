@@ -202,6 +202,17 @@ int mloam_track_cloud(mloam_ctx_t *ctx, const mloam_point_t *h_prev_less_sharp, 
                       const mloam_point_t *h_cur_flat, int n_cf, const double *pose_ini7, double *pose_out7,
                       mloam_solve_stats_t *stats);
 
+/* ---- Estimator::optimizeMap's LiDAR residual blocks for one frame i / one LiDAR n (estimator.cpp:687-848):
+ * LidarPureOdom{PlaneNorm,Edge}Factor (lidar_pure_odom_factor.hpp:27-381) on (pose_pivot [constant, :631], pose_i, ext_n),
+ * ceres::HuberLoss(huber_a = 1.0, :602), ceres::Solve(DENSE_SCHUR, max_iterations = NUM_ITERATIONS, :605-615).
+ * free_mask: 1 = pose_i free (1x6 odometry rows, ext constant as with ESTIMATE_EXTRINSIC == 0, :640), 2 = ext free
+ * (1x6), 3 = both free (1x12 calibration rows [J_pose_i | J_ext], 12x12 normal equations).
+ * Features are the matcher's output (types[n] 's'|'c', sensor-frame points n*3, coefficients n*6 in the pivot frame).
+ * pose_i7 / ext7 are updated in place.  stats->H receives the leading 6x6 block of J^T J. */
+int mloam_odom_solve(mloam_ctx_t *ctx, int n, const unsigned char *h_types, const double *h_points, const double *h_coeffs,
+                     const double *pose_pivot7, double *pose_i7, double *ext7, int free_mask, int max_iterations,
+                     double huber_a, double sqrt_info, mloam_solve_stats_t *stats);
+
 /* ---- multi-GPU: one LiDAR per GPU, one all-reduce of the packed normal equations per LM evaluation
  * (SURVEY.md §8e).  id128 is an ncclUniqueId (128 bytes) created on rank 0 and shared by the caller. */
 int mloam_comm_unique_id(void *id128);

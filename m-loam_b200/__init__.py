@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
-    "mloam_frame_device", "mloam_set_extrinsic", "mloam_match_from_scan", "mloam_track_cloud", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy",
+    "mloam_frame_device", "mloam_set_extrinsic", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy",
 ]
 
 
@@ -314,6 +314,18 @@ class Context:
         self._ck(lib().mloam_track_cloud(self._h, _p(a), a.shape[0], _p(b), b.shape[0], _p(c), c.shape[0], _p(d), d.shape[0], _p(pi),
                                          _p(out), C.byref(st)))
         return out, st.as_dict()
+
+    def odom_solve(self, types, points, coeffs, pivot7, pose_i7, ext7, free_mask: int, max_iterations: int = 4, huber_a: float = 1.0,
+                   sqrt_info: float = 1.0):
+        types = np.ascontiguousarray(types, np.uint8)
+        points = np.ascontiguousarray(points, np.float64)
+        coeffs = np.ascontiguousarray(coeffs, np.float64)
+        pv = np.ascontiguousarray(pivot7, np.float64)
+        xi, xe = np.array(pose_i7, np.float64), np.array(ext7, np.float64)
+        st = SolveStats()
+        self._ck(lib().mloam_odom_solve(self._h, types.shape[0], _p(types), _p(points), _p(coeffs), _p(pv), _p(xi), _p(xe), int(free_mask),
+                                        int(max_iterations), C.c_double(huber_a), C.c_double(sqrt_info), C.byref(st)))
+        return xi, xe, st.as_dict()
 
     def set_extrinsic(self, ext7=None):
         e = None if ext7 is None else np.ascontiguousarray(ext7, np.float64)

@@ -241,6 +241,28 @@ void orc_frame(const float *cloud, int n, const int *scan_start, const int *scan
   }
 }
 
+// ---- Estimator::optimizeMap residual blocks for one frame / one LiDAR (estimator.cpp:687-848): LidarPureOdom factors on
+// (pose_pivot [constant], pose_i, ext_n); free_mask bit 0 frees pose_i, bit 1 frees ext.  ceres::Solve(max_it),
+// HuberLoss(huber_a).  stats[3]: lm_iterations, final_cost, termination
+void orc_odom_solve(int n, const unsigned char *types, const double *points, const double *coeffs, const double *pivot7,
+                    double *pose_i7, double *ext7, int free_mask, int max_it, double huber_a, double sqrt_info, double *stats) {
+  Problem pr;
+  pr.huber_a = huber_a;
+  double xp[7];
+  std::memcpy(xp, pivot7, sizeof(xp));
+  int ip = pr.add_param(xp, true);  // SetParameterBlockConstant(para_pose_[0]), estimator.cpp:631
+  int ii = pr.add_param(pose_i7, !(free_mask & 1));
+  int ie = pr.add_param(ext7, !(free_mask & 2));
+  for (int i = 0; i < n; i++) {
+    ResidualBlock b{types[i] == 's' ? F_ODOM_PLANE : F_ODOM_EDGE, V3{points[i * 3], points[i * 3 + 1], points[i * 3 + 2]},
+                    {0, 0, 0, 0, 0, 0}, sqrt_info, {ip, ii, ie}};
+    for (int j = 0; j < 6; j++) b.coeffs[j] = coeffs[(size_t)i * 6 + j];
+    pr.blocks.push_back(b);
+  }
+  SolveSummary s = solve(pr, max_it);
+  if (stats) stats[0] = s.iterations, stats[1] = s.final_cost, stats[2] = s.termination;
+}
+
 // ---- LidarTracker::trackCloud. stats[3]: n_corner, n_surf, lm_iterations
 void orc_track_cloud(const float *prev_less_sharp, int n_pls, const float *prev_less_flat, int n_plf,
                      const float *cur_sharp, int n_cs, const float *cur_flat, int n_cf, const double *pose_ini7,

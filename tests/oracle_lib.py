@@ -265,6 +265,19 @@ def frame(cloud_, scan_start, scan_end, surf_map, corner_map, pose_init, opts=No
     return out, st
 
 
+def odom_solve(types, points, coeffs, pivot, pose_i, ext, free_mask, max_it=4, huber_a=1.0, sqrt_info=1.0):
+    types = np.ascontiguousarray(types, np.uint8)
+    points = np.ascontiguousarray(points, np.float64)
+    coeffs = np.ascontiguousarray(coeffs, np.float64)
+    pivot = np.ascontiguousarray(pivot, np.float64)
+    xi = np.array(pose_i, np.float64)
+    xe = np.array(ext, np.float64)
+    stats = np.zeros(3)
+    lib().orc_odom_solve(types.shape[0], _p(types), _p(points), _p(coeffs), _p(pivot), _p(xi), _p(xe), int(free_mask), int(max_it),
+                         C.c_double(huber_a), C.c_double(sqrt_info), _p(stats))
+    return xi, xe, {"lm_iterations": int(stats[0]), "final_cost": stats[1], "termination": int(stats[2])}
+
+
 def track_cloud(prev_less_sharp, prev_less_flat, cur_sharp, cur_flat, pose_ini, opts=None):
     a, b, c, d = cloud(prev_less_sharp), cloud(prev_less_flat), cloud(cur_sharp), cloud(cur_flat)
     if opts is None:

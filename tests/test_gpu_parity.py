@@ -421,3 +421,26 @@ def test_cpp_host_shim_selftest(mloam):
     assert os.path.exists(exe), "build() must have produced the host shim self-test"
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "SHIM_SELFTEST OK" in out.stdout, out.stdout[-3000:] + out.stderr[-1000:]
+
+
+# ------------------------------------------------------------------------------------------------ odometry rows (1x6 / 1x12)
+@pytest.mark.parametrize("free_mask,max_it", [(1, 4), (2, 4), (3, 4), (3, 30)])
+def test_odom_solve_matches_oracle(ctx, free_mask, max_it):
+    from test_oracle_cpu import _odom_problem
+
+    rng = np.random.default_rng(90 + free_mask)
+    xp, xi, xe, types, pts, coeffs = _odom_problem(rng, n=3000)
+    d = lambda: syn.pose7(rng.normal(size=3) * 0.02, syn.quat_from_rpy(*(rng.normal(size=3) * 0.004)))
+    xi0 = syn.pose_mul(xi, d()) if free_mask & 1 else xi
+    xe0 = syn.pose_mul(xe, d()) if free_mask & 2 else xe
+    gi, ge, st = ctx.odom_solve(types, pts, coeffs, xp, xi0, xe0, free_mask, max_iterations=max_it)
+    oi, oe, rst = orc.odom_solve(types, pts, coeffs, xp, xi0, xe0, free_mask, max_it=max_it)
+    assert st["lm_iterations"] == rst["lm_iterations"] and st["termination"] == rst["termination"]
+    for a, b in ((gi, oi), (ge, oe)):
+        dt, dr = syn.pose_err(a, b)
+        assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+    assert abs(st["final_cost"] - rst["final_cost"]) <= 1e-9 * max(1.0, rst["final_cost"])
+    if not free_mask & 1:
+        assert np.array_equal(gi, xi0)
+    if not free_mask & 2:
+        assert np.array_equal(ge, xe0)

@@ -266,3 +266,46 @@ def test_track_cloud_recovers_motion():
     assert st["n_corner"] + st["n_surf"] >= 10
     dt, dr = syn.pose_err(out, rel)
     assert dt < 0.05 and dr < 5e-3
+
+
+def _odom_problem(rng, n=400):
+    """Features consistent with a 3-pose chain: planes/lines through the chained point, plus noise."""
+    xp, xi, xe = (rand_pose(rng) for _ in range(3))
+    comp = syn.pose_mul(syn.pose_mul(syn.pose_inv(xp), xi), xe)
+    R = syn.quat_to_mat(comp[3:])
+    pts = rng.normal(size=(n, 3)) * 6
+    types = np.array([ord("s") if k % 3 else ord("c") for k in range(n)], np.uint8)
+    coeffs = np.zeros((n, 6))
+    for k in range(n):
+        lp = R @ pts[k] + comp[:3]
+        if types[k] == ord("s"):
+            nrm = rng.normal(size=3)
+            nrm /= np.linalg.norm(nrm)
+            coeffs[k, :4] = [*nrm, -nrm @ lp + rng.normal() * 0.01]
+        else:
+            d = rng.normal(size=3)
+            d /= np.linalg.norm(d)
+            off = np.cross(d, rng.normal(size=3)) * 0.01
+            coeffs[k] = [*(lp + off + 0.1 * d), *(lp + off - 0.1 * d)]
+    # float-valued like the reference's PointPlaneFeature (built from float clouds)
+    return xp, xi, xe, types, pts.astype(np.float32).astype(np.float64), coeffs.astype(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("free_mask", [1, 2, 3])
+def test_odom_solve_recovers_perturbed_blocks(free_mask):
+    rng = np.random.default_rng(70 + free_mask)
+    xp, xi, xe, types, pts, coeffs = _odom_problem(rng)
+    d = lambda: syn.pose7(rng.normal(size=3) * 0.02, syn.quat_from_rpy(*(rng.normal(size=3) * 0.004)))
+    xi0 = syn.pose_mul(xi, d()) if free_mask & 1 else xi
+    xe0 = syn.pose_mul(xe, d()) if free_mask & 2 else xe
+    oi, oe, st = orc.odom_solve(types, pts, coeffs, xp, xi0, xe0, free_mask, max_it=30)
+    assert st["lm_iterations"] >= 2
+    if not free_mask & 1:
+        assert np.array_equal(oi, xi0)
+    if not free_mask & 2:
+        assert np.array_equal(oe, xe0)
+    # the composed pivot<-sensor transform is what the residuals constrain
+    c_true = syn.pose_mul(syn.pose_mul(syn.pose_inv(xp), xi), xe)
+    c_est = syn.pose_mul(syn.pose_mul(syn.pose_inv(xp), oi), oe)
+    c_ini = syn.pose_mul(syn.pose_mul(syn.pose_inv(xp), xi0), xe0)
+    assert syn.pose_err(c_est, c_true)[0] < 0.25 * syn.pose_err(c_ini, c_true)[0]
