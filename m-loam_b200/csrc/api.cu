@@ -1,6 +1,7 @@
 // api.cu — the C ABI declared in include/mloam_b200.h: context, host<->device staging, and the
 // orchestrators (scan2MapOptimization, the per-sweep frame) expressed as kernel sequences on one stream.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -100,6 +101,7 @@ int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out
     return MLOAM_E_CUDA;
   }
   c->pinned_cap = kPinnedBytes;
+  if (const char *e = getenv("MLOAM_DISABLE_GRAPHS")) c->use_graphs = (e[0] == '0' || e[0] == '\0') ? 1 : 0;
   *out = h;
   return MLOAM_OK;
 }
@@ -110,6 +112,9 @@ void mloam_ctx_destroy(mloam_ctx_t *h) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   mloam_comm_destroy(h);
+  for (auto &g : c->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  c->graphs.clear();
   prof_collect(c);
   for (auto e : c->evt_pool) cudaEventDestroy(e);
   for (auto &m : c->maps) {

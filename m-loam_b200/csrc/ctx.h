@@ -10,6 +10,13 @@
 
 namespace mloam {
 
+// Bumped whenever a device buffer is (re)allocated: captured CUDA graphs hold raw pointers and are re-captured
+// when the epoch they were recorded in is over.
+inline unsigned long long &alloc_epoch() {
+  static unsigned long long e = 0;
+  return e;
+}
+
 // Grow-only device buffer (cudaMalloc only when capacity is exceeded; steady-state frames allocate nothing).
 struct DevBuf {
   void *p = nullptr;
@@ -20,6 +27,7 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
+    alloc_epoch()++;
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -101,6 +109,24 @@ struct Ctx {
 
   // NCCL (multi-GPU); opaque here
   int *d_extract_status = nullptr;  // device flag of the last extraction (1: ring window overflow / bad ScanInfo)
+  // CUDA-graph cache of whole frames (pipeline.cu frame_run)
+  struct ScanRef {
+    const float4 *surf;
+    int n_surf;            // count or upper bound
+    const int *d_n_surf;   // nullable device-side count
+    const float4 *corner;
+    int n_corner;
+    const int *d_n_corner;
+  };
+  struct GraphEntry {
+    unsigned long long key = 0, epoch = 0;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0, seen = 0, s2m_ran = 0;
+    ScanRef S{};
+  };
+  std::vector<GraphEntry> graphs;
+  int use_graphs = 1;
+  int s2m_ran = 0;
   int lm_min_corr = 0;              // lm_init_state: minimum matched features for a Solve (tracker: 10)
   double lm_eig_thre = -1.0;        // < 0: use params.eig_thre; the tracker disables evalDegenracy with 0
   int want_eig = 1;                // k_lm mode 1: always run the 6x6 eigen-solver (1) or only when degenerate (0)

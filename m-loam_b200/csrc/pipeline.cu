@@ -16,22 +16,17 @@ using namespace mloam;
 
 namespace {
 
-struct ScanRef {
-  const float4 *surf;
-  int n_surf;            // count or upper bound
-  const int *d_n_surf;   // nullable
-  const float4 *corner;
-  int n_corner;
-  const int *d_n_corner;
-};
+typedef Ctx::ScanRef ScanRef;
 
-int scan2map_run(Ctx *c, const ScanRef &S, const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+// Enqueue the whole solve on the context stream (no host synchronisation when max_inner == 1, so the sequence can be
+// captured into a CUDA graph); scan2map_finish() waits and unpacks.  c->s2m_ran tells finish whether the gate passed.
+int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
   const mloam_params_t &P = c->params;
-  if (stats) memset(stats, 0, sizeof(*stats));
-  for (int k = 0; k < 7; k++) pose_out7[k] = pose_init7[k];
+  c->s2m_ran = 0;
   const MapStorage &MS = c->maps[MLOAM_MAP_SURF], &MC = c->maps[MLOAM_MAP_CORNER];
   if (!MS.built || !MC.built) return fail(c, MLOAM_E_STATE, "scan2map: build MLOAM_MAP_SURF and MLOAM_MAP_CORNER first");
   if (!((MS.m > 50) && (MC.m > 10))) return MLOAM_OK;  // lidar_mapper_keyframe.cpp:429 ("Map surf num is not enough")
+  c->s2m_ran = 1;
   int rc = reserve_feat(c, 0, S.n_corner);
   if (rc) return rc;
   rc = reserve_feat(c, 1, S.n_surf);
@@ -78,11 +73,22 @@ int scan2map_run(Ctx *c, const ScanRef &S, const double *pose_init7, double *pos
   char *pin = reinterpret_cast<char *>(c->pinned);
   LMState *hs = reinterpret_cast<LMState *>(pin + 4096);
   int *h_cnt = reinterpret_cast<int *>(pin + 3072);
-  h_cnt[0] = S.n_surf, h_cnt[1] = S.n_corner;
   MLOAM_CUDA_OK(c, cudaMemcpyAsync(hs, st, sizeof(LMState), cudaMemcpyDeviceToHost, c->stream));
   if (S.d_n_surf) MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_cnt, S.d_n_surf, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   if (S.d_n_corner) MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_cnt + 1, S.d_n_corner, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  return MLOAM_OK;
+}
+
+int scan2map_finish(Ctx *c, const ScanRef &S, const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+  if (stats) memset(stats, 0, sizeof(*stats));
+  for (int k = 0; k < 7; k++) pose_out7[k] = pose_init7[k];
+  if (!c->s2m_ran) return MLOAM_OK;
+  char *pin = reinterpret_cast<char *>(c->pinned);
+  const LMState *hs = reinterpret_cast<const LMState *>(pin + 4096);
+  int *h_cnt = reinterpret_cast<int *>(pin + 3072);
   MLOAM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  if (!S.d_n_surf) h_cnt[0] = S.n_surf;
+  if (!S.d_n_corner) h_cnt[1] = S.n_corner;
   for (int k = 0; k < 7; k++) pose_out7[k] = hs->x[k];
   if (stats) {
     stats->ran = 1;
@@ -96,6 +102,12 @@ int scan2map_run(Ctx *c, const ScanRef &S, const double *pose_init7, double *pos
     stats->n_surf_in = h_cnt[0], stats->n_corner_in = h_cnt[1];
   }
   return MLOAM_OK;
+}
+
+int scan2map_run(Ctx *c, const ScanRef &S, const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+  int rc = scan2map_enqueue(c, S, pose_init7);
+  if (rc) return rc;
+  return scan2map_finish(c, S, pose_init7, pose_out7, stats);
 }
 
 // Device buffers of one frame: feature sets of extractCloud + the down-sampled scans fed to matching.
@@ -126,9 +138,9 @@ int frame_bufs(Ctx *c, int n, FrameBufs *F) {
   return MLOAM_OK;
 }
 
-int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
-              const float4 *d_surf_map, int n_surf_map, const float4 *d_corner_map, int n_corner_map, int rebuild_maps,
-              const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
+                  const float4 *d_surf_map, int n_surf_map, const float4 *d_corner_map, int n_corner_map, int rebuild_maps,
+                  const double *pose_init7, ScanRef *S_out) {
   const mloam_params_t &P = c->params;
   int rc;
   if (rebuild_maps) {  // lidar_mapper_keyframe.cpp:433-434 (every frame in the reference)
@@ -159,7 +171,85 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
   rc = voxel_downsample_device(c, F.ex.less_flat, n, F.ex.counts + 3, P.surf_leaf, 1, F.surf_ds, F.n_surf_ds, 5);
   if (rc) return rc;
   ScanRef S{F.surf_ds, n, F.n_surf_ds, F.corner_ds, less_cap, F.n_corner_ds};
-  return scan2map_run(c, S, pose_init7, pose_out7, stats);
+  *S_out = S;
+  return scan2map_enqueue(c, S, pose_init7);
+}
+
+unsigned long long fnv1a(unsigned long long h, const void *p, size_t n) {
+  const unsigned char *b = static_cast<const unsigned char *>(p);
+  for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+  return h;
+}
+
+// One frame.  With max_inner == 1 the ~170 launches of a frame form a fixed sequence that depends on the host only
+// through the pose guess (staged in pinned memory) — it is captured once per (buffers, sizes, parameters) into a CUDA
+// graph and replayed: the first call with a new key runs on the stream (and performs every allocation), the second
+// captures + instantiates, later ones replay.  Profiling, multi-GPU (NCCL on the stream) and max_inner > 1 (the host
+// polls the LM done flag) use the plain stream path.
+int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
+              const float4 *d_surf_map, int n_surf_map, const float4 *d_corner_map, int n_corner_map, int rebuild_maps,
+              const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
+  ScanRef S{};
+  const bool can_graph = c->use_graphs && c->params.max_inner == 1 && !c->prof_on && !c->nccl_comm;
+  if (can_graph) {
+    unsigned long long key = 1469598103934665603ull;
+    const void *ptrs[5] = {d_cloud, d_scan_start, d_scan_end, d_surf_map, d_corner_map};
+    const int ints[6] = {n, n_scans, n_surf_map, n_corner_map, rebuild_maps, c->has_ext ? 1 : 0};
+    key = fnv1a(key, ptrs, sizeof(ptrs));
+    key = fnv1a(key, ints, sizeof(ints));
+    key = fnv1a(key, &c->params, sizeof(c->params));
+    key = fnv1a(key, c->ext, sizeof(c->ext));
+    key = fnv1a(key, &c->stream, sizeof(c->stream));
+    Ctx::GraphEntry *e = nullptr;
+    for (auto &g : c->graphs)
+      if (g.key == key) e = &g;
+    if (e && e->exec && e->epoch == alloc_epoch()) {
+      double *stage = reinterpret_cast<double *>(c->pinned);
+      for (int k = 0; k < 7; k++) stage[k] = pose_init7[k];  // the captured H2D node reads this at execution time
+      if (c->has_ext)
+        for (int k = 0; k < 7; k++) stage[32 + k] = c->ext[k];
+      MLOAM_CUDA_OK(c, cudaGraphLaunch(e->exec, c->stream));
+      c->launches += e->launches;
+      c->s2m_ran = e->s2m_ran;
+      return scan2map_finish(c, e->S, pose_init7, pose_out7, stats);
+    }
+    if (e && e->seen >= 1) {  // second sighting: capture
+      if (e->exec) cudaGraphExecDestroy(e->exec), e->exec = nullptr;
+      const long long l0 = c->launches;
+      const unsigned long long ep0 = alloc_epoch();
+      cudaGraph_t graph = nullptr;
+      MLOAM_CUDA_OK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = frame_enqueue(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, d_surf_map, n_surf_map, d_corner_map, n_corner_map,
+                             rebuild_maps, pose_init7, &S);
+      cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+      if (rc == MLOAM_OK && ce == cudaSuccess && graph && ep0 == alloc_epoch() &&
+          cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess) {
+        e->launches = (int)(c->launches - l0), e->epoch = ep0, e->S = S, e->s2m_ran = c->s2m_ran;
+        c->launches = l0;
+        cudaGraphDestroy(graph);
+        MLOAM_CUDA_OK(c, cudaGraphLaunch(e->exec, c->stream));
+        c->launches += e->launches;
+        return scan2map_finish(c, S, pose_init7, pose_out7, stats);
+      }
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      e->exec = nullptr, e->seen = 0;  // capture failed: fall through to the stream path
+      c->launches = l0;
+      if (rc) return rc;
+    } else if (!e) {
+      if (c->graphs.size() >= 32) {
+        if (c->graphs.front().exec) cudaGraphExecDestroy(c->graphs.front().exec);
+        c->graphs.erase(c->graphs.begin());
+      }
+      Ctx::GraphEntry g;
+      g.key = key, g.seen = 1;
+      c->graphs.push_back(g);
+    }
+  }
+  int rc = frame_enqueue(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, d_surf_map, n_surf_map, d_corner_map, n_corner_map,
+                         rebuild_maps, pose_init7, &S);
+  if (rc) return rc;
+  return scan2map_finish(c, S, pose_init7, pose_out7, stats);
 }
 
 }  // namespace

@@ -444,3 +444,30 @@ def test_odom_solve_matches_oracle(ctx, free_mask, max_it):
         assert np.array_equal(gi, xi0)
     if not free_mask & 2:
         assert np.array_equal(ge, xe0)
+
+
+def test_frame_graph_replay_equals_stream_path(mloam, c1):
+    """max_inner == 1 frames are replayed from a captured CUDA graph from their third sighting on; the pose staged in pinned
+    memory must be re-read on every replay, and results must be bit-identical to the plain stream path."""
+    import os
+
+    p = mloam.default_params()
+    p.n_scans, p.max_outer, p.max_inner, p.map_cell = 16, 4, 1, 0.5
+    rng = np.random.Generator(np.random.PCG64(21))
+    inits = [syn.perturb_pose(c1["truth"], rng) for _ in range(5)]
+    os.environ["MLOAM_DISABLE_GRAPHS"] = "1"
+    try:
+        plain = mloam.Context(0, p)
+    finally:
+        os.environ.pop("MLOAM_DISABLE_GRAPHS")
+    ref = [plain.frame(c1["cloud"], c1["ss"], c1["se"], c1["surf_map"], c1["corner_map"], x)[0] for x in inits]
+    n_plain = plain.launch_count()
+    plain.close()
+    g = mloam.Context(0, p)
+    out = [g.frame(c1["cloud"], c1["ss"], c1["se"], c1["surf_map"], c1["corner_map"], x) for x in inits]
+    for (pose, st), r in zip(out, ref):
+        assert np.array_equal(pose, r)
+        assert st["ran"] == 1 and st["n_surf"] > 1000
+    assert len({tuple(p_) for p_, _ in out}) == len(inits)  # different guesses -> different (re-read) inputs
+    assert g.launch_count() == n_plain                       # replayed launches are accounted for
+    g.close()
