@@ -170,6 +170,17 @@ int mloam_scan2map_device(mloam_ctx_t *ctx, const mloam_point_t *d_surf_scan, in
                           const mloam_point_t *d_corner_scan, int n_corner, const double *pose_init7,
                           double *pose_out7, mloam_solve_stats_t *stats);
 
+/* ---- uncertainty-aware mapping (with_ua): evalPointUncertainty (associate_uct.hpp:164-215) for a batch of points
+ * under the pose `pose7` with covariance cov_pose36 (row-major 6x6: translation, rotation) and measurement covariance
+ * cov_meas9 (COV_MEASUREMENT); h_cov6[n*6] receives PointIWithCov::cov_vec (float xx xy xz yy yz zz).
+ * mloam_scan2map_ua is mloam_scan2map with every residual weighted by the clamped sqrt(1/trace) of its scan point's
+ * covariance (extractCov + lidar_map_factor.hpp:34,41; lidar_mapper_keyframe.cpp:541-545,556-560). */
+int mloam_point_uncertainty(mloam_ctx_t *ctx, const mloam_point_t *h_pts, int n, const double *pose7, const double *cov_pose36,
+                            const double *cov_meas9, float *h_cov6);
+int mloam_scan2map_ua(mloam_ctx_t *ctx, const mloam_point_t *h_surf_scan, int n_surf, const float *h_surf_cov6,
+                      const mloam_point_t *h_corner_scan, int n_corner, const float *h_corner_cov6, const double *pose_init7,
+                      double *pose_out7, mloam_solve_stats_t *stats);
+
 /* ---- the whole per-scan hot path for one LiDAR sweep (extractCloud -> scan down-sampling ->
  * scan2MapOptimization), inputs in host memory (mloam_frame) or already resident in HBM
  * (mloam_frame_device).  rebuild_maps != 0 re-runs setInputCloud on the two maps first, as the reference

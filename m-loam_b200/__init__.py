@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
-    "mloam_frame_device", "mloam_set_extrinsic", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy",
+    "mloam_frame_device", "mloam_set_extrinsic", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy",
 ]
 
 
@@ -313,6 +313,25 @@ class Context:
         st = SolveStats()
         self._ck(lib().mloam_track_cloud(self._h, _p(a), a.shape[0], _p(b), b.shape[0], _p(c), c.shape[0], _p(d), d.shape[0], _p(pi),
                                          _p(out), C.byref(st)))
+        return out, st.as_dict()
+
+    def point_uncertainty(self, pts, pose7, cov_pose, cov_meas):
+        pts = _cloud(pts)
+        pose = np.ascontiguousarray(pose7, np.float64)
+        cp = np.ascontiguousarray(cov_pose, np.float64).reshape(36)
+        cm = np.ascontiguousarray(cov_meas, np.float64).reshape(9)
+        out = np.zeros((pts.shape[0], 6), np.float32)
+        self._ck(lib().mloam_point_uncertainty(self._h, _p(pts), pts.shape[0], _p(pose), _p(cp), _p(cm), _p(out)))
+        return out
+
+    def scan2map_ua(self, surf_scan, surf_cov6, corner_scan, corner_cov6, pose_init7):
+        ss, cs = _cloud(surf_scan), _cloud(corner_scan)
+        sc = np.ascontiguousarray(surf_cov6, np.float32)
+        cc = np.ascontiguousarray(corner_cov6, np.float32)
+        pi = np.ascontiguousarray(pose_init7, np.float64)
+        out = np.zeros(7)
+        st = SolveStats()
+        self._ck(lib().mloam_scan2map_ua(self._h, _p(ss), ss.shape[0], _p(sc), _p(cs), cs.shape[0], _p(cc), _p(pi), _p(out), C.byref(st)))
         return out, st.as_dict()
 
     def odom_solve(self, types, points, coeffs, pivot7, pose_i7, ext7, free_mask: int, max_iterations: int = 4, huber_a: float = 1.0,

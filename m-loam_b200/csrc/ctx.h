@@ -117,6 +117,7 @@ struct Ctx {
     const float4 *corner;
     int n_corner;
     const int *d_n_corner;
+    const double *sinfo_surf, *sinfo_corner;  // nullable per-feature sqrt_info (uncertainty-aware mapping)
   };
   struct GraphEntry {
     unsigned long long key = 0, epoch = 0;
@@ -193,6 +194,7 @@ struct FeatSet {
   int n;                       // count, or launch upper bound when d_n is set
   int is_plane;                // 1: LidarMapPlaneNormFactor, 0: LidarMapEdgeFactor
   const int *d_n;              // nullable device-side count
+  const double *sinfo;         // nullable per-feature sqrt_info (with_ua: lidar_map_factor.hpp:34,41 on the point's covariance)
 };
 // Accumulate loss-corrected normal equations of both feature sets at pose *d_pose7 (or LMState x / xc when
 // use_state != 0: 1 -> x, 2 -> xc) into c->partials, then run the LM state machine step (`lm_mode`):
@@ -205,6 +207,9 @@ int factor_evaluate_device(Ctx *c, int kind, int n, const double *d_points, cons
 
 // in place: p <- T * p for the first min(n, *d_n) points (pointAssociateToMap, utility.h:103-117); d_pose7 on device
 int transform_points_device(Ctx *c, float4 *d_pts, int n, const int *d_n, const double *d_pose7);
+
+// uct_kernels.cu: per-point sqrt_info from PointIWithCov::cov_vec (float[6] per point)
+int sqrt_info_device(Ctx *c, const float *d_cov6, int n, double *d_sinfo);
 
 // comm.cu: in-place sum over ranks on the context stream (no-op without a communicator)
 int comm_allreduce_doubles(Ctx *c, double *d_buf, int count);

@@ -40,8 +40,8 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
   int *h_done = reinterpret_cast<int *>(reinterpret_cast<char *>(c->pinned) + 2048);
   const int nc_use = P.point_edge_factor ? S.n_corner : 0, ns_use = P.point_plane_factor ? S.n_surf : 0;
   FeatSet sets[2] = {
-      FeatSet{S.corner, c->feat_valid[0].as<unsigned char>(), c->feat_coeff[0].as<float>(), nc_use, 0, S.d_n_corner},
-      FeatSet{S.surf, c->feat_valid[1].as<unsigned char>(), c->feat_coeff[1].as<float>(), ns_use, 1, S.d_n_surf}};
+      FeatSet{S.corner, c->feat_valid[0].as<unsigned char>(), c->feat_coeff[0].as<float>(), nc_use, 0, S.d_n_corner, S.sinfo_corner},
+      FeatSet{S.surf, c->feat_valid[1].as<unsigned char>(), c->feat_coeff[1].as<float>(), ns_use, 1, S.d_n_surf, S.sinfo_surf}};
   for (int outer = 0; outer < P.max_outer; outer++) {
     // :503-532  match corner then surf at pose_wmap_curr (wo_gf: every feature)
     {
@@ -278,6 +278,37 @@ int mloam_scan2map(mloam_ctx_t *h, const mloam_point_t *h_surf_scan, int n_surf,
   if (n_surf > 0)
     MLOAM_CUDA_OK(c, cudaMemcpyAsync(c->scan_pts[1].p, h_surf_scan, sizeof(float4) * (size_t)n_surf, cudaMemcpyHostToDevice, c->stream));
   ScanRef S{c->scan_pts[1].as<float4>(), n_surf, nullptr, c->scan_pts[0].as<float4>(), n_corner, nullptr};
+  return scan2map_run(c, S, pose_init7, pose_out7, stats);
+}
+
+// scan2MapOptimization with with_ua = true (lidar_mapper_keyframe.cpp:541-545,556-560): every residual is weighted by
+// sqrt_info of its scan point's covariance (PointIWithCov::cov_vec, float[6] per point, from mloam_point_uncertainty).
+int mloam_scan2map_ua(mloam_ctx_t *h, const mloam_point_t *h_surf_scan, int n_surf, const float *h_surf_cov6,
+                      const mloam_point_t *h_corner_scan, int n_corner, const float *h_corner_cov6, const double *pose_init7,
+                      double *pose_out7, mloam_solve_stats_t *stats) {
+  if (!h || !pose_init7 || !pose_out7 || n_surf < 0 || n_corner < 0 || (n_surf > 0 && (!h_surf_scan || !h_surf_cov6)) ||
+      (n_corner > 0 && (!h_corner_scan || !h_corner_cov6)))
+    return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->stream;
+  const int ns[2] = {n_corner, n_surf};
+  const mloam_point_t *hp[2] = {h_corner_scan, h_surf_scan};
+  const float *hc[2] = {h_corner_cov6, h_surf_cov6};
+  DevBuf *cov[2] = {&c->scratch[1], &c->scratch[2]}, *sin[2] = {&c->scratch[3], &c->scratch[4]};
+  for (int t = 0; t < 2; t++) {
+    MLOAM_CUDA_OK(c, c->scan_pts[t].reserve(sizeof(float4) * (size_t)(ns[t] + 1)));
+    MLOAM_CUDA_OK(c, cov[t]->reserve(sizeof(float) * 6 * (size_t)(ns[t] + 1)));
+    MLOAM_CUDA_OK(c, sin[t]->reserve(sizeof(double) * (size_t)(ns[t] + 1)));
+    if (ns[t] > 0) {
+      MLOAM_CUDA_OK(c, cudaMemcpyAsync(c->scan_pts[t].p, hp[t], sizeof(float4) * (size_t)ns[t], cudaMemcpyHostToDevice, st));
+      MLOAM_CUDA_OK(c, cudaMemcpyAsync(cov[t]->p, hc[t], sizeof(float) * 6 * (size_t)ns[t], cudaMemcpyHostToDevice, st));
+      int rc = sqrt_info_device(c, cov[t]->as<float>(), ns[t], sin[t]->as<double>());
+      if (rc) return rc;
+    }
+  }
+  ScanRef S{c->scan_pts[1].as<float4>(), n_surf, nullptr, c->scan_pts[0].as<float4>(), n_corner, nullptr, sin[1]->as<double>(),
+            sin[0]->as<double>()};
   return scan2map_run(c, S, pose_init7, pose_out7, stats);
 }
 

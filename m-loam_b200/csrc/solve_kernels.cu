@@ -25,6 +25,7 @@ struct FeatSetDev {
   int n;
   int is_plane;
   const int *d_n;
+  const double *sinfo;
 };
 struct LinArgs {
   FeatSetDev set[2];
@@ -82,11 +83,12 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
         else acc[NE_H + NE_G + 2] += 1.0;
         continue;
       }
+      const double si = fs.sinfo ? fs.sinfo[i] : a.sqrt_info;  // per-feature weight when mapping is uncertainty-aware
       if (fs.is_plane) {
-        r = plane_factor(P, p, D3{(double)cf[0], (double)cf[1], (double)cf[2]}, (double)cf[3], a.sqrt_info, J, true);
+        r = plane_factor(P, p, D3{(double)cf[0], (double)cf[1], (double)cf[2]}, (double)cf[3], si, J, true);
       } else {
         r = edge_factor(P, p, D3{(double)cf[0], (double)cf[1], (double)cf[2]}, D3{(double)cf[3], (double)cf[4], (double)cf[5]},
-                        a.sqrt_info, J, true);
+                        si, J, true);
       }
       double rho, rho1;
       huber(a.huber_a, r * r, &rho, &rho1);
@@ -456,9 +458,11 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
     if (s < n_sets) {
       a.set[s].pts = sets[s].pts, a.set[s].valid = sets[s].valid, a.set[s].coeff = sets[s].coeff;
       a.set[s].n = sets[s].n, a.set[s].is_plane = sets[s].is_plane, a.set[s].d_n = sets[s].d_n;
+      a.set[s].sinfo = sets[s].sinfo;
       n_total = sets[s].n > n_total ? sets[s].n : n_total;
     } else {
       a.set[s].pts = nullptr, a.set[s].valid = nullptr, a.set[s].coeff = nullptr, a.set[s].n = 0, a.set[s].is_plane = 0, a.set[s].d_n = nullptr;
+      a.set[s].sinfo = nullptr;
     }
   }
   const int want_eig = c->want_eig;

@@ -214,6 +214,32 @@ void orc_scan2map(const float *surf_map, int n_sm, const float *corner_map, int 
   if (H36) std::memcpy(H36, r.H_last, sizeof(r.H_last));
 }
 
+// ---- evalPointUncertainty for a batch: cov6[n*6] float (PointIWithCov::cov_vec layout)
+void orc_point_uncertainty(const float *pts, int n, const double *pose7, const double *cov_pose36, const double *cov_meas9, float *cov6) {
+  Pose p = to_pose(pose7);
+  for (int i = 0; i < n; i++)
+    eval_point_uncertainty(PointI{pts[i * 4], pts[i * 4 + 1], pts[i * 4 + 2], pts[i * 4 + 3]}, p, cov_pose36, cov_meas9, cov6 + (size_t)i * 6);
+}
+
+// ---- scan2MapOptimization with with_ua = true: per scan point cov_vec (float[6]) -> trace -> sqrt_info clamp
+void orc_scan2map_ua(const float *surf_map, int n_sm, const float *corner_map, int n_cm, const float *surf_scan, int n_ss,
+                     const float *surf_cov6, const float *corner_scan, int n_cs, const float *corner_cov6, const double *pose_init7,
+                     const double *opts, double *pose_out7, double *stats) {
+  Scan2MapOptions o;
+  o.max_outer = (int)opts[O_MAX_OUTER], o.max_inner = (int)opts[O_MAX_INNER], o.huber_a = opts[O_HUBER];
+  o.eig_thre = opts[O_EIG_THRE], o.n_neigh = (int)opts[O_N_NEIGH], o.check_fov = opts[O_CHECK_FOV] != 0;
+  o.point_plane = opts[O_POINT_PLANE] != 0, o.point_edge = opts[O_POINT_EDGE] != 0, o.cov_trace = opts[O_COV_TRACE];
+  o.mp = mp_from(opts);
+  std::vector<double> ts(n_ss), tc(n_cs);  // extractCov: float cov_vec -> Matrix3d; trace in double (point_with_cov.hpp:202-214)
+  for (int i = 0; i < n_ss; i++) ts[i] = (double)surf_cov6[i * 6] + (double)surf_cov6[i * 6 + 3] + (double)surf_cov6[i * 6 + 5];
+  for (int i = 0; i < n_cs; i++) tc[i] = (double)corner_cov6[i * 6] + (double)corner_cov6[i * 6 + 3] + (double)corner_cov6[i * 6 + 5];
+  o.surf_cov_trace = &ts, o.corner_cov_trace = &tc;
+  Cloud sm = to_cloud(surf_map, n_sm), cm = to_cloud(corner_map, n_cm), ss = to_cloud(surf_scan, n_ss), cs = to_cloud(corner_scan, n_cs);
+  Scan2MapResult r = scan2map(sm, cm, ss, cs, to_pose(pose_init7), o);
+  pose_to_param(r.pose, pose_out7);
+  if (stats) stats[0] = r.ran, stats[1] = r.n_surf, stats[2] = r.n_corner, stats[3] = r.lm_iterations, stats[4] = r.final_cost;
+}
+
 // ---- the whole per-sweep hot path on the CPU: extractCloud -> downsampleCurrentScan -> scan2MapOptimization
 // (the bench's cpu_baseline / --impl reference step).  stats[20]: [0..15] as orc_scan2map, [16] t_extract,
 // [17] t_downsample, [18] n_surf_in, [19] n_corner_in

@@ -19,6 +19,8 @@ struct Scan2MapOptions {
   bool point_plane = true;    // POINT_PLANE_FACTOR
   bool point_edge = true;     // POINT_EDGE_FACTOR
   double cov_trace = 0.0075;  // trace(COV_MEASUREMENT) = 3 * 0.0025 (with_ua=false, :541-545)
+  // with_ua=true (:541-545,556-560): per scan point covariance traces (extractCov of PointIWithCov); null = with_ua false
+  const std::vector<double> *surf_cov_trace = nullptr, *corner_cov_trace = nullptr;
   MatchParams mp;
 };
 struct Scan2MapResult {
@@ -67,12 +69,14 @@ inline Scan2MapResult scan2map(const Cloud &surf_map, const Cloud &corner_map, c
     res.t_match += now_s() - t0;
     res.n_surf = (int)surf_f.size(), res.n_corner = (int)corner_f.size();
     for (const Feature &f : surf_f) {  // :537-549
-      ResidualBlock b{F_PLANE, f.point, {f.coeffs[0], f.coeffs[1], f.coeffs[2], f.coeffs[3], 0, 0}, sinfo, {pid, 0, 0}};
+      const double si = o.surf_cov_trace ? map_sqrt_info((*o.surf_cov_trace)[f.idx]) : sinfo;
+      ResidualBlock b{F_PLANE, f.point, {f.coeffs[0], f.coeffs[1], f.coeffs[2], f.coeffs[3], 0, 0}, si, {pid, 0, 0}};
       problem.blocks.push_back(b);
     }
     for (const Feature &f : corner_f) {  // :552-571
+      const double si = o.corner_cov_trace ? map_sqrt_info((*o.corner_cov_trace)[f.idx]) : sinfo;
       ResidualBlock b{F_EDGE, f.point, {f.coeffs[0], f.coeffs[1], f.coeffs[2], f.coeffs[3], f.coeffs[4], f.coeffs[5]},
-                      sinfo, {pid, 0, 0}};
+                      si, {pid, 0, 0}};
       problem.blocks.push_back(b);
     }
     t0 = now_s();
@@ -96,6 +100,36 @@ inline Scan2MapResult scan2map(const Cloud &surf_map, const Cloud &corner_map, c
   }
   res.pose = pose_wmap_curr;
   return res;
+}
+
+// evalPointUncertainty, estimator/src/lidarMapper/associate_uct.hpp:164-215 (pointToFS :149-156):
+// cov_point = top-left 3x3 of G diag(cov_pose(6x6), COV_MEASUREMENT(3x3)) G^T,  G = [ I3 | -[T p]x | R ].
+// Output packed like PointIWithCov::cov_vec (float [xx xy xz yy yz zz], point_with_cov.hpp:45-53).
+inline void eval_point_uncertainty(const PointI &pi, const Pose &pose, const double cov_pose[36], const double cov_meas[9], float cov6[6]) {
+  const V3 tp = qrot(pose.q, V3{(double)pi.x, (double)pi.y, (double)pi.z}) + pose.t;
+  const M3 R = qmat(pose.q);
+  const M3 S = skew(tp);
+  double G[3][9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) G[i][j] = (i == j) ? 1.0 : 0.0, G[i][3 + j] = -S(i, j), G[i][6 + j] = R(i, j);
+  double Sig[9][9] = {{0}};
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) Sig[i][j] = cov_pose[i * 6 + j];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) Sig[6 + i][6 + j] = cov_meas[i * 3 + j];
+  double C[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0;
+      for (int a = 0; a < 9; a++) {
+        double t = 0;
+        for (int b = 0; b < 9; b++) t += Sig[a][b] * G[j][b];
+        s += G[i][a] * t;
+      }
+      C[i][j] = s;
+    }
+  cov6[0] = (float)C[0][0], cov6[1] = (float)C[0][1], cov6[2] = (float)C[0][2], cov6[3] = (float)C[1][1], cov6[4] = (float)C[1][2],
+  cov6[5] = (float)C[2][2];
 }
 
 struct TrackOptions {

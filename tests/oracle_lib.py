@@ -265,6 +265,30 @@ def frame(cloud_, scan_start, scan_end, surf_map, corner_map, pose_init, opts=No
     return out, st
 
 
+def point_uncertainty(pts, pose7, cov_pose, cov_meas):
+    pts = cloud(pts)
+    pose7 = np.ascontiguousarray(pose7, np.float64)
+    cp = np.ascontiguousarray(cov_pose, np.float64).reshape(36)
+    cm = np.ascontiguousarray(cov_meas, np.float64).reshape(9)
+    out = np.zeros((pts.shape[0], 6), np.float32)
+    lib().orc_point_uncertainty(_p(pts), pts.shape[0], _p(pose7), _p(cp), _p(cm), _p(out))
+    return out
+
+
+def scan2map_ua(surf_map, corner_map, surf_scan, surf_cov6, corner_scan, corner_cov6, pose_init, opts=None):
+    sm, cm, ss, cs = cloud(surf_map), cloud(corner_map), cloud(surf_scan), cloud(corner_scan)
+    sc = np.ascontiguousarray(surf_cov6, np.float32)
+    cc = np.ascontiguousarray(corner_cov6, np.float32)
+    opts = default_opts() if opts is None else np.ascontiguousarray(opts, np.float64)
+    pose_init = np.ascontiguousarray(pose_init, np.float64)
+    out = np.empty(7)
+    stats = np.zeros(8)
+    lib().orc_scan2map_ua(_p(sm), sm.shape[0], _p(cm), cm.shape[0], _p(ss), ss.shape[0], _p(sc), _p(cs), cs.shape[0], _p(cc),
+                          _p(pose_init), _p(opts), _p(out), _p(stats))
+    return out, {"ran": stats[0], "n_surf": int(stats[1]), "n_corner": int(stats[2]), "lm_iterations": int(stats[3]),
+                 "final_cost": stats[4]}
+
+
 def odom_solve(types, points, coeffs, pivot, pose_i, ext, free_mask, max_it=4, huber_a=1.0, sqrt_info=1.0):
     types = np.ascontiguousarray(types, np.uint8)
     points = np.ascontiguousarray(points, np.float64)

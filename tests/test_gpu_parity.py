@@ -471,3 +471,34 @@ def test_frame_graph_replay_equals_stream_path(mloam, c1):
     assert len({tuple(p_) for p_, _ in out}) == len(inits)  # different guesses -> different (re-read) inputs
     assert g.launch_count() == n_plain                       # replayed launches are accounted for
     g.close()
+
+
+# ------------------------------------------------------------------------------------------------ uncertainty-aware mapping
+def test_point_uncertainty_and_scan2map_ua(ctx, c1):
+    rng = np.random.default_rng(12)
+    ext = syn.pose7([0.3, -0.2, 0.1], syn.quat_from_rpy(0.02, -0.01, 0.5))
+    A = rng.normal(size=(6, 6)) * 0.01
+    cov_pose = A @ A.T + np.diag([1e-4] * 3 + [1e-5] * 3)
+    cov_meas = np.diag([0.0025, 0.0025, 0.0025])
+    pts = c1["surf_scan"]
+    cov6 = ctx.point_uncertainty(pts, ext, cov_pose, cov_meas)
+    ref6 = orc.point_uncertainty(pts, ext, cov_pose, cov_meas)
+    assert np.allclose(cov6, ref6, rtol=2e-6, atol=1e-9)
+    assert np.all(cov6[:, [0, 3, 5]] > 0)
+    # known answer: zero pose covariance -> cov = R COV_MEASUREMENT R^T = 0.0025 I for an isotropic measurement covariance
+    iso = ctx.point_uncertainty(pts[:16], ext, np.zeros((6, 6)), cov_meas)
+    assert np.allclose(iso[:, [0, 3, 5]], 0.0025, rtol=1e-6) and np.allclose(iso[:, [1, 2, 4]], 0.0, atol=1e-9)
+    # weighted solve: distance-dependent covariances (far points weigh less), both factor types
+    sc = ctx.point_uncertainty(c1["surf_scan"], ext, cov_pose * 40, cov_meas)
+    cc = ctx.point_uncertainty(c1["corner_scan"], ext, cov_pose * 40, cov_meas)
+    tr = sc[:, 0] + sc[:, 3] + sc[:, 5]
+    assert (np.sqrt(1 / tr) < 3).mean() > 0.2  # a good share of the weights is below the clamp
+    ctx.map_build(1, c1["surf_map"], 0.5)
+    ctx.map_build(0, c1["corner_map"], 0.5)
+    pose, st = ctx.scan2map_ua(c1["surf_scan"], sc, c1["corner_scan"], cc, c1["init"])
+    ref, rst = orc.scan2map_ua(c1["surf_map"], c1["corner_map"], c1["surf_scan"], sc, c1["corner_scan"], cc, c1["init"])
+    dt, dr = syn.pose_err(pose, ref)
+    assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+    assert st["n_surf"] == rst["n_surf"] and st["lm_iterations"] == rst["lm_iterations"]
+    plain, _ = ctx.scan2map(c1["surf_scan"], c1["corner_scan"], c1["init"])
+    assert not np.allclose(pose, plain, atol=1e-9)  # the weights matter
