@@ -95,6 +95,10 @@ int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out
   if (params) c->params = *params;
   else mloam_default_params(&c->params);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_maps, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(&c->pinned, kPinnedBytes) != cudaSuccess || c->lm_state.reserve(sizeof(LMState) + 64) != cudaSuccess ||
       c->scratch[7].reserve(4096) != cudaSuccess) {
     delete h;
@@ -125,6 +129,10 @@ void mloam_ctx_destroy(mloam_ctx_t *h) {
   for (auto &s : c->scratch) s.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamSynchronize(c->stream2), cudaStreamDestroy(c->stream2);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_maps) cudaEventDestroy(c->ev_maps);
   delete h;
 }
 

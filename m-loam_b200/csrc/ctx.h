@@ -79,6 +79,10 @@ struct Ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t stream2 = nullptr;        // side stream: submap upload + build run concurrently with extraction
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_maps = nullptr;         // recorded on stream2 after the host API's submap H2D copies
+  bool maps_pending = false;             // the map-build branch must wait on ev_maps (external to a captured graph)
   mloam_params_t params;
   std::string err;
   long long launches = 0;

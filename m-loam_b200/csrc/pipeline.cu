@@ -143,11 +143,36 @@ int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start,
                   const double *pose_init7, ScanRef *S_out) {
   const mloam_params_t &P = c->params;
   int rc;
+  bool forked = false;
   if (rebuild_maps) {  // lidar_mapper_keyframe.cpp:433-434 (every frame in the reference)
+    // The two submap builds do not depend on the sweep: they run on a forked side stream, concurrently with
+    // extraction + scan down-sampling, and join right before matching (also inside a captured graph).
+    // With stage profiling on the branch stays on the main stream so that per-stage event times do not overlap.
+    forked = !c->prof_on;
+    if (!forked) {
+      if (c->maps_pending) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_maps, 0));
+      rc = map_build_device(c, MLOAM_MAP_SURF, d_surf_map, n_surf_map, pick_cell(c, 0.f));
+      if (rc == MLOAM_OK) rc = map_build_device(c, MLOAM_MAP_CORNER, d_corner_map, n_corner_map, pick_cell(c, 0.f));
+      if (rc) return rc;
+    }
+  }
+  if (forked) {
+    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_fork, c->stream));
+    MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    if (c->maps_pending) {
+      // mloam_frame copied the submaps on stream2 outside of any capture: inside a captured graph the branch waits
+      // on that record as an external event node; on the plain stream path stream2 is already ordered after it.
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      MLOAM_CUDA_OK(c, cudaStreamIsCapturing(c->stream2, &cs));
+      if (cs == cudaStreamCaptureStatusActive) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream2, c->ev_maps, cudaEventWaitExternal));
+    }
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->stream2;
     rc = map_build_device(c, MLOAM_MAP_SURF, d_surf_map, n_surf_map, pick_cell(c, 0.f));
+    if (rc == MLOAM_OK) rc = map_build_device(c, MLOAM_MAP_CORNER, d_corner_map, n_corner_map, pick_cell(c, 0.f));
+    c->stream = main_stream;
     if (rc) return rc;
-    rc = map_build_device(c, MLOAM_MAP_CORNER, d_corner_map, n_corner_map, pick_cell(c, 0.f));
-    if (rc) return rc;
+    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_join, c->stream2));
   }
   FrameBufs F;
   rc = frame_bufs(c, n, &F);
@@ -170,6 +195,7 @@ int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start,
   if (rc) return rc;
   rc = voxel_downsample_device(c, F.ex.less_flat, n, F.ex.counts + 3, P.surf_leaf, 1, F.surf_ds, F.n_surf_ds, 5);
   if (rc) return rc;
+  if (forked) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join the map-build branch
   ScanRef S{F.surf_ds, n, F.n_surf_ds, F.corner_ds, less_cap, F.n_corner_ds};
   *S_out = S;
   return scan2map_enqueue(c, S, pose_init7);
@@ -194,7 +220,7 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
   if (can_graph) {
     unsigned long long key = 1469598103934665603ull;
     const void *ptrs[5] = {d_cloud, d_scan_start, d_scan_end, d_surf_map, d_corner_map};
-    const int ints[6] = {n, n_scans, n_surf_map, n_corner_map, rebuild_maps, c->has_ext ? 1 : 0};
+    const int ints[7] = {n, n_scans, n_surf_map, n_corner_map, rebuild_maps, c->has_ext ? 1 : 0, c->maps_pending ? 1 : 0};
     key = fnv1a(key, ptrs, sizeof(ptrs));
     key = fnv1a(key, ints, sizeof(ints));
     key = fnv1a(key, &c->params, sizeof(c->params));
@@ -428,11 +454,17 @@ int mloam_frame(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *
     DevBuf &ms = c->scratch[1], &mc = c->scratch[2];
     MLOAM_CUDA_OK(c, ms.reserve(sizeof(float4) * (size_t)(n_surf_map + 1)));
     MLOAM_CUDA_OK(c, mc.reserve(sizeof(float4) * (size_t)(n_corner_map + 1)));
-    MLOAM_CUDA_OK(c, cudaMemcpyAsync(ms.p, h_surf_map, sizeof(float4) * (size_t)n_surf_map, cudaMemcpyHostToDevice, st));
-    MLOAM_CUDA_OK(c, cudaMemcpyAsync(mc.p, h_corner_map, sizeof(float4) * (size_t)n_corner_map, cudaMemcpyHostToDevice, st));
+    // The submaps (16 B/point, ~8x the sweep) go up on the side stream so that the copy overlaps extraction and scan
+    // down-sampling of the sweep; the map-build branch of frame_enqueue is ordered after ev_maps.
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(ms.p, h_surf_map, sizeof(float4) * (size_t)n_surf_map, cudaMemcpyHostToDevice, c->stream2));
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(mc.p, h_corner_map, sizeof(float4) * (size_t)n_corner_map, cudaMemcpyHostToDevice, c->stream2));
+    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_maps, c->stream2));
+    c->maps_pending = true;
     d_sm = ms.as<float4>(), d_cm = mc.as<float4>();
   }
-  return frame_run(c, d_cloud, n, d_ss, d_se, n_scans, d_sm, n_surf_map, d_cm, n_corner_map, rebuild_maps, pose_init7, pose_out7, stats);
+  const int rc = frame_run(c, d_cloud, n, d_ss, d_se, n_scans, d_sm, n_surf_map, d_cm, n_corner_map, rebuild_maps, pose_init7, pose_out7, stats);
+  c->maps_pending = false;
+  return rc;
 }
 
 int mloam_set_extrinsic(mloam_ctx_t *h, const double *ext7) {
