@@ -97,6 +97,7 @@ struct Ctx {
   DevBuf knn_pos[2];              // int[n_neigh] per query: neighbour positions handed from k_match_knn to k_match_fit
   DevBuf partials;                // per-block packed normal equations
   DevBuf lm_state;                // LMState
+  void *ticket_zeroed_for = nullptr;  // partials allocation whose last-block ticket has been zeroed
   DevBuf scratch[8];              // general scratch (knn outputs, factor batches, extraction, voxel)
   void *pinned = nullptr;         // pinned host staging (LMState mirror + small results)
   size_t pinned_cap = 0;

@@ -35,12 +35,24 @@ struct LinArgs {
   const LMState *state;    // state->x (use_state 1) / state->xc (use_state 2)
   int use_state;
   int respect_done;
+  // fused LM tail (single GPU): the block that finishes last reduces the partials and advances the state machine
+  int lm_mode;             // 1 | 2, or 0: no tail (partials only)
+  int want_eig;
+  double eig_thre;
+  unsigned *ticket;        // zero between launches
+  LMState *state_rw;
 };
+
+__device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMState *gst, int mode, double eig_thre, int want_eig, double *out_ne);
 
 __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__restrict__ partials) {
   __shared__ double sm[LIN_THREADS / 32][NE_PACK];
+  __shared__ bool is_last;
   const double *px = a.use_state == 1 ? a.state->x : (a.use_state == 2 ? a.state->xc : a.pose);
-  if (a.respect_done && a.state && a.state->done) return;  // Solve already terminated: nothing to evaluate
+  if (a.respect_done && a.state && a.state->done) {  // Solve already terminated: nothing to evaluate
+    if (a.lm_mode != 0 && blockIdx.x == 0 && threadIdx.x == 0) a.state_rw->work[0] = 0, a.state_rw->work[1] = 0;
+    return;
+  }
   const PoseR P = make_poser(px);
   double acc[NE_PACK];
 #pragma unroll
@@ -128,6 +140,17 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
     for (int w = 0; w < LIN_THREADS / 32; w++) v += sm[w][threadIdx.x];
     partials[(size_t)blockIdx.x * NE_PACK + threadIdx.x] = v;
   }
+  if (a.lm_mode == 0) return;
+  // ---- fused tail: the last block to arrive sums the partials in block order (so the result does not depend on
+  // which block that is) and runs the LM step that a separate k_lm launch used to do.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  lm_tail(partials, (int)gridDim.x, a.state_rw, a.lm_mode, a.eig_thre, a.want_eig, nullptr);
+  if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
 // ---------------------------------------------------------------------------------------- small dense (device)
@@ -293,31 +316,9 @@ __device__ void unpack_ne(const double *ne, double *H, double *g) {
   for (int k = 0; k < 6; k++) g[k] = ne[NE_H + k];
 }
 
+// One thread advances the state machine on a shared-memory copy of the state (lm_tail stages it in and out).
 // mode 1: begin a Solve with the evaluation at x.  mode 2: digest the evaluation at xc.
-__global__ void __launch_bounds__(LM_THREADS) k_lm(const double *__restrict__ partials, int n_blocks, LMState *st, int mode, double eig_thre, int want_eig,
-                     double *__restrict__ out_ne) {
-  // block partials -> packed normal equations, in a fixed order (deterministic): warp w sums blocks w, w+8, ...
-  // for component `lane`, then the 8 warp sums are added in warp order.
-  __shared__ double ne[NE_PACK];
-  __shared__ double wsum[LM_THREADS / 32][32];
-  {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    double v = 0.0;
-    if (lane < NE_PACK)
-      for (int b = w; b < n_blocks; b += LM_THREADS / 32) v += partials[(size_t)b * NE_PACK + lane];
-    wsum[w][lane] = v;
-    __syncthreads();
-    if (threadIdx.x < NE_PACK) {
-      double t = 0.0;
-#pragma unroll
-      for (int ww = 0; ww < LM_THREADS / 32; ww++) t += wsum[ww][threadIdx.x];
-      ne[threadIdx.x] = t;
-      if (out_ne) out_ne[threadIdx.x] = t;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0 && mode != 0) st->work[0] = 0, st->work[1] = 0;  // re-arm the match work queues
-  if (threadIdx.x != 0 || mode == 0) return;
+__device__ void lm_advance(LMState *st, const double *ne, int mode, double eig_thre, int want_eig) {
   double H[36], g[6];
   unpack_ne(ne, H, g);
   const double cost = ne[NE_H + NE_G];
@@ -422,6 +423,64 @@ __global__ void __launch_bounds__(LM_THREADS) k_lm(const double *__restrict__ pa
   lm_compute_step(st);
 }
 
+// Called by all LM_THREADS threads of one block.  Block partials -> packed normal equations in a fixed order
+// (deterministic): warp w sums blocks w, w+8, ... for component `lane`, then the 8 warp sums are added in warp order.
+// The LM state lives in global memory between launches; it is staged through shared memory here because the
+// single-threaded state machine touches it a few hundred times (each a dependent L2 round trip otherwise).
+__device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMState *gst, int mode, double eig_thre, int want_eig, double *out_ne) {
+  __shared__ double ne[NE_PACK];
+  __shared__ double wsum[LM_THREADS / 32][32];
+  __shared__ LMState s;
+  static_assert(sizeof(LMState) % 8 == 0, "LMState is staged as 8-byte words");
+  constexpr int kWords = (int)(sizeof(LMState) / 8);
+  if (mode != 0) {
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(gst);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(&s);
+    for (int k = threadIdx.x; k < kWords; k += LM_THREADS) dst[k] = __ldcg(src + k);
+  }
+  {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int S = LM_THREADS / 32;
+    double v = 0.0;
+    if (lane < NE_PACK) {
+      const double *p = partials + lane;
+      int b = w;
+      for (; b + 3 * S < n_blocks; b += 4 * S) {  // four loads in flight, same summation order
+        const double a0 = __ldcg(p + (size_t)b * NE_PACK), a1 = __ldcg(p + (size_t)(b + S) * NE_PACK),
+                     a2 = __ldcg(p + (size_t)(b + 2 * S) * NE_PACK), a3 = __ldcg(p + (size_t)(b + 3 * S) * NE_PACK);
+        v += a0, v += a1, v += a2, v += a3;
+      }
+      for (; b < n_blocks; b += S) v += __ldcg(p + (size_t)b * NE_PACK);
+    }
+    wsum[w][lane] = v;
+    __syncthreads();
+    if (threadIdx.x < NE_PACK) {
+      double t = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < S; ww++) t += wsum[ww][threadIdx.x];
+      ne[threadIdx.x] = t;
+      if (out_ne) out_ne[threadIdx.x] = t;
+    }
+  }
+  __syncthreads();
+  if (mode == 0) return;
+  if (threadIdx.x == 0) {
+    s.work[0] = 0, s.work[1] = 0;  // re-arm the match work queues
+    lm_advance(&s, ne, mode, eig_thre, want_eig);
+  }
+  __syncthreads();
+  {
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&s);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(gst);
+    for (int k = threadIdx.x; k < kWords; k += LM_THREADS) dst[k] = src[k];
+  }
+}
+
+__global__ void __launch_bounds__(LM_THREADS) k_lm(const double *__restrict__ partials, int n_blocks, LMState *st, int mode, double eig_thre,
+                                                  int want_eig, double *__restrict__ out_ne) {
+  lm_tail(partials, n_blocks, st, mode, eig_thre, want_eig, out_ne);
+}
+
 __global__ void k_lm_init(LMState *st, const double *pose7, int max_inner, int min_corr) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     for (int k = 0; k < 7; k++) st->x[k] = pose7[k], st->xc[k] = pose7[k];
@@ -474,11 +533,24 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
   if (nb < 1) nb = 1;
   const int max_nb = c->sm_count;
   if (nb > max_nb) nb = max_nb;
-  MLOAM_CUDA_OK(c, c->partials.reserve(sizeof(double) * NE_PACK * (size_t)(max_nb + 2)));
+  MLOAM_CUDA_OK(c, c->partials.reserve(sizeof(double) * NE_PACK * (size_t)(max_nb + 3)));
+  unsigned *ticket = reinterpret_cast<unsigned *>(c->partials.as<double>() + (size_t)NE_PACK * (max_nb + 2));
+  if (c->ticket_zeroed_for != c->partials.p) {  // a fresh partials buffer: the last-block ticket starts at zero
+    MLOAM_CUDA_OK(c, cudaMemsetAsync(ticket, 0, sizeof(double), c->stream));
+    c->ticket_zeroed_for = c->partials.p;
+  }
+  const double eig_thre = c->lm_eig_thre >= 0.0 ? c->lm_eig_thre : c->params.eig_thre;
+  const bool fused = lm_mode != 0 && !c->nccl_comm && !d_out30;
+  a.lm_mode = fused ? lm_mode : 0, a.want_eig = want_eig, a.eig_thre = eig_thre, a.ticket = ticket;
+  a.state_rw = c->lm_state.as<LMState>();
   {
     ProfScope ps(c, "linearize");
     k_linearize<<<nb, LIN_THREADS, 0, c->stream>>>(a, c->partials.as<double>());
     c->launches++;
+  }
+  if (fused) {
+    MLOAM_CUDA_OK(c, cudaGetLastError());
+    return MLOAM_OK;
   }
   if (c->nccl_comm && lm_mode != 0) {
     // multi-GPU: rank-local sum -> NCCL all-reduce of the 30 packed doubles -> identical LM step on every rank
