@@ -289,7 +289,7 @@ def main():
             st_k = step_device(args.warmup + k)[1]
             feats_prof += st_k["n_surf_in"] + st_k["n_corner_in"]
     barrier()
-    prof = {name: ctx.profile_get(name) for name in ("map_build", "extract", "voxel", "match", "fit", "linearize", "lm")}
+    prof = {name: ctx.profile_get(name) for name in ("map_build", "extract", "voxel", "match", "fit", "linearize", "lm", "lm_tail_reduce", "lm_tail_advance")}
     ctx.profile(False)
 
     # ---- e2e: HOST buffers through the C ABI (H2D sweep + both submaps, D2H pose) — wall clock around synchronous calls
@@ -308,7 +308,7 @@ def main():
         t_e2e = float(tt.item())
     e2e_value = world * e2e_steps / t_e2e
     h2d = int(frames[0]["cloud"].nbytes + 2 * RINGS * 4 + surf_map.nbytes + corner_map.nbytes + 7 * 8)
-    d2h = int(7 * 8 + 4 * 2 + 1272)  # pose + counts + LM state read-back
+    d2h = int(7 * 8 + 4 * 2 + 1304)  # pose + counts + LM state read-back
 
     if rank != 0:
         if world > 1:

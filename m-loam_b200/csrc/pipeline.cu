@@ -90,6 +90,14 @@ int scan2map_finish(Ctx *c, const ScanRef &S, const double *pose_init7, double *
   if (!S.d_n_surf) h_cnt[0] = S.n_surf;
   if (!S.d_n_corner) h_cnt[1] = S.n_corner;
   for (int k = 0; k < 7; k++) pose_out7[k] = hs->x[k];
+  if (c->prof_on) {  // device-side cycle counters of the fused LM tail, reported next to the event-timed stages
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+    if (khz > 0) {
+      c->prof["lm_tail_reduce"].ms += (double)hs->dbg_cycles[0] / khz, c->prof["lm_tail_reduce"].launches += hs->dbg_cycles[2];
+      c->prof["lm_tail_advance"].ms += (double)hs->dbg_cycles[1] / khz, c->prof["lm_tail_advance"].launches += hs->dbg_cycles[2];
+    }
+  }
   if (stats) {
     stats->ran = 1;
     stats->n_corner = hs->n_valid[0], stats->n_surf = hs->n_valid[1];

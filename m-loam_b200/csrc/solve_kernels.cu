@@ -201,32 +201,41 @@ __device__ void eig_sym6(const double *Ain, double *w, double *V) {
   }
 }
 
-__device__ bool chol6(double *A) {
-  const int N = 6;
+__device__ __forceinline__ bool chol6(double *A) {
+  constexpr int N = 6;
+#pragma unroll
   for (int j = 0; j < N; j++) {
     double d = A[j * N + j];
+#pragma unroll
     for (int k = 0; k < j; k++) d -= A[j * N + k] * A[j * N + k];
     if (!(d > 0.0)) return false;
     d = sqrt(d);
     A[j * N + j] = d;
+    const double inv_guard = d;
+#pragma unroll
     for (int i = j + 1; i < N; i++) {
       double s = A[i * N + j];
+#pragma unroll
       for (int k = 0; k < j; k++) s -= A[i * N + k] * A[j * N + k];
-      A[i * N + j] = s / d;
+      A[i * N + j] = s / inv_guard;
     }
   }
   return true;
 }
-__device__ void chol6_solve(const double *L, const double *b, double *x) {
-  const int N = 6;
+__device__ __forceinline__ void chol6_solve(const double *L, const double *b, double *x) {
+  constexpr int N = 6;
   double y[6];
+#pragma unroll
   for (int i = 0; i < N; i++) {
     double s = b[i];
+#pragma unroll
     for (int k = 0; k < i; k++) s -= L[i * N + k] * y[k];
     y[i] = s / L[i * N + i];
   }
+#pragma unroll
   for (int i = N - 1; i >= 0; i--) {
     double s = y[i];
+#pragma unroll
     for (int k = i + 1; k < N; k++) s -= L[k * N + i] * x[k];
     x[i] = s / L[i * N + i];
   }
@@ -253,13 +262,19 @@ __device__ void lm_compute_step(LMState *st) {
       return;
     }
     double Hs[36], gs[6], A[36], step[6];
+#pragma unroll
     for (int a = 0; a < 6; a++) {
       gs[a] = st->scale[a] * st->g[a];
+#pragma unroll
       for (int b = 0; b < 6; b++) Hs[a * 6 + b] = st->scale[a] * st->H[a * 6 + b] * st->scale[b];
     }
-    if (!st->reuse_diagonal)
+    if (!st->reuse_diagonal) {
+#pragma unroll
       for (int j = 0; j < 6; j++) st->diag[j] = fmin(fmax(Hs[j * 6 + j], kMinDiag), kMaxDiag);
+    }
+#pragma unroll
     for (int i = 0; i < 36; i++) A[i] = Hs[i];
+#pragma unroll
     for (int j = 0; j < 6; j++) {
       const double l = sqrt(st->diag[j] / st->radius);
       A[j * 6 + j] += l * l;
@@ -267,6 +282,7 @@ __device__ void lm_compute_step(LMState *st) {
     bool ok = chol6(A);
     if (ok) {
       chol6_solve(A, gs, step);
+#pragma unroll
       for (int j = 0; j < 6; j++) {
         step[j] = -step[j];
         if (!isfinite(step[j])) ok = false;
@@ -278,9 +294,11 @@ __device__ void lm_compute_step(LMState *st) {
     double mcc = 0;
     if (ok) {
       double sg = 0, sHs = 0;
+#pragma unroll
       for (int a = 0; a < 6; a++) {
         sg += step[a] * gs[a];
         double t = 0;
+#pragma unroll
         for (int b = 0; b < 6; b++) t += Hs[a * 6 + b] * step[b];
         sHs += step[a] * t;
       }
@@ -298,6 +316,7 @@ __device__ void lm_compute_step(LMState *st) {
     }
     st->num_invalid = 0;
     double delta[6];
+#pragma unroll
     for (int j = 0; j < 6; j++) delta[j] = step[j] * st->scale[j];
     pose_plus(st->x, delta, st->V_update, st->xc);
     st->model_cost_change = mcc;
@@ -433,6 +452,7 @@ __device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMSta
   __shared__ LMState s;
   static_assert(sizeof(LMState) % 8 == 0, "LMState is staged as 8-byte words");
   constexpr int kWords = (int)(sizeof(LMState) / 8);
+  const long long t0 = clock64();
   if (mode != 0) {
     const unsigned long long *src = reinterpret_cast<const unsigned long long *>(gst);
     unsigned long long *dst = reinterpret_cast<unsigned long long *>(&s);
@@ -445,10 +465,12 @@ __device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMSta
     if (lane < NE_PACK) {
       const double *p = partials + lane;
       int b = w;
-      for (; b + 3 * S < n_blocks; b += 4 * S) {  // four loads in flight, same summation order
-        const double a0 = __ldcg(p + (size_t)b * NE_PACK), a1 = __ldcg(p + (size_t)(b + S) * NE_PACK),
-                     a2 = __ldcg(p + (size_t)(b + 2 * S) * NE_PACK), a3 = __ldcg(p + (size_t)(b + 3 * S) * NE_PACK);
-        v += a0, v += a1, v += a2, v += a3;
+      for (; b + 7 * S < n_blocks; b += 8 * S) {  // eight loads in flight, same summation order
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = __ldcg(p + (size_t)(b + u * S) * NE_PACK);
+#pragma unroll
+        for (int u = 0; u < 8; u++) v += t[u];
       }
       for (; b < n_blocks; b += S) v += __ldcg(p + (size_t)b * NE_PACK);
     }
@@ -466,7 +488,9 @@ __device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMSta
   if (mode == 0) return;
   if (threadIdx.x == 0) {
     s.work[0] = 0, s.work[1] = 0;  // re-arm the match work queues
+    const long long t1 = clock64();
     lm_advance(&s, ne, mode, eig_thre, want_eig);
+    s.dbg_cycles[0] += t1 - t0, s.dbg_cycles[1] += clock64() - t1, s.dbg_cycles[2] += 1;
   }
   __syncthreads();
   {
@@ -492,6 +516,7 @@ __global__ void k_lm_init(LMState *st, const double *pose7, int max_inner, int m
     st->cost = 0, st->initial_cost = 0;
     for (int i = 0; i < 36; i++) st->V_update[i] = (i % 7 == 0) ? 1.0 : 0.0, st->H0[i] = 0, st->H[i] = 0;
     for (int i = 0; i < 6; i++) st->eig[i] = 0, st->g[i] = 0;
+    for (int i = 0; i < 4; i++) st->dbg_cycles[i] = 0;
   }
 }
 
@@ -531,8 +556,11 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
   a.respect_done = (lm_mode == 2) ? 1 : 0;
   int nb = (n_total + LIN_THREADS - 1) / LIN_THREADS;
   if (nb < 1) nb = 1;
+  // n_total is a launch upper bound (device-side counts are usually far smaller): 64 blocks x 256 threads cover a
+  // typical frame's ~10^4 features one per thread, and the tail's fixed-order sum reads 64 partials in one round.
   const int max_nb = c->sm_count;
   if (nb > max_nb) nb = max_nb;
+  if (nb > 64) nb = 64;
   MLOAM_CUDA_OK(c, c->partials.reserve(sizeof(double) * NE_PACK * (size_t)(max_nb + 3)));
   unsigned *ticket = reinterpret_cast<unsigned *>(c->partials.as<double>() + (size_t)NE_PACK * (max_nb + 2));
   if (c->ticket_zeroed_for != c->partials.p) {  // a fresh partials buffer: the last-block ticket starts at zero
