@@ -207,6 +207,7 @@ struct FeatSet {
 int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, double huber_a, const double *d_pose7,
                      int use_state, int lm_mode, double *d_out29);
 int lm_init_state(Ctx *c, const double *pose7_host, int max_inner, double eig_thre);
+void eig_report_host(const double *H36, double *w6);  // ascending eigenvalues of a symmetric 6x6 (host side)
 int factor_evaluate_device(Ctx *c, int kind, int n, const double *d_points, const double *d_coeffs, const double *d_sqrt_info,
                            const double *d_params, double *d_res, double *d_jac);
 

@@ -53,9 +53,9 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
       rc = match_pair_device(c, jobs, 2, d_pose, cfg, &st->work[0]);
       if (rc) return rc;
     }
-    // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve.  The
-    // eigenvalue report is only produced for the last outer iteration (earlier ones just need the decision).
-    c->want_eig = (outer == P.max_outer - 1) ? 1 : 0;
+    // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve.  The device
+    // only needs the degeneracy decision; scan2map_finish fills in the eigenvalue report of the last iteration.
+    c->want_eig = 0;
     rc = linearize_device(c, sets, 2, sinfo, P.huber_a, nullptr, 1, 1, nullptr);
     c->want_eig = 1;
     if (rc) return rc;
@@ -107,6 +107,11 @@ int scan2map_finish(Ctx *c, const ScanRef &S, const double *pose_init7, double *
     stats->final_cost = hs->cost;
     memcpy(stats->eig, hs->eig, sizeof(stats->eig));
     memcpy(stats->H, hs->H0, sizeof(stats->H));
+    // evalDegenracy's eigenvalues (lidar_mapper_keyframe.cpp:1172-1204): the device decides degeneracy with a
+    // Cholesky test of H - thre*I and only runs the eigen-solver when that fails; the report of a healthy Solve is
+    // computed here from the same H.
+    const double thre = c->lm_eig_thre >= 0.0 ? c->lm_eig_thre : c->params.eig_thre;
+    if (!hs->is_degenerate && !hs->skipped && hs->rows > 0 && thre > 0.0) eig_report_host(hs->H0, stats->eig);
     stats->n_surf_in = h_cnt[0], stats->n_corner_in = h_cnt[1];
   }
   return MLOAM_OK;

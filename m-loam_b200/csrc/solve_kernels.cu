@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
 }
 
 // ---------------------------------------------------------------------------------------- small dense (device)
-__device__ void eig_sym6(const double *Ain, double *w, double *V) {
+__host__ __device__ void eig_sym6(const double *Ain, double *w, double *V) {
   const int N = 6;
   double a[36], v[36];
   for (int i = 0; i < 36; i++) a[i] = Ain[i], v[i] = (i % 7 == 0) ? 1.0 : 0.0;
@@ -199,6 +199,13 @@ __device__ void eig_sym6(const double *Ain, double *w, double *V) {
     w[j] = a[idx[j] * N + idx[j]];
     for (int k = 0; k < N; k++) V[k * N + j] = v[k * N + idx[j]];
   }
+}
+
+// Eigenvalue report of a non-degenerate Solve, filled in by the host from the read-back H0 (the device only runs the
+// 6x6 Jacobi solver when the Cholesky test says a direction is degenerate — a ~10^5-cycle single-thread job).
+void eig_report_host(const double *H36, double *w6) {
+  double V[36];
+  eig_sym6(H36, w6, V);
 }
 
 __device__ __forceinline__ bool chol6(double *A) {
