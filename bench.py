@@ -85,7 +85,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -93,18 +93,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def wait_first(self, timeout=15.0):
+        """nvidia-smi takes a second or two to initialise (and contends for the driver while it does): the timed
+        region only starts once it is already streaming samples."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             pass
+        t_begin = getattr(self, "t_begin", 0.0)
+        inside = [r for (t, r) in self.rows if t_begin <= t <= t_end + 0.05]
+        if not inside:  # timed region shorter than one sampling period: the closest sample taken under load
+            inside = [r for (t, r) in self.rows[-2:]]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -245,13 +260,15 @@ def main():
 
     # ---- value: inputs resident in HBM, per-step CUDA events on the launching stream, L2 flushed between steps.
     # (Profiling is off here: with max_inner == 1 the library replays the frame as a captured CUDA graph.)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.wait_first()
     for k in range(args.warmup + n_frames):  # every distinct frame buffer is seen twice -> its graph is captured before timing
         step_device(k)
         if k >= n_frames:
             step_device(k)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark()
     launches0 = ctx.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     last = None

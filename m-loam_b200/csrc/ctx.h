@@ -95,6 +95,7 @@ struct Ctx {
   DevBuf feat_coeff[2];           // float[6] per query
   DevBuf feat_nn[2];              // int[n_neigh] per query (optional)
   DevBuf knn_pos[2];              // int[n_neigh] per query: neighbour positions handed from k_match_knn to k_match_fit
+  DevBuf knn_changed[2];          // unsigned char per query: neighbour list differs from the previous iteration's
   DevBuf partials;                // per-block packed normal equations
   DevBuf lm_state;                // LMState
   void *ticket_zeroed_for = nullptr;  // partials allocation whose last-block ticket has been zeroed
@@ -132,6 +133,7 @@ struct Ctx {
   };
   std::vector<GraphEntry> graphs;
   int use_graphs = 1;
+  int use_seeds = 1;               // seed the kNN of re-association iterations > 0 with the previous neighbour lists
   int s2m_ran = 0;
   int lm_min_corr = 0;              // lm_init_state: minimum matched features for a Solve (tracker: 10)
   double lm_eig_thre = -1.0;        // < 0: use params.eig_thre; the tracker disables evalDegenracy with 0
@@ -181,6 +183,8 @@ struct MatchJob {
   unsigned char *valid;     // out
   float *coeff;             // out, n * 6
   int *nn;                  // out, nullable, n * n_neigh original indices
+  int seeded;               // 1: same features against the same map as the previous call with this job index — its neighbour
+                            // lists (Ctx::knn_pos) seed the search and unchanged lists keep their fit
 };
 int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_pose7, const MatchCfg &cfg, int *d_work);
 

@@ -160,6 +160,46 @@ __device__ __forceinline__ HashEntry hash_lookup(const MapView &map, unsigned lo
 
 __device__ __forceinline__ int cell_bit(int fx, int fy, int fz) { return ((fz & 3) << 4) | ((fy & 3) << 2) | (fx & 3); }
 
+// Seeded search (temporal coherence between the re-association iterations of one scan2MapOptimization): the caller
+// knows K map points — the previous iteration's neighbours — whose largest squared distance to the moved query is
+// r2 < max_sqdist.  Every point of the true K-nearest set then lies in the ball of radius sqrt(r2), so scanning the
+// cells that intersect that ball (usually 1-8 instead of the 27 + 27 probes of the blind search) gives the exact
+// result, ties included.  Returns false (nothing written) when the ball needs more than 32 cells.
+template <int K>
+__device__ __forceinline__ bool warp_knn_seeded(const MapView &map, RunBuf &rb, float qx, float qy, float qz, float r2, int lane,
+                                                TopK<K> &out) {
+  const float eps = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 8.0f * map.cell) + 1e-6f;
+  const float rr = sqrtf(r2) * 1.0002f + eps;
+  const int lx = (int)floorf((qx - rr) * map.inv_cell), hx = (int)floorf((qx + rr) * map.inv_cell);
+  const int ly = (int)floorf((qy - rr) * map.inv_cell), hy = (int)floorf((qy + rr) * map.inv_cell);
+  const int lz = (int)floorf((qz - rr) * map.inv_cell), hz = (int)floorf((qz + rr) * map.inv_cell);
+  const int nx = hx - lx + 1, ny = hy - ly + 1, nz = hz - lz + 1;
+  if (nx > 32 || ny > 32 || nz > 32 || nx * ny * nz > 32) return false;
+  const int ncell = nx * ny * nz;
+  int start = 0, count = 0;
+  if (lane < ncell) {
+    const int fx = lx + lane % nx, fy = ly + (lane / nx) % ny, fz = lz + lane / (nx * ny);
+    const float lox = (float)fx * map.cell, loy = (float)fy * map.cell, loz = (float)fz * map.cell;
+    const float gx = fmaxf(fmaxf(lox - qx, qx - (lox + map.cell)) - eps, 0.0f);
+    const float gy = fmaxf(fmaxf(loy - qy, qy - (loy + map.cell)) - eps, 0.0f);
+    const float gz = fmaxf(fmaxf(loz - qz, qz - (loz + map.cell)) - eps, 0.0f);
+    if (gx * gx + gy * gy + gz * gz <= rr * rr) {
+      const HashEntry e = hash_lookup(map, pack_cell(fx, fy, fz));
+      start = e.start, count = e.count;
+    }
+  }
+  int total;
+  const int excl = warp_excl_scan(count, lane, &total);
+  __syncwarp();
+  rb.start[lane] = start;
+  rb.pref[lane] = excl;
+  __syncwarp();
+  topk_reset(out);
+  scan_runs<K, 32>(map, rb, total, qx, qy, qz, lane, out);
+  __syncwarp();
+  return true;
+}
+
 // REJECT_PARTIAL: the caller only wants results when K neighbours exist inside the radius (every matcher gate).
 // rb: this warp's run table in shared memory.
 template <int K, bool REJECT_PARTIAL>

@@ -23,7 +23,9 @@ struct KnnSet {
   const float4 *pts;   // sensor-frame features
   int n;               // count, or launch upper bound when d_n is set
   const int *d_n;      // nullable device-side count
-  int *pos;            // out: n * K positions into map.sorted (-1: gate failed)
+  int *pos;            // out: n * K positions into map.sorted (-1: gate failed); in: the previous result when seeded
+  int seeded;          // pos holds this set's result of the previous re-association iteration on the SAME map
+  unsigned char *changed;  // out (nullable): 1 when the neighbour list differs from the seed (or there was none)
 };
 
 #ifndef MLOAM_KNN_MINBLOCKS
@@ -54,14 +56,39 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
     const float4 p = __ldg((in_a ? a.pts : b.pts) + j);
     const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
     TopK<K> best;
-    warp_knn<K, true>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best);
+    int *const pos_out = (in_a ? a.pos : b.pos) + (size_t)j * K;
+    const int seeded = in_a ? a.seeded : b.seeded;
+    unsigned char *const changed = in_a ? a.changed : b.changed;
+    // temporal coherence: the previous iteration's neighbours bound the search ball of the (slightly) moved query
+    int prev = -1;
+    bool found = false;
+    if (seeded) {
+      if (lane < K) prev = pos_out[lane];
+      if (__shfl_sync(MLOAM_FULL_MASK, prev, 0) >= 0) {
+        unsigned d2b = 0u;
+        if (lane < K) {
+          const float4 v = __ldg((in_a ? a.map.sorted : b.map.sorted) + prev);
+          const float ex = v.x - sel.x, ey = v.y - sel.y, ez = v.z - sel.z;
+          d2b = __float_as_uint(ex * ex + ey * ey + ez * ez);  // non-negative floats order like their bit patterns
+        }
+        const float r2 = __uint_as_float(__reduce_max_sync(MLOAM_FULL_MASK, d2b));
+        if (r2 < min_match_sq_dis)
+          found = warp_knn_seeded<K>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, r2, lane, best);
+      }
+    }
+    if (!found) warp_knn<K, true>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best);
     const bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
                     __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
     int mypos = -1;
 #pragma unroll
     for (int k = 0; k < K; k++)
       if (lane == k) mypos = best.pos[k];
-    if (lane < K) (in_a ? a.pos : b.pos)[(size_t)j * K + lane] = ok ? mypos : -1;
+    const int newpos = ok ? mypos : -1;
+    if (lane < K) pos_out[lane] = newpos;
+    if (changed) {
+      const bool diff = __any_sync(MLOAM_FULL_MASK, lane < K && (!seeded || newpos != prev));
+      if (lane == 0) changed[j] = diff ? 1 : 0;
+    }
     if (!work) i += gridDim.x * MWARPS;
   }
 }
@@ -88,10 +115,14 @@ struct FitSet {
   float *coeff;          // out: n * 6
   int *nn;               // out (nullable): n * K original map indices
   int is_plane;
+  const unsigned char *changed;  // nullable: 0 -> same neighbours as the previous iteration, valid/coeff already hold the fit
 };
 
 template <int K>
 __device__ __forceinline__ void fit_one(const FitSet &s, int j, const PoseD &T, float min_plane_dis, int check_fov) {
+  // The fit depends on the map points only: with an unchanged neighbour list the previous iteration's valid / coeff
+  // stand (the FOV gate depends on the pose, so it disables the shortcut).
+  if (s.changed && !check_fov && !s.changed[j]) return;
   const int *ps = s.pos + (size_t)j * K;
   bool ok = ps[0] >= 0;
   float out[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -202,7 +233,11 @@ int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_
     DevBuf &pb = c->knn_pos[t];
     MLOAM_CUDA_OK(c, pb.reserve(sizeof(int) * (size_t)K * (size_t)(J.n + 1)));
     k.map = c->maps[J.slot].view();
+    DevBuf &cb = c->knn_changed[t];
+    MLOAM_CUDA_OK(c, cb.reserve((size_t)(J.n + 1)));
     k.pts = J.pts, k.n = J.n, k.d_n = J.d_n, k.pos = pb.as<int>();
+    k.seeded = J.seeded, k.changed = cb.as<unsigned char>();
+    f.changed = (J.seeded && !J.nn) ? cb.as<unsigned char>() : nullptr;
     f.sorted = k.map.sorted, f.pts = J.pts, f.n = J.n, f.d_n = J.d_n, f.pos = pb.as<int>();
     f.valid = J.valid, f.coeff = J.coeff, f.nn = J.nn, f.is_plane = J.type == 's' ? 1 : 0;
     n_upper += J.n;
@@ -231,7 +266,7 @@ int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_
 
 int match_from_map_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const int *d_n, const double *d_pose7,
                           const MatchCfg &cfg, unsigned char *d_valid, float *d_coeff, int *d_nn, int *d_work) {
-  MatchJob j{slot, type, d_pts, n, d_n, d_valid, d_coeff, d_nn};
+  MatchJob j{slot, type, d_pts, n, d_n, d_valid, d_coeff, d_nn, 0};
   return match_pair_device(c, &j, 1, d_pose7, cfg, d_work);
 }
 

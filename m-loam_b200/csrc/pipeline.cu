@@ -45,11 +45,14 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
   for (int outer = 0; outer < P.max_outer; outer++) {
     // :503-532  match corner then surf at pose_wmap_curr (wo_gf: every feature)
     {
+      // From the second iteration on the same features meet the same maps at a slightly moved pose: the previous
+      // neighbour lists seed the search (exact, see knn.cuh) and unchanged lists keep their line / plane fit.
+      const int seeded = (outer > 0 && c->use_seeds) ? 1 : 0;
       MatchJob jobs[2] = {
           MatchJob{MLOAM_MAP_CORNER, 'c', S.corner, nc_use, S.d_n_corner, c->feat_valid[0].as<unsigned char>(),
-                   c->feat_coeff[0].as<float>(), nullptr},
+                   c->feat_coeff[0].as<float>(), nullptr, seeded},
           MatchJob{MLOAM_MAP_SURF, 's', S.surf, ns_use, S.d_n_surf, c->feat_valid[1].as<unsigned char>(),
-                   c->feat_coeff[1].as<float>(), nullptr}};
+                   c->feat_coeff[1].as<float>(), nullptr, seeded}};
       rc = match_pair_device(c, jobs, 2, d_pose, cfg, &st->work[0]);
       if (rc) return rc;
     }

@@ -473,6 +473,35 @@ def test_frame_graph_replay_equals_stream_path(mloam, c1):
     g.close()
 
 
+@pytest.mark.parametrize("outer,inner,guess", [(6, 1, 0.0), (3, 4, 0.0), (4, 1, 0.6)])
+def test_seeded_reassociation_is_exact(mloam, c1, outer, inner, guess):
+    """From the second re-association on, the kNN is seeded with the previous neighbour lists and unchanged lists keep
+    their fit.  That is an exact shortcut: poses, match counts and the Hessian must be BIT-identical to the blind
+    search — also when the pose moves a lot between iterations (a poor initial guess)."""
+    import os
+
+    p = mloam.default_params()
+    p.max_outer, p.max_inner, p.map_cell = outer, inner, 0.5
+    init = np.array(c1["init"], dtype=np.float64)
+    init[:3] += guess
+    res = []
+    for disable in ("1", "0"):
+        os.environ["MLOAM_DISABLE_SEEDS"] = disable
+        try:
+            cx = mloam.Context(0, p)
+        finally:
+            os.environ.pop("MLOAM_DISABLE_SEEDS")
+        cx.map_build(1, c1["surf_map"], 0.5)
+        cx.map_build(0, c1["corner_map"], 0.5)
+        res.append(cx.scan2map(c1["surf_scan"], c1["corner_scan"], init))
+        cx.close()
+    (pa, sa), (pb, sb) = res
+    assert np.array_equal(pa, pb)
+    assert sa["n_surf"] == sb["n_surf"] and sa["n_corner"] == sb["n_corner"] and sa["n_surf"] > 500
+    assert sa["lm_iterations"] == sb["lm_iterations"]
+    assert np.array_equal(np.asarray(sa["H"]), np.asarray(sb["H"])) and sa["final_cost"] == sb["final_cost"]
+
+
 # ------------------------------------------------------------------------------------------------ uncertainty-aware mapping
 def test_point_uncertainty_and_scan2map_ua(ctx, c1):
     rng = np.random.default_rng(12)
