@@ -96,6 +96,7 @@ struct Ctx {
   DevBuf feat_nn[2];              // int[n_neigh] per query (optional)
   DevBuf knn_pos[2];              // int[n_neigh] per query: neighbour positions handed from k_match_knn to k_match_fit
   DevBuf knn_changed[2];          // unsigned char per query: neighbour list differs from the previous iteration's
+  DevBuf knn_anchor[2];           // float4 per query: position of its last real search + tolerated displacement
   DevBuf partials;                // per-block packed normal equations
   DevBuf lm_state;                // LMState
   void *ticket_zeroed_for = nullptr;  // partials allocation whose last-block ticket has been zeroed

@@ -165,11 +165,11 @@ __device__ __forceinline__ int cell_bit(int fx, int fy, int fz) { return ((fz & 
 // r2 < max_sqdist.  Every point of the true K-nearest set then lies in the ball of radius sqrt(r2), so scanning the
 // cells that intersect that ball (usually 1-8 instead of the 27 + 27 probes of the blind search) gives the exact
 // result, ties included.  Returns false (nothing written) when the ball needs more than 32 cells.
-template <int K>
-__device__ __forceinline__ bool warp_knn_seeded(const MapView &map, RunBuf &rb, float qx, float qy, float qz, float r2, int lane,
-                                                TopK<K> &out) {
+template <int K, int N>
+__device__ __forceinline__ bool warp_knn_seeded(const MapView &map, RunBuf &rb, float qx, float qy, float qz, float r2, float pad,
+                                                int lane, TopK<N> &out, float *explored) {
   const float eps = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 8.0f * map.cell) + 1e-6f;
-  const float rr = sqrtf(r2) * 1.0002f + eps;
+  const float rr = sqrtf(r2) * 1.0002f + eps + pad;  // pad > 0 widens the ball so that the (K+1)-th distance is seen too
   const int lx = (int)floorf((qx - rr) * map.inv_cell), hx = (int)floorf((qx + rr) * map.inv_cell);
   const int ly = (int)floorf((qy - rr) * map.inv_cell), hy = (int)floorf((qy + rr) * map.inv_cell);
   const int lz = (int)floorf((qz - rr) * map.inv_cell), hz = (int)floorf((qz + rr) * map.inv_cell);
@@ -195,17 +195,22 @@ __device__ __forceinline__ bool warp_knn_seeded(const MapView &map, RunBuf &rb, 
   rb.pref[lane] = excl;
   __syncwarp();
   topk_reset(out);
-  scan_runs<K, 32>(map, rb, total, qx, qy, qz, lane, out);
+  scan_runs<N, 32>(map, rb, total, qx, qy, qz, lane, out);
   __syncwarp();
+  *explored = fmaxf(rr - 2.0f * eps, 0.0f);  // every map point closer than this has been scanned
   return true;
 }
 
 // REJECT_PARTIAL: the caller only wants results when K neighbours exist inside the radius (every matcher gate).
 // rb: this warp's run table in shared memory.
-template <int K, bool REJECT_PARTIAL>
+// N >= K: selection width.  The search is driven by the K-th distance as before; with N = K + 1 the extra slot holds
+// the nearest point outside the K-set AMONG THE SCANNED ONES, and *explored (nullable) the distance below which every
+// map point has been scanned (0 when unknown) — together a lower bound on the (K+1)-th distance.
+template <int K, bool REJECT_PARTIAL, int N = K>
 __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float qx, float qy, float qz, float max_sqdist, int lane,
-                                         TopK<K> &out) {
+                                         TopK<N> &out, float *explored = nullptr) {
   topk_reset(out);
+  if (explored) *explored = 0.0f;
   const int cx = (int)floorf(qx * map.inv_cell), cy = (int)floorf(qy * map.inv_cell), cz = (int)floorf(qz * map.inv_cell);
   const float eps = 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 8.0f * map.cell) + 1e-6f;
   const float radius = sqrtf(max_sqdist);
@@ -243,7 +248,7 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
     rb.start[lane] = start;
     rb.pref[lane] = excl;
     __syncwarp();
-    scan_runs<K, 32>(map, rb, total, qx, qy, qz, lane, out);
+    scan_runs<N, 32>(map, rb, total, qx, qy, qz, lane, out);
   }
   auto face_gap = [&](int r) {  // distance from the query to the nearest face of the visited cube [c-r, c+r+1) * cell
     float g = qx - (float)(cx - r) * map.cell;
@@ -259,8 +264,10 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
     const float g = face_gap(1);
     if (g > 0.0f) {
       const float g2 = g * g;
-      if (g2 >= max_sqdist) return;
-      if (out.key[K - 1] != MLOAM_KEY_NONE && kth() < g2) return;
+      if (g2 >= max_sqdist || (out.key[K - 1] != MLOAM_KEY_NONE && kth() < g2)) {
+        if (explored) *explored = g;
+        return;
+      }
     }
   }
   if (coarse_ok) {
@@ -304,7 +311,7 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
           __syncwarp();
           for (int r = nr + lane; r < KNN_RUNS; r += 32) rb.pref[r] = npts;
           __syncwarp();
-          scan_runs<K, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
+          scan_runs<N, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
           if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
           nr = 0, npts = 0;
           __syncwarp();
@@ -328,7 +335,7 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
       __syncwarp();
       for (int r = nr + lane; r < KNN_RUNS; r += 32) rb.pref[r] = npts;
       __syncwarp();
-      scan_runs<K, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
+      scan_runs<N, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
     }
     return;
   }
@@ -358,7 +365,7 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
       rb.start[lane] = start;
       rb.pref[lane] = excl;
       __syncwarp();
-      scan_runs<K, 32>(map, rb, total, qx, qy, qz, lane, out);
+      scan_runs<N, 32>(map, rb, total, qx, qy, qz, lane, out);
     }
     const float g = face_gap(r);
     if (g > 0.0f) {

@@ -26,6 +26,7 @@ struct KnnSet {
   int *pos;            // out: n * K positions into map.sorted (-1: gate failed); in: the previous result when seeded
   int seeded;          // pos holds this set's result of the previous re-association iteration on the SAME map
   unsigned char *changed;  // out (nullable): 1 when the neighbour list differs from the seed (or there was none)
+  float4 *anchor;      // per feature: map-frame position of its last real search + the displacement it tolerates
 };
 
 #ifndef MLOAM_KNN_MINBLOCKS
@@ -55,35 +56,77 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
     const int j = in_a ? i : i - na;
     const float4 p = __ldg((in_a ? a.pts : b.pts) + j);
     const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
-    TopK<K> best;
+    TopK<K + 1> best;  // slot K: nearest scanned point outside the K-set (feeds the anchor's slack)
     int *const pos_out = (in_a ? a.pos : b.pos) + (size_t)j * K;
     const int seeded = in_a ? a.seeded : b.seeded;
     unsigned char *const changed = in_a ? a.changed : b.changed;
-    // temporal coherence: the previous iteration's neighbours bound the search ball of the (slightly) moved query
-    int prev = -1;
-    bool found = false;
+    float4 *const anchor = (in_a ? a.anchor : b.anchor) + j;
+    // Temporal coherence between re-association iterations (all three shortcuts are exact, see knn.cuh):
+    //   keep    the query moved less than the anchor's slack since its last real search: the K-set cannot have
+    //           changed, only its order — recompute the K distances and re-rank (no cell probes, no scan)
+    //   ball    otherwise the previous neighbours bound the search ball around the moved query
+    //   blind   no previous neighbours (or a ball of more than 32 cells)
+    int prev = -1, newpos = -1;
+    bool done = false;
+    float r2 = 3.0e38f;
     if (seeded) {
       if (lane < K) prev = pos_out[lane];
+      const float4 an = *anchor;
       if (__shfl_sync(MLOAM_FULL_MASK, prev, 0) >= 0) {
+        unsigned long long key = MLOAM_KEY_NONE;
         unsigned d2b = 0u;
         if (lane < K) {
           const float4 v = __ldg((in_a ? a.map.sorted : b.map.sorted) + prev);
           const float ex = v.x - sel.x, ey = v.y - sel.y, ez = v.z - sel.z;
           d2b = __float_as_uint(ex * ex + ey * ey + ez * ez);  // non-negative floats order like their bit patterns
+          key = ((unsigned long long)d2b << 32) | (unsigned)__float_as_int(v.w);
         }
-        const float r2 = __uint_as_float(__reduce_max_sync(MLOAM_FULL_MASK, d2b));
-        if (r2 < min_match_sq_dis)
-          found = warp_knn_seeded<K>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, r2, lane, best);
+        r2 = __uint_as_float(__reduce_max_sync(MLOAM_FULL_MASK, d2b));
+        const float mx = sel.x - an.x, my = sel.y - an.y, mz = sel.z - an.z;
+        const float moved = sqrtf(mx * mx + my * my + mz * mz);
+        if (an.w > 0.0f && moved + 2e-5f < an.w) {
+          int rank = 0;
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const unsigned long long other = __shfl_sync(MLOAM_FULL_MASK, key, k);
+            if (other < key) rank++;
+          }
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            const int rk = __shfl_sync(MLOAM_FULL_MASK, rank, k), pk = __shfl_sync(MLOAM_FULL_MASK, prev, k);
+            if (rk == lane) newpos = pk;
+          }
+          if (!(r2 < min_match_sq_dis)) newpos = -1;  // :407,571,667,814
+          done = true;
+        }
       }
     }
-    if (!found) warp_knn<K, true>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best);
-    const bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
-                    __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
-    int mypos = -1;
+    if (!done) {
+      float explored = 0.0f;
+      bool found = false;
+      if (r2 < min_match_sq_dis)
+        found = warp_knn_seeded<K, K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, r2,
+                                          0.1f * (in_a ? a.map.cell : b.map.cell), lane, best, &explored);
+      if (!found)
+        warp_knn<K, true, K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best,
+                                 &explored);
+      const bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
+                      __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
+      int mypos = -1;
 #pragma unroll
-    for (int k = 0; k < K; k++)
-      if (lane == k) mypos = best.pos[k];
-    const int newpos = ok ? mypos : -1;
+      for (int k = 0; k < K; k++)
+        if (lane == k) mypos = best.pos[k];
+      newpos = ok ? mypos : -1;
+      // anchor: K-set members are within rK of this position, everything else at least lb away
+      float slack = 0.0f;
+      if (ok) {
+        const float rK = sqrtf(__uint_as_float((unsigned)(best.key[K - 1] >> 32)));
+        float lb = explored;
+        if (best.key[K] != MLOAM_KEY_NONE) lb = fminf(lb, sqrtf(__uint_as_float((unsigned)(best.key[K] >> 32))));
+        slack = 0.5f * (lb - rK) - 2e-5f;
+      }
+      if (lane == 0) *anchor = make_float4(sel.x, sel.y, sel.z, slack);
+    }
     if (lane < K) pos_out[lane] = newpos;
     if (changed) {
       const bool diff = __any_sync(MLOAM_FULL_MASK, lane < K && (!seeded || newpos != prev));
@@ -236,7 +279,9 @@ int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_
     DevBuf &cb = c->knn_changed[t];
     MLOAM_CUDA_OK(c, cb.reserve((size_t)(J.n + 1)));
     k.pts = J.pts, k.n = J.n, k.d_n = J.d_n, k.pos = pb.as<int>();
-    k.seeded = J.seeded, k.changed = cb.as<unsigned char>();
+    DevBuf &ab = c->knn_anchor[t];
+    MLOAM_CUDA_OK(c, ab.reserve(sizeof(float4) * (size_t)(J.n + 1)));
+    k.seeded = J.seeded, k.changed = cb.as<unsigned char>(), k.anchor = ab.as<float4>();
     f.changed = (J.seeded && !J.nn) ? cb.as<unsigned char>() : nullptr;
     f.sorted = k.map.sorted, f.pts = J.pts, f.n = J.n, f.d_n = J.d_n, f.pos = pb.as<int>();
     f.valid = J.valid, f.coeff = J.coeff, f.nn = J.nn, f.is_plane = J.type == 's' ? 1 : 0;
