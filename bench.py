@@ -307,6 +307,7 @@ def main():
             feats_prof += st_k["n_surf_in"] + st_k["n_corner_in"]
     barrier()
     prof = {name: ctx.profile_get(name) for name in ("map_build", "extract", "voxel", "match", "fit", "linearize", "lm", "lm_tail_reduce", "lm_tail_advance")}
+    knn_paths = {name: ctx.profile_get(name)[1] / prof_steps for name in ("knn_keep_matched", "knn_keep_rejected", "knn_ball", "knn_blind")}
     ctx.profile(False)
 
     # ---- e2e: HOST buffers through the C ABI (H2D sweep + both submaps, D2H pose) — wall clock around synchronous calls
@@ -379,7 +380,7 @@ def main():
             "data": "synthetic", "config": config, "ms_per_gn_iter": 1e3 * t_max / args.steps / GN_ITERS,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches), "cuda_graph_replay": os.environ.get("MLOAM_DISABLE_GRAPHS", "0") in ("", "0") and world == 1,
-            "clocks": clocks, "roofline": roofline, "stage_ms_per_step": stage_ms,
+            "clocks": clocks, "roofline": roofline, "stage_ms_per_step": stage_ms, "knn_queries_per_step_by_path": knn_paths,
             "features_per_step": feats / args.steps}
     if cpu is not None:
         line["cpu_baseline"] = cpu

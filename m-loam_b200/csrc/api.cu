@@ -105,6 +105,7 @@ int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out
     return MLOAM_E_CUDA;
   }
   c->pinned_cap = kPinnedBytes;
+  cudaMemset(c->scratch[7].p, 0, 4096);
   if (const char *e = getenv("MLOAM_DISABLE_GRAPHS")) c->use_graphs = (e[0] == '0' || e[0] == '\0') ? 1 : 0;
   if (const char *e = getenv("MLOAM_DISABLE_SEEDS")) c->use_seeds = (e[0] == '0' || e[0] == '\0') ? 1 : 0;
   *out = h;
@@ -172,6 +173,15 @@ int mloam_profile_get(mloam_ctx_t *h, const char *name, double *ms_total, long l
   Ctx *c = &h->c;
   cudaStreamSynchronize(c->stream);
   prof_collect(c);
+  static const char *kPaths[4] = {"knn_keep_matched", "knn_keep_rejected", "knn_ball", "knn_blind"};
+  for (int k = 0; k < 4; k++)
+    if (!strcmp(name, kPaths[k])) {  // query counts of the matcher's search paths (k_match_knn), reported as `launches`
+      unsigned v = 0;
+      MLOAM_CUDA_OK(c, cudaMemcpy(&v, c->scratch[7].as<char>() + kKnnPathStatsOffset + 4 * k, 4, cudaMemcpyDeviceToHost));
+      if (ms_total) *ms_total = 0.0;
+      if (launches) *launches = v;
+      return MLOAM_OK;
+    }
   auto it = c->prof.find(name);
   if (ms_total) *ms_total = it == c->prof.end() ? 0.0 : it->second.ms;
   if (launches) *launches = it == c->prof.end() ? 0 : it->second.launches;
@@ -181,6 +191,7 @@ int mloam_profile_reset(mloam_ctx_t *h) {
   if (!h) return MLOAM_E_INVALID;
   cudaStreamSynchronize(h->c.stream);
   prof_collect(&h->c);
+  cudaMemset(h->c.scratch[7].as<char>() + kKnnPathStatsOffset, 0, 16);
   h->c.prof.clear();
   return MLOAM_OK;
 }

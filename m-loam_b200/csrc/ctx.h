@@ -63,6 +63,8 @@ struct MapStorage {
   }
 };
 
+constexpr size_t kKnnPathStatsOffset = 3072;  // 4 unsigned counters inside Ctx::scratch[7] (zeroed at creation / profile reset)
+
 struct ProfSlot {
   double ms = 0;
   long long launches = 0;

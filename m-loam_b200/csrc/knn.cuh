@@ -208,7 +208,12 @@ __device__ __forceinline__ bool warp_knn_seeded(const MapView &map, RunBuf &rb, 
 // map point has been scanned (0 when unknown) — together a lower bound on the (K+1)-th distance.
 template <int K, bool REJECT_PARTIAL, int N = K>
 __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float qx, float qy, float qz, float max_sqdist, int lane,
-                                         TopK<N> &out, float *explored = nullptr) {
+                                         TopK<N> &out, float *explored = nullptr, float pad = 0.0f) {
+  // *explored: every map point closer than this has been scanned into `out` — or, on the REJECT_PARTIAL block exit,
+  // counted: fewer than K points exist inside that distance.  Hence min(K-th scanned, *explored) bounds the true K-th
+  // distance from below, and min((K+1)-th scanned, *explored) the (K+1)-th.  pad > 0 lets the mask-guided finish look
+  // that much beyond the radius, so that a query WITHOUT K neighbours inside the radius learns how far it is from
+  // having them (the result inside the radius is unaffected).
   topk_reset(out);
   if (explored) *explored = 0.0f;
   const int cx = (int)floorf(qx * map.inv_cell), cy = (int)floorf(qy * map.inv_cell), cz = (int)floorf(qz * map.inv_cell);
@@ -228,7 +233,19 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
       if (slot >= 0) bmask = __ldg(map.block_mask + slot);
     }
     const int total = __reduce_add_sync(MLOAM_FULL_MASK, cnt);
-    if (REJECT_PARTIAL && coarse_ok && total < K) return;
+    if (REJECT_PARTIAL && coarse_ok && total < K) {
+      if (explored) {  // distance from the query to the hull of the 3x3x3 blocks
+        const float bw = map.cell * (float)B;
+        float g = qx - (float)((ccx - 1) * B) * map.cell;
+        g = fminf(g, (float)((ccx + 2) * B) * map.cell - qx);
+        g = fminf(g, qy - (float)((ccy - 1) * B) * map.cell);
+        g = fminf(g, (float)((ccy + 2) * B) * map.cell - qy);
+        g = fminf(g, qz - (float)((ccz - 1) * B) * map.cell);
+        g = fminf(g, (float)((ccz + 2) * B) * map.cell - qz);
+        *explored = fmaxf(fminf(g, 2.0f * bw) - eps, 0.0f);
+      }
+      return;
+    }
   }
   // ---- ring 1
   {
@@ -273,6 +290,10 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
   if (coarse_ok) {
     // ---- finish with the block masks
     float bound = max_sqdist;
+    if (pad > 0.0f) {  // look a little beyond the radius, but never beyond what the 27 blocks cover
+      const float reach_r = fminf(radius + pad, (map.cell * (float)B - 64.0f * eps) / 1.0002f);
+      bound = fmaxf(bound, reach_r * reach_r);
+    }
     if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
     // blocks that are non-empty and whose box reaches into the bound (ties at equal distance are kept)
     bool reach = false;
@@ -336,6 +357,10 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
       for (int r = nr + lane; r < KNN_RUNS; r += 32) rb.pref[r] = npts;
       __syncwarp();
       scan_runs<N, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
+    }
+    if (explored) {  // cells were pruned against bounds that never dropped below the final one
+      if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
+      *explored = fmaxf(sqrtf(bound) - eps, 0.0f);
     }
     return;
   }

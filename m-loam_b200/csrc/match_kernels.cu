@@ -34,7 +34,8 @@ struct KnnSet {
 #endif
 template <int K>
 __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
-    k_match_knn(KnnSet a, KnnSet b, const double *__restrict__ pose7, float min_match_sq_dis, int *__restrict__ work) {
+    k_match_knn(KnnSet a, KnnSet b, const double *__restrict__ pose7, float min_match_sq_dis, int *__restrict__ work,
+                unsigned *__restrict__ path_stats) {
   __shared__ RunBuf rbuf[MWARPS];
   const int lane = threadIdx.x & 31;
   const int na = a.d_n ? min(a.n, *a.d_n) : a.n;
@@ -72,7 +73,16 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
     if (seeded) {
       if (lane < K) prev = pos_out[lane];
       const float4 an = *anchor;
-      if (__shfl_sync(MLOAM_FULL_MASK, prev, 0) >= 0) {
+      const float mx = sel.x - an.x, my = sel.y - an.y, mz = sel.z - an.z;
+      const float moved = sqrtf(mx * mx + my * my + mz * mz);
+      const bool within = an.w > 0.0f && moved + 2e-5f < an.w;
+      if (__shfl_sync(MLOAM_FULL_MASK, prev, 0) < 0) {
+        // rejected last time with the K-th neighbour at least radius + an.w away from the anchor: still rejected
+        if (within) {
+          done = true;
+          if (path_stats && lane == 0) atomicAdd(path_stats + 1, 1u);
+        }
+      } else {
         unsigned long long key = MLOAM_KEY_NONE;
         unsigned d2b = 0u;
         if (lane < K) {
@@ -82,9 +92,7 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
           key = ((unsigned long long)d2b << 32) | (unsigned)__float_as_int(v.w);
         }
         r2 = __uint_as_float(__reduce_max_sync(MLOAM_FULL_MASK, d2b));
-        const float mx = sel.x - an.x, my = sel.y - an.y, mz = sel.z - an.z;
-        const float moved = sqrtf(mx * mx + my * my + mz * mz);
-        if (an.w > 0.0f && moved + 2e-5f < an.w) {
+        if (within) {
           int rank = 0;
 #pragma unroll
           for (int k = 0; k < K; k++) {
@@ -96,8 +104,12 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
             const int rk = __shfl_sync(MLOAM_FULL_MASK, rank, k), pk = __shfl_sync(MLOAM_FULL_MASK, prev, k);
             if (rk == lane) newpos = pk;
           }
-          if (!(r2 < min_match_sq_dis)) newpos = -1;  // :407,571,667,814
+          if (!(r2 < min_match_sq_dis)) {  // :407,571,667,814 — the slack of a match says nothing about a rejection
+            newpos = -1;
+            if (lane == 0) *anchor = make_float4(sel.x, sel.y, sel.z, 0.0f);
+          }
           done = true;
+          if (path_stats && lane == 0) atomicAdd(path_stats + 0, 1u);
         }
       }
     }
@@ -109,7 +121,8 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
                                           0.1f * (in_a ? a.map.cell : b.map.cell), lane, best, &explored);
       if (!found)
         warp_knn<K, true, K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best,
-                                 &explored);
+                                 &explored, 0.05f);
+      if (path_stats && lane == 0) atomicAdd(path_stats + (found ? 2 : 3), 1u);
       const bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
                       __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
       int mypos = -1;
@@ -124,6 +137,12 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
         float lb = explored;
         if (best.key[K] != MLOAM_KEY_NONE) lb = fminf(lb, sqrtf(__uint_as_float((unsigned)(best.key[K] >> 32))));
         slack = 0.5f * (lb - rK) - 2e-5f;
+      } else {
+        // rejected: the K-th neighbour is at least lbK away; while the query stays within lbK - radius of here the
+        // verdict stands
+        float lbK = explored;
+        if (best.key[K - 1] != MLOAM_KEY_NONE) lbK = fminf(lbK, sqrtf(__uint_as_float((unsigned)(best.key[K - 1] >> 32))));
+        slack = lbK - sqrtf(min_match_sq_dis) - 2e-5f;
       }
       if (lane == 0) *anchor = make_float4(sel.x, sel.y, sel.z, slack);
     }
@@ -291,10 +310,12 @@ int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_
   cudaStream_t st = c->stream;
   {
     ProfScope ps(c, "match");
+    // with stage profiling on: how many queries took the keep (matched / rejected), ball and blind paths
+    unsigned *path_stats = c->prof_on ? reinterpret_cast<unsigned *>(c->scratch[7].as<char>() + kKnnPathStatsOffset) : nullptr;
     int nb = (n_upper + MWARPS - 1) / MWARPS;
     if (nb > MLOAM_KNN_MINBLOCKS * c->sm_count) nb = MLOAM_KNN_MINBLOCKS * c->sm_count;  // 3 CTAs x 8 warps resident per SM; warps pull / stride over features
-    if (K == 5) k_match_knn<5><<<nb, MWARPS * 32, 0, st>>>(ks[0], ks[1], d_pose7, cfg.min_match_sq_dis, d_work);
-    else k_match_knn<10><<<nb, MWARPS * 32, 0, st>>>(ks[0], ks[1], d_pose7, cfg.min_match_sq_dis, d_work);
+    if (K == 5) k_match_knn<5><<<nb, MWARPS * 32, 0, st>>>(ks[0], ks[1], d_pose7, cfg.min_match_sq_dis, d_work, path_stats);
+    else k_match_knn<10><<<nb, MWARPS * 32, 0, st>>>(ks[0], ks[1], d_pose7, cfg.min_match_sq_dis, d_work, path_stats);
     c->launches++;
   }
   {
