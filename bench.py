@@ -75,64 +75,93 @@ def make_workload(syn, n_gpus: int, rank: int, n_frames: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md's clocks line), sampled in-process
+    through NVML every 10 ms — an `nvidia-smi -lms` child was seen to stall kernel submission for milliseconds at a
+    time on these hosts, which is not what a 1.5 ms step should be measured next to.  Falls back to that child when
+    NVML is not importable."""
+
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+        self.t_begin = 0.0
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].strip().isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                active = [name for name, attr in self.REASONS if mask & int(getattr(n, attr))]
+                self.rows.append((time.perf_counter(), sm, self.max_sm, active))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm, mx = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            active = [name for (name, _), v in zip(self.REASONS, f[3:7]) if v.lower().startswith("active")]
+            self.rows.append((time.perf_counter(), sm, mx, active))
 
     def wait_first(self, timeout=15.0):
-        """nvidia-smi takes a second or two to initialise (and contends for the driver while it does): the timed
-        region only starts once it is already streaming samples."""
         t0 = time.perf_counter()
-        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+        while (self.nvml is not None or self.proc is not None) and not self.rows and time.perf_counter() - t0 < timeout:
             time.sleep(0.02)
 
     def mark(self):
         self.t_begin = time.perf_counter()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         t_end = time.perf_counter()
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            pass
-        t_begin = getattr(self, "t_begin", 0.0)
-        inside = [r for (t, r) in self.rows if t_begin <= t <= t_end + 0.05]
-        if not inside:  # timed region shorter than one sampling period: the closest sample taken under load
-            inside = [r for (t, r) in self.rows[-2:]]
-        sm, mx, reasons = [], [], set()
-        for r in inside:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        inside = [r for r in self.rows if self.t_begin <= r[0] <= t_end + 0.02]
+        if not inside:  # timed region shorter than one sampling period: the closest samples taken under load
+            inside = self.rows[-2:]
+        sm = [r[1] for r in inside]
+        mx = [r[2] for r in inside]
+        reasons = sorted({x for r in inside for x in r[3]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_arm(syn, orc, surf_map, corner_map, frames, steps, warmup, try_all_cores=True):
@@ -307,7 +336,9 @@ def main():
             feats_prof += st_k["n_surf_in"] + st_k["n_corner_in"]
     barrier()
     prof = {name: ctx.profile_get(name) for name in ("map_build", "extract", "voxel", "match", "fit", "linearize", "lm", "lm_tail_reduce", "lm_tail_advance")}
-    knn_paths = {name: ctx.profile_get(name)[1] / prof_steps for name in ("knn_keep_matched", "knn_keep_rejected", "knn_ball", "knn_blind")}
+    knn_paths = {name: ctx.profile_get(name)[1] / prof_steps for name in ("knn_keep_matched", "knn_keep_rejected", "knn_ball", "knn_blind", "knn_cycles_keep_matched",
+                              "knn_cycles_keep_rejected", "knn_cycles_ball", "knn_cycles_blind")}
+    knn_paths["max_query_cycles"] = ctx.profile_get("knn_max_query_cycles")[1]
     ctx.profile(False)
 
     # ---- e2e: HOST buffers through the C ABI (H2D sweep + both submaps, D2H pose) — wall clock around synchronous calls

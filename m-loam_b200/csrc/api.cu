@@ -173,13 +173,16 @@ int mloam_profile_get(mloam_ctx_t *h, const char *name, double *ms_total, long l
   Ctx *c = &h->c;
   cudaStreamSynchronize(c->stream);
   prof_collect(c);
-  static const char *kPaths[4] = {"knn_keep_matched", "knn_keep_rejected", "knn_ball", "knn_blind"};
-  for (int k = 0; k < 4; k++)
-    if (!strcmp(name, kPaths[k])) {  // query counts of the matcher's search paths (k_match_knn), reported as `launches`
-      unsigned v = 0;
-      MLOAM_CUDA_OK(c, cudaMemcpy(&v, c->scratch[7].as<char>() + kKnnPathStatsOffset + 4 * k, 4, cudaMemcpyDeviceToHost));
+  // query counts / SM cycles of the matcher's search paths (k_match_knn), reported through `launches`
+  static const char *kPaths[9] = {"knn_keep_matched", "knn_keep_rejected", "knn_ball", "knn_blind", "knn_max_query_cycles",
+                                  "knn_cycles_keep_matched", "knn_cycles_keep_rejected", "knn_cycles_ball", "knn_cycles_blind"};
+  for (int k = 0; k < 9; k++)
+    if (!strcmp(name, kPaths[k])) {
+      unsigned long long v = 0;
+      const size_t off = kKnnPathStatsOffset + (k < 5 ? 4 * (size_t)k : 32 + 8 * (size_t)(k - 5));
+      MLOAM_CUDA_OK(c, cudaMemcpy(&v, c->scratch[7].as<char>() + off, k < 5 ? 4 : 8, cudaMemcpyDeviceToHost));
       if (ms_total) *ms_total = 0.0;
-      if (launches) *launches = v;
+      if (launches) *launches = (long long)v;
       return MLOAM_OK;
     }
   auto it = c->prof.find(name);
@@ -191,7 +194,7 @@ int mloam_profile_reset(mloam_ctx_t *h) {
   if (!h) return MLOAM_E_INVALID;
   cudaStreamSynchronize(h->c.stream);
   prof_collect(&h->c);
-  cudaMemset(h->c.scratch[7].as<char>() + kKnnPathStatsOffset, 0, 16);
+  cudaMemset(h->c.scratch[7].as<char>() + kKnnPathStatsOffset, 0, 64);
   h->c.prof.clear();
   return MLOAM_OK;
 }

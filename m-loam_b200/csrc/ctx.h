@@ -63,7 +63,7 @@ struct MapStorage {
   }
 };
 
-constexpr size_t kKnnPathStatsOffset = 3072;  // 4 unsigned counters inside Ctx::scratch[7] (zeroed at creation / profile reset)
+constexpr size_t kKnnPathStatsOffset = 3072;  // 64 B of matcher counters inside Ctx::scratch[7] (zeroed at creation / profile reset)
 
 struct ProfSlot {
   double ms = 0;

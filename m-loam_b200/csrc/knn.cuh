@@ -289,12 +289,18 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
   }
   if (coarse_ok) {
     // ---- finish with the block masks
-    float bound = max_sqdist;
-    if (pad > 0.0f) {  // look a little beyond the radius, but never beyond what the 27 blocks cover
-      const float reach_r = fminf(radius + pad, (map.cell * (float)B - 64.0f * eps) / 1.0002f);
-      bound = fmaxf(bound, reach_r * reach_r);
-    }
-    if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
+    // lim: min(radius^2, K-th so far) — what the result needs.  Cells are pruned against `bound`, which with pad > 0
+    // reaches pad beyond sqrt(lim) (but never beyond what the 27 blocks cover) so that the caller also learns how
+    // isolated the K-set is.
+    const float cover = fmaxf((map.cell * (float)B - 64.0f * eps) / 1.0002f, radius);
+    auto prune_of = [&](float lim2) {
+      if (!(pad > 0.0f)) return lim2;
+      const float r = fminf(sqrtf(lim2) + pad, cover);
+      return fmaxf(lim2, r * r);
+    };
+    float lim = max_sqdist;
+    if (out.key[K - 1] != MLOAM_KEY_NONE) lim = fminf(lim, kth());
+    float bound = prune_of(lim);
     // blocks that are non-empty and whose box reaches into the bound (ties at equal distance are kept)
     bool reach = false;
     if (lane < 27 && bmask) {
@@ -333,7 +339,7 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
           for (int r = nr + lane; r < KNN_RUNS; r += 32) rb.pref[r] = npts;
           __syncwarp();
           scan_runs<N, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
-          if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
+          if (out.key[K - 1] != MLOAM_KEY_NONE) lim = fminf(lim, kth()), bound = prune_of(lim);
           nr = 0, npts = 0;
           __syncwarp();
         }
@@ -359,8 +365,8 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
       scan_runs<N, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
     }
     if (explored) {  // cells were pruned against bounds that never dropped below the final one
-      if (out.key[K - 1] != MLOAM_KEY_NONE) bound = fminf(bound, kth());
-      *explored = fmaxf(sqrtf(bound) - eps, 0.0f);
+      if (out.key[K - 1] != MLOAM_KEY_NONE) lim = fminf(lim, kth());
+      *explored = fmaxf(sqrtf(prune_of(lim)) - eps, 0.0f);
     }
     return;
   }

@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
     if (i >= n) break;
     const bool in_a = i < na;
     const int j = in_a ? i : i - na;
+    const long long t_query = path_stats ? clock64() : 0ll;
+    int path = 3;  // 0 keep (matched), 1 keep (rejected), 2 ball, 3 blind
     const float4 p = __ldg((in_a ? a.pts : b.pts) + j);
     const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
     TopK<K + 1> best;  // slot K: nearest scanned point outside the K-set (feeds the anchor's slack)
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
         // rejected last time with the K-th neighbour at least radius + an.w away from the anchor: still rejected
         if (within) {
           done = true;
-          if (path_stats && lane == 0) atomicAdd(path_stats + 1, 1u);
+          path = 1;
         }
       } else {
         unsigned long long key = MLOAM_KEY_NONE;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
             if (lane == 0) *anchor = make_float4(sel.x, sel.y, sel.z, 0.0f);
           }
           done = true;
-          if (path_stats && lane == 0) atomicAdd(path_stats + 0, 1u);
+          path = 0;
         }
       }
     }
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
       if (!found)
         warp_knn<K, true, K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best,
                                  &explored, 0.05f);
-      if (path_stats && lane == 0) atomicAdd(path_stats + (found ? 2 : 3), 1u);
+      path = found ? 2 : 3;
       const bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
                       __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
       int mypos = -1;
@@ -150,6 +152,12 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
     if (changed) {
       const bool diff = __any_sync(MLOAM_FULL_MASK, lane < K && (!seeded || newpos != prev));
       if (lane == 0) changed[j] = diff ? 1 : 0;
+    }
+    if (path_stats && lane == 0) {  // stage profiling: queries and SM cycles per search path, slowest single query
+      const unsigned long long dt = (unsigned long long)(clock64() - t_query);
+      atomicAdd(path_stats + path, 1u);
+      atomicAdd(reinterpret_cast<unsigned long long *>(path_stats + 8) + path, dt);
+      atomicMax(path_stats + 4, (unsigned)(dt > 0xffffffffull ? 0xffffffffull : dt));
     }
     if (!work) i += gridDim.x * MWARPS;
   }
