@@ -339,6 +339,12 @@ def main():
     knn_paths = {name: ctx.profile_get(name)[1] / prof_steps for name in ("knn_keep_matched", "knn_keep_rejected", "knn_ball", "knn_blind", "knn_cycles_keep_matched",
                               "knn_cycles_keep_rejected", "knn_cycles_ball", "knn_cycles_blind")}
     knn_paths["max_query_cycles"] = ctx.profile_get("knn_max_query_cycles")[1]
+    knn_paths["queries_over_32k_cycles"] = ctx.profile_get("knn_queries_over_32k_cycles")[1] / prof_steps
+    knn_paths["queries_over_64k_cycles"] = ctx.profile_get("knn_queries_over_64k_cycles")[1] / prof_steps
+    for nm in ("cycles_coarse", "cycles_ring1", "cycles_finish", "ring1_points", "finish_points", "finish_blocks", "finish_cells", "finish_queries"):
+        knn_paths["blind_" + nm] = ctx.profile_get("knn_blind_" + nm)[1] / prof_steps
+    slowest = ctx.profile_get("knn_slowest_query")[1]
+    knn_paths["slowest_query"] = {"cycles": slowest >> 32, "path": (slowest >> 30) & 3, "set": (slowest >> 29) & 1, "feature": slowest & 0x1fffffff}
     ctx.profile(False)
 
     # ---- e2e: HOST buffers through the C ABI (H2D sweep + both submaps, D2H pose) — wall clock around synchronous calls

@@ -174,13 +174,24 @@ int mloam_profile_get(mloam_ctx_t *h, const char *name, double *ms_total, long l
   cudaStreamSynchronize(c->stream);
   prof_collect(c);
   // query counts / SM cycles of the matcher's search paths (k_match_knn), reported through `launches`
-  static const char *kPaths[9] = {"knn_keep_matched", "knn_keep_rejected", "knn_ball", "knn_blind", "knn_max_query_cycles",
-                                  "knn_cycles_keep_matched", "knn_cycles_keep_rejected", "knn_cycles_ball", "knn_cycles_blind"};
-  for (int k = 0; k < 9; k++)
+  static const char *kBlind[8] = {"knn_blind_cycles_coarse", "knn_blind_cycles_ring1", "knn_blind_cycles_finish", "knn_blind_ring1_points",
+                                  "knn_blind_finish_points", "knn_blind_finish_blocks", "knn_blind_finish_cells", "knn_blind_finish_queries"};
+  for (int k = 0; k < 8; k++)
+    if (!strcmp(name, kBlind[k])) {
+      unsigned long long v = 0;
+      MLOAM_CUDA_OK(c, cudaMemcpy(&v, c->scratch[7].as<char>() + kKnnPathStatsOffset + 96 + 8 * (size_t)k, 8, cudaMemcpyDeviceToHost));
+      if (ms_total) *ms_total = 0.0;
+      if (launches) *launches = (long long)v;
+      return MLOAM_OK;
+    }
+  static const char *kPaths[12] = {"knn_keep_matched", "knn_keep_rejected", "knn_ball", "knn_blind", "knn_max_query_cycles",
+                                   "knn_queries_over_32k_cycles", "knn_queries_over_64k_cycles", "knn_cycles_keep_matched",
+                                   "knn_cycles_keep_rejected", "knn_cycles_ball", "knn_cycles_blind", "knn_slowest_query"};
+  for (int k = 0; k < 12; k++)
     if (!strcmp(name, kPaths[k])) {
       unsigned long long v = 0;
-      const size_t off = kKnnPathStatsOffset + (k < 5 ? 4 * (size_t)k : 32 + 8 * (size_t)(k - 5));
-      MLOAM_CUDA_OK(c, cudaMemcpy(&v, c->scratch[7].as<char>() + off, k < 5 ? 4 : 8, cudaMemcpyDeviceToHost));
+      const size_t off = kKnnPathStatsOffset + (k < 7 ? 4 * (size_t)k : 32 + 8 * (size_t)(k - 7));
+      MLOAM_CUDA_OK(c, cudaMemcpy(&v, c->scratch[7].as<char>() + off, k < 7 ? 4 : 8, cudaMemcpyDeviceToHost));
       if (ms_total) *ms_total = 0.0;
       if (launches) *launches = (long long)v;
       return MLOAM_OK;
@@ -194,7 +205,7 @@ int mloam_profile_reset(mloam_ctx_t *h) {
   if (!h) return MLOAM_E_INVALID;
   cudaStreamSynchronize(h->c.stream);
   prof_collect(&h->c);
-  cudaMemset(h->c.scratch[7].as<char>() + kKnnPathStatsOffset, 0, 64);
+  cudaMemset(h->c.scratch[7].as<char>() + kKnnPathStatsOffset, 0, 160);
   h->c.prof.clear();
   return MLOAM_OK;
 }

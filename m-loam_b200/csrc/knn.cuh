@@ -42,6 +42,12 @@ __device__ __forceinline__ void topk_reset(TopK<K> &t) {
 
 // Per-warp run table (shared memory): run r = points [start[r], start[r] + count) with pref[r] = points before it.
 constexpr int KNN_RUNS = 64;
+
+// Optional per-query instrumentation of the blind search (stage profiling only).
+struct KnnDbg {
+  long long t_coarse, t_ring1, t_finish;  // SM cycles per phase
+  int ring1_pts, finish_pts, finish_blocks, finish_cells;
+};
 struct RunBuf {
   int start[KNN_RUNS];
   int pref[KNN_RUNS];
@@ -208,7 +214,8 @@ __device__ __forceinline__ bool warp_knn_seeded(const MapView &map, RunBuf &rb, 
 // map point has been scanned (0 when unknown) — together a lower bound on the (K+1)-th distance.
 template <int K, bool REJECT_PARTIAL, int N = K>
 __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float qx, float qy, float qz, float max_sqdist, int lane,
-                                         TopK<N> &out, float *explored = nullptr, float pad = 0.0f) {
+                                         TopK<N> &out, float *explored = nullptr, float pad = 0.0f, KnnDbg *dbg = nullptr) {
+  long long t_mark = dbg ? clock64() : 0ll;
   // *explored: every map point closer than this has been scanned into `out` — or, on the REJECT_PARTIAL block exit,
   // counted: fewer than K points exist inside that distance.  Hence min(K-th scanned, *explored) bounds the true K-th
   // distance from below, and min((K+1)-th scanned, *explored) the (K+1)-th.  pad > 0 lets the mask-guided finish look
@@ -233,6 +240,10 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
       if (slot >= 0) bmask = __ldg(map.block_mask + slot);
     }
     const int total = __reduce_add_sync(MLOAM_FULL_MASK, cnt);
+    if (dbg) {
+      const long long t = clock64();
+      dbg->t_coarse = t - t_mark, t_mark = t;
+    }
     if (REJECT_PARTIAL && coarse_ok && total < K) {
       if (explored) {  // distance from the query to the hull of the 3x3x3 blocks
         const float bw = map.cell * (float)B;
@@ -266,6 +277,10 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
     rb.pref[lane] = excl;
     __syncwarp();
     scan_runs<N, 32>(map, rb, total, qx, qy, qz, lane, out);
+    if (dbg) {
+      const long long t = clock64();
+      dbg->t_ring1 = t - t_mark, t_mark = t, dbg->ring1_pts = total;
+    }
   }
   auto face_gap = [&](int r) {  // distance from the query to the nearest face of the visited cube [c-r, c+r+1) * cell
     float g = qx - (float)(cx - r) * map.cell;
@@ -314,16 +329,31 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
     }
     int nr = 0, npts = 0;  // runs / points currently in the table (warp-uniform)
     __syncwarp();          // ring 1 is done reading the table
-    for (unsigned todo = __ballot_sync(MLOAM_FULL_MASK, reach); todo; todo &= todo - 1) {
-      const int bl = __ffs(todo) - 1;
-      const unsigned long long m = __shfl_sync(MLOAM_FULL_MASK, bmask, bl);
-      const int b0x = (ccx + bl % 3 - 1) * B, b0y = (ccy + (bl % 9) / 3 - 1) * B, b0z = (ccz + bl / 9 - 1) * B;
+    // The occupied cells of all reaching blocks form ONE flat candidate list (block b contributes popc(mask_b)
+    // entries): 32 candidates per step are tested against the bound and probed together, so the cost is one
+    // dependent table access per 32 candidate cells instead of one per block half.
+    const int my_cnt = reach ? __popcll(bmask) : 0;
+    int n_cand;
+    const int my_base = warp_excl_scan(my_cnt, lane, &n_cand);
+    for (int t0 = 0; t0 < n_cand; t0 += 32) {
+      const int t = t0 + lane;
+      int bl = 0;  // largest block index with base <= t
 #pragma unroll
-      for (int half = 0; half < 2; half++) {
-        const int b = lane + 32 * half;  // this lane's cell of the block
-        bool take = (m >> b) & 1ull;
-        const int fx = b0x + (b & 3), fy = b0y + ((b >> 2) & 3), fz = b0z + (b >> 4);
-        if (take && abs(fx - cx) <= 1 && abs(fy - cy) <= 1 && abs(fz - cz) <= 1) take = false;  // ring 1 did it
+      for (int step = 16; step > 0; step >>= 1) {
+        const int cand = bl + step;
+        const int v = __shfl_sync(MLOAM_FULL_MASK, my_base, cand < 27 ? cand : 26);
+        if (cand < 27 && v <= t) bl = cand;
+      }
+      const unsigned long long m = __shfl_sync(MLOAM_FULL_MASK, bmask, bl);
+      const int u = t - __shfl_sync(MLOAM_FULL_MASK, my_base, bl);
+      bool take = t < n_cand;
+      int fx = 0, fy = 0, fz = 0;
+      if (take) {
+        const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+        const int nlo = __popc(lo);
+        const int b = u < nlo ? (int)__fns(lo, 0u, u + 1) : 32 + (int)__fns(hi, 0u, u - nlo + 1);
+        fx = (ccx + bl % 3 - 1) * B + (b & 3), fy = (ccy + (bl % 9) / 3 - 1) * B + ((b >> 2) & 3), fz = (ccz + bl / 9 - 1) * B + (b >> 4);
+        if (abs(fx - cx) <= 1 && abs(fy - cy) <= 1 && abs(fz - cz) <= 1) take = false;  // ring 1 did it
         if (take) {
           const float lox = (float)fx * map.cell, loy = (float)fy * map.cell, loz = (float)fz * map.cell;
           const float gx = fmaxf(fmaxf(lox - qx, qx - (lox + map.cell)) - eps, 0.0f);
@@ -331,39 +361,43 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
           const float gz = fmaxf(fmaxf(loz - qz, qz - (loz + map.cell)) - eps, 0.0f);
           take = gx * gx + gy * gy + gz * gz <= bound;
         }
-        const unsigned tk = __ballot_sync(MLOAM_FULL_MASK, take);
-        if (!tk) continue;
-        const int ncell = __popc(tk);
-        if (nr + ncell > KNN_RUNS) {  // flush the table through the flat scan
-          __syncwarp();
-          for (int r = nr + lane; r < KNN_RUNS; r += 32) rb.pref[r] = npts;
-          __syncwarp();
-          scan_runs<N, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
-          if (out.key[K - 1] != MLOAM_KEY_NONE) lim = fminf(lim, kth()), bound = prune_of(lim);
-          nr = 0, npts = 0;
-          __syncwarp();
-        }
-        int start = 0, count = 0;
-        if (take) {
-          const HashEntry e = hash_lookup(map, pack_cell(fx, fy, fz));
-          start = e.start, count = e.count;
-        }
-        int tot;
-        const int excl = warp_excl_scan(count, lane, &tot);
-        if (take) {
-          const int slot = nr + __popc(tk & ((1u << lane) - 1u));
-          rb.start[slot] = start;
-          rb.pref[slot] = npts + excl;
-        }
-        nr += ncell, npts += tot;
       }
+      if (dbg) dbg->finish_blocks++;
+      const unsigned tk = __ballot_sync(MLOAM_FULL_MASK, take);
+      if (!tk) continue;
+      const int ncell = __popc(tk);
+      if (nr + ncell > KNN_RUNS) {  // flush the table through the flat scan
+        __syncwarp();
+        for (int r = nr + lane; r < KNN_RUNS; r += 32) rb.pref[r] = npts;
+        __syncwarp();
+        scan_runs<N, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
+        if (dbg) dbg->finish_pts += npts, dbg->finish_cells += nr;
+        if (out.key[K - 1] != MLOAM_KEY_NONE) lim = fminf(lim, kth()), bound = prune_of(lim);
+        nr = 0, npts = 0;
+        __syncwarp();
+      }
+      int start = 0, count = 0;
+      if (take) {
+        const HashEntry e = hash_lookup(map, pack_cell(fx, fy, fz));
+        start = e.start, count = e.count;
+      }
+      int tot;
+      const int excl = warp_excl_scan(count, lane, &tot);
+      if (take) {
+        const int slot = nr + __popc(tk & ((1u << lane) - 1u));
+        rb.start[slot] = start;
+        rb.pref[slot] = npts + excl;
+      }
+      nr += ncell, npts += tot;
     }
     if (nr > 0) {
       __syncwarp();
       for (int r = nr + lane; r < KNN_RUNS; r += 32) rb.pref[r] = npts;
       __syncwarp();
       scan_runs<N, KNN_RUNS>(map, rb, npts, qx, qy, qz, lane, out);
+      if (dbg) dbg->finish_pts += npts, dbg->finish_cells += nr;
     }
+    if (dbg) dbg->t_finish = clock64() - t_mark;
     if (explored) {  // cells were pruned against bounds that never dropped below the final one
       if (out.key[K - 1] != MLOAM_KEY_NONE) lim = fminf(lim, kth());
       *explored = fmaxf(sqrtf(prune_of(lim)) - eps, 0.0f);

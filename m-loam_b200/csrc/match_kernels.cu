@@ -121,9 +121,18 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
       if (r2 < min_match_sq_dis)
         found = warp_knn_seeded<K, K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, r2,
                                           0.1f * (in_a ? a.map.cell : b.map.cell), lane, best, &explored);
-      if (!found)
+      if (!found) {
+        KnnDbg dbg = {0, 0, 0, 0, 0, 0, 0};
         warp_knn<K, true, K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best,
-                                 &explored, 0.05f);
+                                 &explored, 0.05f, path_stats ? &dbg : nullptr);
+        if (path_stats && lane == 0) {
+          unsigned long long *q = reinterpret_cast<unsigned long long *>(path_stats + 24);
+          atomicAdd(q + 0, (unsigned long long)dbg.t_coarse), atomicAdd(q + 1, (unsigned long long)dbg.t_ring1);
+          atomicAdd(q + 2, (unsigned long long)dbg.t_finish), atomicAdd(q + 3, (unsigned long long)dbg.ring1_pts);
+          atomicAdd(q + 4, (unsigned long long)dbg.finish_pts), atomicAdd(q + 5, (unsigned long long)dbg.finish_blocks);
+          atomicAdd(q + 6, (unsigned long long)dbg.finish_cells), atomicAdd(q + 7, dbg.t_finish ? 1ull : 0ull);
+        }
+      }
       path = found ? 2 : 3;
       const bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
                       __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
@@ -158,6 +167,11 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
       atomicAdd(path_stats + path, 1u);
       atomicAdd(reinterpret_cast<unsigned long long *>(path_stats + 8) + path, dt);
       atomicMax(path_stats + 4, (unsigned)(dt > 0xffffffffull ? 0xffffffffull : dt));
+      if (dt > 32768ull) atomicAdd(path_stats + 5, 1u);
+      if (dt > 65536ull) atomicAdd(path_stats + 6, 1u);
+      // slowest query: cycles << 32 | path << 30 | set << 29 | feature index
+      atomicMax(reinterpret_cast<unsigned long long *>(path_stats + 16),
+                (dt << 32) | ((unsigned long long)path << 30) | ((unsigned long long)(in_a ? 0 : 1) << 29) | (unsigned)(j & 0x1fffffff));
     }
     if (!work) i += gridDim.x * MWARPS;
   }
