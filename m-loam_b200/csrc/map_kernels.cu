@@ -201,16 +201,13 @@ __global__ void __launch_bounds__(QWARPS * 32)
     const float4 p = __ldg(q + i);
     float3 s = make_float3(p.x, p.y, p.z);
     if (pose7) s = associate(pose_from_param(pose7), p.x, p.y, p.z);
-    TopK<K> best;
+    Best best;
     warp_knn<K, false>(map, rbuf[threadIdx.x >> 5], s.x, s.y, s.z, max_sqdist, lane, best);
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        const float d2 = __uint_as_float((unsigned)(best.key[k] >> 32));
-        const bool ok = best.key[k] != MLOAM_KEY_NONE && d2 < max_sqdist;
-        idx[(size_t)i * K + k] = ok ? (int)(unsigned)(best.key[k] & 0xffffffffu) : -1;
-        sqd[(size_t)i * K + k] = ok ? d2 : INFINITY;
-      }
+    if (lane < K) {  // lane r holds the r-th neighbour
+      const float d2 = key_d2(best.key);
+      const bool ok = best.key != MLOAM_KEY_NONE && d2 < max_sqdist;
+      idx[(size_t)i * K + lane] = ok ? (int)(unsigned)(best.key & 0xffffffffu) : -1;
+      sqd[(size_t)i * K + lane] = ok ? d2 : INFINITY;
     }
   }
 }

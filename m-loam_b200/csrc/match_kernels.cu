@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
     int path = 3;  // 0 keep (matched), 1 keep (rejected), 2 ball, 3 blind
     const float4 p = __ldg((in_a ? a.pts : b.pts) + j);
     const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
-    TopK<K + 1> best;  // slot K: nearest scanned point outside the K-set (feeds the anchor's slack)
+    Best best;  // selection width K + 1: lane K holds the nearest scanned point outside the K-set (feeds the anchor's slack)
     int *const pos_out = (in_a ? a.pos : b.pos) + (size_t)j * K;
     const int seeded = in_a ? a.seeded : b.seeded;
     unsigned char *const changed = in_a ? a.changed : b.changed;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
       float explored = 0.0f;
       bool found = false;
       if (r2 < min_match_sq_dis)
-        found = warp_knn_seeded<K, K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, r2,
+        found = warp_knn_seeded<K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, r2,
                                           0.1f * (in_a ? a.map.cell : b.map.cell), lane, best, &explored);
       if (!found) {
         KnnDbg dbg = {0, 0, 0, 0, 0, 0, 0};
@@ -134,25 +134,21 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
         }
       }
       path = found ? 2 : 3;
-      const bool ok = best.key[K - 1] != MLOAM_KEY_NONE &&
-                      __uint_as_float((unsigned)(best.key[K - 1] >> 32)) < min_match_sq_dis;  // :407,571,667,814
-      int mypos = -1;
-#pragma unroll
-      for (int k = 0; k < K; k++)
-        if (lane == k) mypos = best.pos[k];
-      newpos = ok ? mypos : -1;
+      const unsigned long long kK = best_key(best, K - 1), kK1 = best_key(best, K);
+      const bool ok = kK != MLOAM_KEY_NONE && key_d2(kK) < min_match_sq_dis;  // :407,571,667,814
+      newpos = (ok && lane < K) ? best.pos : -1;
       // anchor: K-set members are within rK of this position, everything else at least lb away
       float slack = 0.0f;
       if (ok) {
-        const float rK = sqrtf(__uint_as_float((unsigned)(best.key[K - 1] >> 32)));
+        const float rK = sqrtf(key_d2(kK));
         float lb = explored;
-        if (best.key[K] != MLOAM_KEY_NONE) lb = fminf(lb, sqrtf(__uint_as_float((unsigned)(best.key[K] >> 32))));
+        if (kK1 != MLOAM_KEY_NONE) lb = fminf(lb, sqrtf(key_d2(kK1)));
         slack = 0.5f * (lb - rK) - 2e-5f;
       } else {
         // rejected: the K-th neighbour is at least lbK away; while the query stays within lbK - radius of here the
         // verdict stands
         float lbK = explored;
-        if (best.key[K - 1] != MLOAM_KEY_NONE) lbK = fminf(lbK, sqrtf(__uint_as_float((unsigned)(best.key[K - 1] >> 32))));
+        if (kK != MLOAM_KEY_NONE) lbK = fminf(lbK, sqrtf(key_d2(kK)));
         slack = lbK - sqrtf(min_match_sq_dis) - 2e-5f;
       }
       if (lane == 0) *anchor = make_float4(sel.x, sel.y, sel.z, slack);

@@ -82,13 +82,14 @@ __global__ void __launch_bounds__(TWARPS * 32)
   for (int i = blockIdx.x * TWARPS + (threadIdx.x >> 5); i < n; i += gridDim.x * TWARPS) {
     const float4 p = __ldg(pts + i);
     const float3 sel = associate(T, p.x, p.y, p.z);  // TransformToStart, b_distortion = false (utility.h:55-77)
-    TopK<1> best;
+    Best best;
     warp_knn<1, true>(map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, dist_sq_thr, lane, best);
-    bool ok = best.key[0] != MLOAM_KEY_NONE && __uint_as_float((unsigned)(best.key[0] >> 32)) < dist_sq_thr;  // :158 / :296
+    const unsigned long long k0 = best_key(best, 0);
+    bool ok = k0 != MLOAM_KEY_NONE && key_d2(k0) < dist_sq_thr;  // :158 / :296
     float out[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int closest = -1, j2 = -1, j3 = -1;
     if (ok) {
-      closest = (int)(unsigned)(best.key[0] & 0xffffffffu);
+      closest = (int)(unsigned)(k0 & 0xffffffffu);
       const float4 c = __ldg(map.orig + closest);
       const int ring = (int)c.w;
       // running minima start at DISTANCE_SQ_THRESHOLD (:163 / :301): candidates must be strictly below it
