@@ -343,6 +343,8 @@ def main():
     knn_paths["queries_over_64k_cycles"] = ctx.profile_get("knn_queries_over_64k_cycles")[1] / prof_steps
     for nm in ("cycles_coarse", "cycles_ring1", "cycles_finish", "ring1_points", "finish_points", "finish_blocks", "finish_cells", "finish_queries"):
         knn_paths["blind_" + nm] = ctx.profile_get("knn_blind_" + nm)[1] / prof_steps
+    knn_paths["slow_blind_record"] = dict(zip(("cycles", "coarse", "ring1", "finish", "ring1_pts", "finish_pts", "finish_cells", "finish_steps", "feature", "pre"),
+                                              [ctx.profile_get("knn_slow_rec%d" % k)[1] for k in range(10)]))
     slowest = ctx.profile_get("knn_slowest_query")[1]
     knn_paths["slowest_query"] = {"cycles": slowest >> 32, "path": (slowest >> 30) & 3, "set": (slowest >> 29) & 1, "feature": slowest & 0x1fffffff}
     ctx.profile(False)

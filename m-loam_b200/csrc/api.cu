@@ -174,6 +174,13 @@ int mloam_profile_get(mloam_ctx_t *h, const char *name, double *ms_total, long l
   cudaStreamSynchronize(c->stream);
   prof_collect(c);
   // query counts / SM cycles of the matcher's search paths (k_match_knn), reported through `launches`
+  if (!strncmp(name, "knn_slow_rec", 12) && name[12] >= '0' && name[12] <= '9') {
+    long long v = 0;
+    MLOAM_CUDA_OK(c, cudaMemcpy(&v, c->scratch[7].as<char>() + kKnnPathStatsOffset + 160 + 8 * (size_t)(name[12] - '0'), 8, cudaMemcpyDeviceToHost));
+    if (ms_total) *ms_total = 0.0;
+    if (launches) *launches = v;
+    return MLOAM_OK;
+  }
   static const char *kBlind[8] = {"knn_blind_cycles_coarse", "knn_blind_cycles_ring1", "knn_blind_cycles_finish", "knn_blind_ring1_points",
                                   "knn_blind_finish_points", "knn_blind_finish_blocks", "knn_blind_finish_cells", "knn_blind_finish_queries"};
   for (int k = 0; k < 8; k++)
@@ -205,7 +212,7 @@ int mloam_profile_reset(mloam_ctx_t *h) {
   if (!h) return MLOAM_E_INVALID;
   cudaStreamSynchronize(h->c.stream);
   prof_collect(&h->c);
-  cudaMemset(h->c.scratch[7].as<char>() + kKnnPathStatsOffset, 0, 160);
+  cudaMemset(h->c.scratch[7].as<char>() + kKnnPathStatsOffset, 0, 256);
   h->c.prof.clear();
   return MLOAM_OK;
 }

@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
                                           0.1f * (in_a ? a.map.cell : b.map.cell), lane, best, &explored);
       if (!found) {
         KnnDbg dbg = {0, 0, 0, 0, 0, 0, 0};
+        const long long t_blind = path_stats ? clock64() : 0ll;
         warp_knn<K, true, K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best,
                                  &explored, 0.05f, path_stats ? &dbg : nullptr);
         if (path_stats && lane == 0) {
@@ -131,6 +132,13 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
           atomicAdd(q + 2, (unsigned long long)dbg.t_finish), atomicAdd(q + 3, (unsigned long long)dbg.ring1_pts);
           atomicAdd(q + 4, (unsigned long long)dbg.finish_pts), atomicAdd(q + 5, (unsigned long long)dbg.finish_blocks);
           atomicAdd(q + 6, (unsigned long long)dbg.finish_cells), atomicAdd(q + 7, dbg.t_finish ? 1ull : 0ull);
+          const long long dt_blind = clock64() - t_blind;
+          if (dt_blind > 90000) {  // a record of one very slow blind query (benign race: any of them will do)
+            long long *rec = reinterpret_cast<long long *>(path_stats + 40);
+            rec[0] = dt_blind, rec[1] = dbg.t_coarse, rec[2] = dbg.t_ring1, rec[3] = dbg.t_finish, rec[4] = dbg.ring1_pts;
+            rec[5] = dbg.finish_pts, rec[6] = dbg.finish_cells, rec[7] = dbg.finish_blocks, rec[8] = (in_a ? 0 : 1) * 1000000 + j;
+            rec[9] = (long long)(t_blind - t_query);
+          }
         }
       }
       path = found ? 2 : 3;
