@@ -278,15 +278,43 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
   const int B = 1 << MLOAM_COARSE_SHIFT;
   const int ccx = cx >> MLOAM_COARSE_SHIFT, ccy = cy >> MLOAM_COARSE_SHIFT, ccz = cz >> MLOAM_COARSE_SHIFT;
   const bool coarse_ok = map.cell * (float)B >= radius * 1.0002f + 64.0f * eps;
-  // ---- step 0: block occupancy
+  // ---- step 0 + ring 1 probes, issued together: lane l < 27 fetches the occupancy record of block l of the 3x3x3
+  // blocks around the query's block (point count + 64-bit mask of occupied cells; the mask is read speculatively from
+  // the record's home slot) AND the record of cell l of the 3x3x3 cells around the query's cell — three independent
+  // loads in flight per lane, one memory round trip instead of three dependent ones.
   unsigned long long bmask = 0ull;
+  int start = 0, count = 0;  // this lane's ring-1 run
   {
     int cnt = 0;
     if (lane < 27) {
-      int slot;
-      const HashEntry e = hash_lookup(map, coarse_key(ccx + lane % 3 - 1, ccy + (lane % 9) / 3 - 1, ccz + lane / 9 - 1), &slot);
-      cnt = e.start;  // block records keep their point count in `start`
-      if (slot >= 0) bmask = __ldg(map.block_mask + slot);
+      const int dx = lane % 3 - 1, dy = (lane % 9) / 3 - 1, dz = lane / 9 - 1;
+      const unsigned long long kb = coarse_key(ccx + dx, ccy + dy, ccz + dz), kc = pack_cell(cx + dx, cy + dy, cz + dz);
+      unsigned hb = hash_cell(kb) & map.mask, hc = hash_cell(kc) & map.mask;
+      uint4 eb = __ldg(reinterpret_cast<const uint4 *>(map.table + hb));
+      uint4 ec = __ldg(reinterpret_cast<const uint4 *>(map.table + hc));
+      const unsigned long long m_home = __ldg(map.block_mask + hb);
+      bool moved = false;
+      while (true) {  // block record
+        const unsigned long long k = ((unsigned long long)eb.y << 32) | eb.x;
+        if (k == kb) {
+          cnt = (int)eb.z;  // block records keep their point count in `start`
+          bmask = moved ? __ldg(map.block_mask + hb) : m_home;
+          break;
+        }
+        if (k == MLOAM_EMPTY_KEY) break;
+        hb = (hb + 1) & map.mask, moved = true;
+        eb = __ldg(reinterpret_cast<const uint4 *>(map.table + hb));
+      }
+      while (true) {  // cell record
+        const unsigned long long k = ((unsigned long long)ec.y << 32) | ec.x;
+        if (k == kc) {
+          start = (int)ec.z, count = (int)ec.w;
+          break;
+        }
+        if (k == MLOAM_EMPTY_KEY) break;
+        hc = (hc + 1) & map.mask;
+        ec = __ldg(reinterpret_cast<const uint4 *>(map.table + hc));
+      }
     }
     const int total = __reduce_add_sync(MLOAM_FULL_MASK, cnt);
     if (dbg) {
@@ -307,18 +335,8 @@ __device__ __forceinline__ void warp_knn(const MapView &map, RunBuf &rb, float q
       return;
     }
   }
-  // ---- ring 1
+  // ---- ring 1: scan the 27 cells' runs as one flat list
   {
-    const int dx = lane % 3 - 1, dy = (lane % 9) / 3 - 1, dz = lane / 9 - 1;  // lanes 27..31 idle
-    const int fx = cx + dx, fy = cy + dy, fz = cz + dz;
-    const int bl = ((fz >> MLOAM_COARSE_SHIFT) - ccz + 1) * 9 + ((fy >> MLOAM_COARSE_SHIFT) - ccy + 1) * 3 +
-                   ((fx >> MLOAM_COARSE_SHIFT) - ccx + 1);
-    const unsigned long long m = __shfl_sync(MLOAM_FULL_MASK, bmask, lane < 27 ? bl : 0);
-    int start = 0, count = 0;
-    if (lane < 27 && ((m >> cell_bit(fx, fy, fz)) & 1ull)) {
-      const HashEntry e = hash_lookup(map, pack_cell(fx, fy, fz));
-      start = e.start, count = e.count;
-    }
     const int total = fill_runs32(rb, start, count, lane);
     out = scan_runs<N>(map.sorted, &rb, total, qx, qy, qz, out);
     if (dbg) {

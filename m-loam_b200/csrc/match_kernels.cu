@@ -42,22 +42,28 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
   const int nb = b.d_n ? min(b.n, *b.d_n) : b.n;
   const int n = na + nb;
   const PoseD T = pose_from_param(pose7);
-  int i = blockIdx.x * MWARPS + (threadIdx.x >> 5);
-  int next = 0;
-  if (work) {  // software-pipelined queue: the next index is requested before the current feature is processed
-    if (lane == 0) next = atomicAdd(work, 1);
+  // Feature indices come from a dynamic queue (an atomic head, `work`) or a static stride.  Both the index and the
+  // feature point are fetched two queries ahead, so neither the atomic nor the point load sits on a query's critical path.
+  const int stride = gridDim.x * MWARPS;
+  auto fetch = [&](int idx) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < n) v = __ldg(idx < na ? a.pts + idx : b.pts + (idx - na));
+    return v;
+  };
+  int i = blockIdx.x * MWARPS + (threadIdx.x >> 5), i_next = i + stride;
+  if (work) {
+    int t0 = 0, t1 = 0;
+    if (lane == 0) t0 = atomicAdd(work, 1), t1 = atomicAdd(work, 1);
+    i = __shfl_sync(MLOAM_FULL_MASK, t0, 0), i_next = __shfl_sync(MLOAM_FULL_MASK, t1, 0);
   }
-  while (true) {
-    if (work) {
-      i = __shfl_sync(MLOAM_FULL_MASK, next, 0);
-      if (i < n && lane == 0) next = atomicAdd(work, 1);
-    }
-    if (i >= n) break;
+  float4 p = fetch(i), p_next = fetch(i_next);
+  while (i < n) {
+    int i_after = i_next + stride;
+    if (work && lane == 0) i_after = (i_next < n) ? atomicAdd(work, 1) : n;  // in flight while this query is processed
     const bool in_a = i < na;
     const int j = in_a ? i : i - na;
     const long long t_query = path_stats ? clock64() : 0ll;
     int path = 3;  // 0 keep (matched), 1 keep (rejected), 2 ball, 3 blind
-    const float4 p = __ldg((in_a ? a.pts : b.pts) + j);
     const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
     Best best;  // selection width K + 1: lane K holds the nearest scanned point outside the K-set (feeds the anchor's slack)
     int *const pos_out = (in_a ? a.pos : b.pos) + (size_t)j * K;
@@ -177,7 +183,9 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
       atomicMax(reinterpret_cast<unsigned long long *>(path_stats + 16),
                 (dt << 32) | ((unsigned long long)path << 30) | ((unsigned long long)(in_a ? 0 : 1) << 29) | (unsigned)(j & 0x1fffffff));
     }
-    if (!work) i += gridDim.x * MWARPS;
+    if (work) i_after = __shfl_sync(MLOAM_FULL_MASK, i_after, 0);
+    i = i_next, p = p_next;
+    i_next = i_after, p_next = fetch(i_after);
   }
 }
 
