@@ -99,6 +99,8 @@ struct Ctx {
   DevBuf knn_pos[2];              // int[n_neigh] per query: neighbour positions handed from k_match_knn to k_match_fit
   DevBuf knn_changed[2];          // unsigned char per query: neighbour list differs from the previous iteration's
   DevBuf knn_anchor[2];           // float4 per query: position of its last real search + tolerated displacement
+  DevBuf knn_heavy[2];            // 2 x unsigned char per query: "needed a real search" verdicts of the last two launches
+  int knn_parity = 0;             // which half of knn_heavy the next seeded launch reads
   DevBuf partials;                // per-block packed normal equations
   DevBuf lm_state;                // LMState
   void *ticket_zeroed_for = nullptr;  // partials allocation whose last-block ticket has been zeroed

@@ -27,6 +27,8 @@ struct KnnSet {
   int seeded;          // pos holds this set's result of the previous re-association iteration on the SAME map
   unsigned char *changed;  // out (nullable): 1 when the neighbour list differs from the seed (or there was none)
   float4 *anchor;      // per feature: map-frame position of its last real search + the displacement it tolerates
+  const unsigned char *heavy_in;  // nullable: 1 where the previous launch had to search (ball / blind) — those go first
+  unsigned char *heavy_out;       // this launch's verdict, for the next one
 };
 
 #ifndef MLOAM_KNN_MINBLOCKS
@@ -44,22 +46,45 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
   const PoseD T = pose_from_param(pose7);
   // Feature indices come from a dynamic queue (an atomic head, `work`) or a static stride.  Both the index and the
   // feature point are fetched two queries ahead, so neither the atomic nor the point load sits on a query's critical path.
+  // With heavy_in the queue runs over 2n virtual indices: pass 0 takes the features that needed a real search last
+  // time (tens of thousands of cycles each), pass 1 the cheap rest — long queries start first instead of forming the
+  // tail of the launch.
+  const bool two_pass = a.heavy_in != nullptr || b.heavy_in != nullptr;
+  const int n_virtual = two_pass ? 2 * n : n;
   const int stride = gridDim.x * MWARPS;
-  auto fetch = [&](int idx) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (idx < n) v = __ldg(idx < na ? a.pts + idx : b.pts + (idx - na));
-    return v;
+  auto fetch = [&](int v, int *skip) {
+    float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+    *skip = 0;
+    if (v < n_virtual) {
+      const int idx = v >= n ? v - n : v;
+      const bool ina = idx < na;
+      pt = __ldg(ina ? a.pts + idx : b.pts + (idx - na));
+      if (two_pass) {
+        const unsigned char *hin = ina ? a.heavy_in : b.heavy_in;
+        const int heavy = hin ? (int)hin[ina ? idx : idx - na] : 0;
+        *skip = (heavy != 0) != (v < n);  // pass 0 (v < n): heavy ones; pass 1: the others
+      }
+    }
+    return pt;
   };
-  int i = blockIdx.x * MWARPS + (threadIdx.x >> 5), i_next = i + stride;
+  int v = blockIdx.x * MWARPS + (threadIdx.x >> 5), v_next = v + stride;
   if (work) {
     int t0 = 0, t1 = 0;
     if (lane == 0) t0 = atomicAdd(work, 1), t1 = atomicAdd(work, 1);
-    i = __shfl_sync(MLOAM_FULL_MASK, t0, 0), i_next = __shfl_sync(MLOAM_FULL_MASK, t1, 0);
+    v = __shfl_sync(MLOAM_FULL_MASK, t0, 0), v_next = __shfl_sync(MLOAM_FULL_MASK, t1, 0);
   }
-  float4 p = fetch(i), p_next = fetch(i_next);
-  while (i < n) {
-    int i_after = i_next + stride;
-    if (work && lane == 0) i_after = (i_next < n) ? atomicAdd(work, 1) : n;  // in flight while this query is processed
+  int skip, skip_next;
+  float4 p = fetch(v, &skip), p_next = fetch(v_next, &skip_next);
+  while (v < n_virtual) {
+    int v_after = v_next + stride;
+    if (work && lane == 0) v_after = (v_next < n_virtual) ? atomicAdd(work, 1) : n_virtual;  // in flight during this query
+    const int i = v >= n ? v - n : v;
+    if (skip) {
+      if (work) v_after = __shfl_sync(MLOAM_FULL_MASK, v_after, 0);
+      v = v_next, p = p_next, skip = skip_next;
+      v_next = v_after, p_next = fetch(v_after, &skip_next);
+      continue;
+    }
     const bool in_a = i < na;
     const int j = in_a ? i : i - na;
     const long long t_query = path_stats ? clock64() : 0ll;
@@ -183,9 +208,11 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
       atomicMax(reinterpret_cast<unsigned long long *>(path_stats + 16),
                 (dt << 32) | ((unsigned long long)path << 30) | ((unsigned long long)(in_a ? 0 : 1) << 29) | (unsigned)(j & 0x1fffffff));
     }
-    if (work) i_after = __shfl_sync(MLOAM_FULL_MASK, i_after, 0);
-    i = i_next, p = p_next;
-    i_next = i_after, p_next = fetch(i_after);
+    unsigned char *const hout = in_a ? a.heavy_out : b.heavy_out;
+    if (hout && lane == 0) hout[j] = path >= 2 ? 1 : 0;
+    if (work) v_after = __shfl_sync(MLOAM_FULL_MASK, v_after, 0);
+    v = v_next, p = p_next, skip = skip_next;
+    v_next = v_after, p_next = fetch(v_after, &skip_next);
   }
 }
 
@@ -311,6 +338,7 @@ int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_
   KnnSet ks[2];
   FitSet fs[2];
   int n_upper = 0;
+  bool flip = false;
   for (int t = 0; t < 2; t++) {
     KnnSet &k = ks[t];
     FitSet &f = fs[t];
@@ -335,12 +363,20 @@ int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_
     DevBuf &ab = c->knn_anchor[t];
     MLOAM_CUDA_OK(c, ab.reserve(sizeof(float4) * (size_t)(J.n + 1)));
     k.seeded = J.seeded, k.changed = cb.as<unsigned char>(), k.anchor = ab.as<float4>();
+    // search verdicts ("had to search") alternate between two halves from launch to launch: read the previous, write the next
+    DevBuf &hb = c->knn_heavy[t];
+    const size_t half = ((size_t)J.n + 256) & ~(size_t)255;
+    MLOAM_CUDA_OK(c, hb.reserve(2 * half));
+    k.heavy_in = J.seeded ? hb.as<unsigned char>() + half * (size_t)c->knn_parity : nullptr;
+    k.heavy_out = hb.as<unsigned char>() + half * (size_t)(J.seeded ? (c->knn_parity ^ 1) : c->knn_parity);
+    flip = flip || J.seeded;
     f.changed = (J.seeded && !J.nn) ? cb.as<unsigned char>() : nullptr;
     f.sorted = k.map.sorted, f.pts = J.pts, f.n = J.n, f.d_n = J.d_n, f.pos = pb.as<int>();
     f.valid = J.valid, f.coeff = J.coeff, f.nn = J.nn, f.is_plane = J.type == 's' ? 1 : 0;
     n_upper += J.n;
   }
   if (n_upper <= 0) return MLOAM_OK;
+  if (flip) c->knn_parity ^= 1;
   cudaStream_t st = c->stream;
   {
     ProfScope ps(c, "match");
