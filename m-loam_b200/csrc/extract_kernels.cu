@@ -602,6 +602,182 @@ __global__ void k_less_flat_gather(const float4 *__restrict__ P, const int *__re
   }
 }
 
+// ------------------------------------------------------------------------------------------ per-ring voxel grid
+// :258-271 in ONE CTA per ring: gather the ring's less-flat points (label <= 0, ring order), pcl::VoxelGrid(0.2) on
+// them — bounding box, voxel index, a bitonic sort of (voxel index << 14 | offset in ring) in shared memory (the
+// offset in the low bits makes the order inside a voxel the input order, i.e. what a stable sort gives), run heads,
+// ordered float centroid sums — and stage the centroids at the ring's own window of `stage_out`.  Replaces the
+// flag / scan / gather kernels and a 5-pass segmented radix sort (about 40 launches) for the per-ring filter.
+constexpr int RV_THREADS = 512;
+constexpr int RV_MAX_P2 = 16384;  // >= RING_MAX
+
+__device__ __forceinline__ int block_excl_scan_512(int v, int *warp_tot /* smem[17] */, int *total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(MLOAM_FULL_MASK, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    const int x = lane < RV_THREADS / 32 ? warp_tot[lane] : 0;
+    int s = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(MLOAM_FULL_MASK, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane < RV_THREADS / 32) warp_tot[lane] = s - x;
+    if (lane == 31) warp_tot[16] = s;
+  }
+  __syncthreads();
+  const int r = warp_tot[w] + inc - v;
+  *total = warp_tot[16];
+  __syncthreads();  // warp_tot may be reused right away
+  return r;
+}
+
+__global__ void __launch_bounds__(RV_THREADS)
+    k_ring_voxel(const float4 *__restrict__ P, const int *__restrict__ label, int n, const int *__restrict__ scan_start,
+                 const int *__restrict__ scan_end, float inv, float4 *__restrict__ stage_out, int *__restrict__ ring_cnt) {
+  extern __shared__ unsigned long long rv_keys[];  // RV_MAX_P2
+  __shared__ int warp_tot[17];
+  __shared__ unsigned bb[6];  // ordered-uint min xyz, max xyz
+  const int ring = blockIdx.x;
+  const int s = scan_start[ring], e = scan_end[ring];
+  const int len = e - s;
+  // the rings k_ring_pick processes (:155 and the on-chip window check)
+  if (len < 6 || len + 10 > RING_MAX || s - 5 < 0 || e + 5 > n) {
+    if (threadIdx.x == 0) ring_cnt[ring] = 0;
+    return;
+  }
+  if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu, bb[3 + threadIdx.x] = 0u;
+  __syncthreads();
+  // pass 1: bounding box of the finite less-flat points (getMinMax3D) + their number
+  int nq = 0;
+  {
+    unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+    int cnt = 0;
+    for (int t = threadIdx.x; t < len; t += RV_THREADS) {
+      if (label[s + t] > 0) continue;
+      cnt++;
+      const float4 p = P[s + t];
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        mn[0] = min(mn[0], f2ord(p.x)), mn[1] = min(mn[1], f2ord(p.y)), mn[2] = min(mn[2], f2ord(p.z));
+        mx[0] = max(mx[0], f2ord(p.x)), mx[1] = max(mx[1], f2ord(p.y)), mx[2] = max(mx[2], f2ord(p.z));
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      mn[d] = __reduce_min_sync(MLOAM_FULL_MASK, mn[d]);
+      mx[d] = __reduce_max_sync(MLOAM_FULL_MASK, mx[d]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) atomicMin(&bb[d], mn[d]), atomicMax(&bb[3 + d], mx[d]);
+    }
+    int dummy = block_excl_scan_512(cnt, warp_tot, &nq);
+    (void)dummy;
+  }
+  if (nq == 0) {
+    if (threadIdx.x == 0) ring_cnt[ring] = 0;
+    return;
+  }
+  const float mn0 = ord2f(bb[0]), mn1 = ord2f(bb[1]), mn2 = ord2f(bb[2]);
+  const float mx0 = ord2f(bb[3]), mx1 = ord2f(bb[4]), mx2 = ord2f(bb[5]);
+  const long long ddx = (long long)((mx0 - mn0) * inv) + 1, ddy = (long long)((mx1 - mn1) * inv) + 1, ddz = (long long)((mx2 - mn2) * inv) + 1;
+  const bool pass_through = ddx * ddy * ddz > 2147483647ll;  // :92-101
+  const int minb0 = (int)floorf(mn0 * inv), minb1 = (int)floorf(mn1 * inv), minb2 = (int)floorf(mn2 * inv);
+  const int div0 = (int)floorf(mx0 * inv) - minb0 + 1, div1 = (int)floorf(mx1 * inv) - minb1 + 1;
+  int P2 = 1;
+  while (P2 < nq) P2 <<= 1;
+  // pass 2: keys, written densely in ring order (tile by tile so that the compaction keeps that order)
+  int carry = 0;
+  for (int base = 0; base < len; base += RV_THREADS) {
+    const int t = base + threadIdx.x;
+    const bool f = t < len && label[s + t] <= 0;
+    int tile_total;
+    const int q = carry + block_excl_scan_512(f ? 1 : 0, warp_tot, &tile_total);
+    if (f) {
+      const float4 p = P[s + t];
+      unsigned long long key = 0xffffffffffffffffull;  // non-finite points are dropped
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        unsigned idx;
+        if (pass_through) {
+          idx = (unsigned)q;
+        } else {
+          const int i0 = (int)(floorf(p.x * inv) - (float)minb0);
+          const int i1 = (int)(floorf(p.y * inv) - (float)minb1);
+          const int i2 = (int)(floorf(p.z * inv) - (float)minb2);
+          idx = (unsigned)(i0 + i1 * div0 + i2 * (div0 * div1));
+        }
+        key = ((unsigned long long)idx << 14) | (unsigned)t;
+      }
+      rv_keys[q] = key;
+    }
+    carry += tile_total;
+  }
+  for (int t = nq + threadIdx.x; t < P2; t += RV_THREADS) rv_keys[t] = 0xffffffffffffffffull;
+  __syncthreads();
+  // bitonic sort, ascending
+  for (int k2 = 2; k2 <= P2; k2 <<= 1) {
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (int t = threadIdx.x; t < P2; t += RV_THREADS) {
+        const int ixj = t ^ j2;
+        if (ixj > t) {
+          const unsigned long long a = rv_keys[t], b = rv_keys[ixj];
+          const bool up = (t & k2) == 0;
+          if ((a > b) == up) rv_keys[t] = b, rv_keys[ixj] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // run heads -> output slots -> ordered centroid sums (:239-250 and the centroid loop)
+  carry = 0;
+  for (int base = 0; base < nq; base += RV_THREADS) {
+    const int k = base + threadIdx.x;
+    bool head = false;
+    unsigned long long key = 0xffffffffffffffffull;
+    if (k < nq) {
+      key = rv_keys[k];
+      head = key != 0xffffffffffffffffull && (k == 0 || (rv_keys[k - 1] >> 14) != (key >> 14));
+    }
+    int tile_total;
+    const int slot = carry + block_excl_scan_512(head ? 1 : 0, warp_tot, &tile_total);
+    if (head) {
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int j = k;
+      for (; j < nq && (rv_keys[j] >> 14) == (key >> 14); j++) {
+        const float4 p = P[s + (int)(rv_keys[j] & 0x3fffull)];
+        sx = sx + p.x, sy = sy + p.y, sz = sz + p.z, si = si + p.w;
+      }
+      const float cnt = (float)(j - k);
+      stage_out[s + slot] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+    }
+    carry += tile_total;
+  }
+  if (threadIdx.x == 0) ring_cnt[ring] = carry;
+}
+
+// Concatenate the rings' staged centroids in ring order (the order of :271's `+=`).
+__global__ void k_ring_voxel_emit(const float4 *__restrict__ stage_out, const int *__restrict__ ring_cnt, const int *__restrict__ scan_start,
+                                  int n_scans, float4 *__restrict__ out, int *__restrict__ n_out) {
+  __shared__ int off;
+  const int r = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int a = 0;
+    for (int q = 0; q < r; q++) a += ring_cnt[q];
+    off = a;
+    if (r == n_scans - 1) *n_out = a + ring_cnt[r];
+  }
+  __syncthreads();
+  const int cnt = ring_cnt[r], s = scan_start[r];
+  for (int k = threadIdx.x; k < cnt; k += blockDim.x) out[off + k] = stage_out[s + k];
+}
+
 __global__ void k_transform_points(float4 *pts, int n, const int *__restrict__ d_n, const double *__restrict__ pose7) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (d_n) n = min(n, *d_n);
@@ -651,29 +827,23 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
   c->d_extract_status = status;
   float4 *lf = reinterpret_cast<float4 *>(p + o_lf);
   int *tmp = reinterpret_cast<int *>(p + o_tmp);
-  VoxelWork vw;
-  int rc = voxel_work_reserve(c, c->scratch[5], n, n_scans, &vw);
-  if (rc) return rc;
   MLOAM_CUDA_OK(c, cudaMemsetAsync(out.counts, 0, 4 * sizeof(int), st));
   MLOAM_CUDA_OK(c, cudaMemsetAsync(status, 0, sizeof(int), st));
-  MLOAM_CUDA_OK(c, cudaMemsetAsync(seg_begin, 0, 130 * sizeof(int), st));
   if (n == 0) return MLOAM_OK;
   const int nb = (n + 255) / 256;
   k_curvature<<<(n + CURV_THREADS - 1) / CURV_THREADS, CURV_THREADS, 0, st>>>(d_cloud, n, curv, gap, label);
-  k_ring_of_init<<<nb, 256, 0, st>>>(ring_of, n);
   k_ring_pick<<<n_scans, RING_THREADS, 0, st>>>(curv, gap, n, d_scan_start, d_scan_end, label, ring_of, stage, status);
   k_emit_picks<<<n_scans, 128, 0, st>>>(d_cloud, stage, n_scans, out.sharp, out.less_sharp, out.flat, out.counts);
-  k_less_flat_flags<<<nb, 256, 0, st>>>(ring_of, label, n, flag);
+  // :258-271 less-flat candidates + per-ring pcl::VoxelGrid(0.2): one CTA per ring, then the ring-order concatenation
+  static bool smem_opt_in = false;
+  if (!smem_opt_in) {
+    MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_ring_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, RV_MAX_P2 * (int)sizeof(unsigned long long)));
+    smem_opt_in = true;
+  }
+  k_ring_voxel<<<n_scans, RV_THREADS, RV_MAX_P2 * sizeof(unsigned long long), st>>>(d_cloud, label, n, d_scan_start, d_scan_end, 1.0f / 0.2f, lf,
+                                                                                    seg_begin);
+  k_ring_voxel_emit<<<n_scans, 128, 0, st>>>(lf, seg_begin, d_scan_start, n_scans, out.less_flat, out.counts + 3);
   c->launches += 5;
-  scan_exclusive(c, flag, pos, n, tmp, out.counts + 3 /* provisional: points entering the per-ring voxel grid */);
-  k_less_flat_gather<<<nb, 256, 0, st>>>(d_cloud, ring_of, flag, pos, d_scan_start, n, lf, seg, seg_begin);
-  c->launches++;
-  // :266-271 per-ring pcl::VoxelGrid(0.2) == one segmented voxel pipeline over all rings.  The number of
-  // less-flat candidates is only known on the device: the pipeline runs over the upper bound n with the
-  // device-side count gating the tail, so no host round trip is needed.
-  MLOAM_CUDA_OK(c, cudaMemcpyAsync(n_lf, out.counts + 3, sizeof(int), cudaMemcpyDeviceToDevice, st));
-  rc = voxel_pipeline(c, lf, seg, seg_begin, n, n_lf, n_scans, 0.2f, 0, vw, out.less_flat, out.counts + 3);
-  if (rc) return rc;
   if (d_curv_or_null) MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_curv_or_null, curv, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   if (d_label_or_null) MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_label_or_null, label, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
   MLOAM_CUDA_OK(c, cudaGetLastError());
