@@ -74,8 +74,14 @@ static void scan_exclusive(Ctx *c, const int *d_in, int *d_out, int n, int *d_tm
 
 // Stable LSD radix sort, 8-bit digits.  Tile layout: warp w of the block owns keys
 // [blk*TILE + w*256, +256), visited in 8 rounds of 32 consecutive keys -> input order is preserved per digit.
-__global__ void k_rs_hist(const unsigned long long *__restrict__ keys, int n, int shift, int *__restrict__ hist, int nblk) {
+// hist[d * nblk + b] = keys of block b with digit d.  The block that finishes last turns the table into the exclusive
+// prefix the scatter needs (digit-major, block-minor) — the three scan launches of a pass folded into this one.
+// d_n_valid (nullable): device-side key count; blocks beyond it contribute nothing.
+__global__ void k_rs_hist(const unsigned long long *__restrict__ keys, int n, const int *__restrict__ d_n_valid, int shift,
+                          int *__restrict__ hist, int nblk, unsigned *__restrict__ ticket) {
   __shared__ int h[256];
+  __shared__ bool is_last;
+  if (d_n_valid) n = min(n, *d_n_valid);
   h[threadIdx.x] = 0;
   __syncthreads();
   const int base = blockIdx.x * PRIM_TILE;
@@ -86,12 +92,30 @@ __global__ void k_rs_hist(const unsigned long long *__restrict__ keys, int n, in
   }
   __syncthreads();
   hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  int *row = hist + threadIdx.x * nblk;  // thread d owns digit d
+  int sum = 0;
+  for (int b = 0; b < nblk; b++) sum += __ldcg(row + b);
+  int run = prim_block_scan(sum, nullptr);
+  for (int b = 0; b < nblk; b++) {
+    const int t = __ldcg(row + b);
+    row[b] = run;
+    run += t;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
 }
-__global__ void k_rs_scatter(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, int n, int shift,
-                             const int *__restrict__ offs, int nblk, unsigned long long *__restrict__ keys_out,
-                             unsigned *__restrict__ vals_out) {
+__global__ void k_rs_scatter(const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals, int n,
+                             const int *__restrict__ d_n_valid, int shift, const int *__restrict__ offs, int nblk,
+                             unsigned long long *__restrict__ keys_out, unsigned *__restrict__ vals_out) {
   __shared__ int cnt[PRIM_THREADS / 32][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (d_n_valid) n = min(n, *d_n_valid);
+  if (blockIdx.x * PRIM_TILE >= n) return;
   for (int k = threadIdx.x; k < (PRIM_THREADS / 32) * 256; k += PRIM_THREADS) (&cnt[0][0])[k] = 0;
   __syncthreads();
   const int wbase = blockIdx.x * PRIM_TILE + w * (PRIM_ITEMS * 32);
@@ -143,20 +167,20 @@ struct SortBufs {
   unsigned *v0, *v1;
   int *hist;  // 256 * nblk
   int *tmp;   // scan tiles
+  unsigned *ticket;  // zero before the first pass (k_seg_init), self-resetting
 };
-// Sorts (k0,v0) by the low `nbits` of the key; returns which buffer holds the result (0 or 1).
-static int radix_sort(Ctx *c, SortBufs b, int n, int nbits) {
+// Sorts the first min(n, *d_n_valid) entries of (k0,v0) by the low `nbits` of the key; returns which buffer holds the
+// result (0 or 1).  Two launches per 8-bit pass.
+static int radix_sort(Ctx *c, SortBufs b, int n, const int *d_n_valid, int nbits) {
   if (n <= 0) return 0;
   const int nblk = (n + PRIM_TILE - 1) / PRIM_TILE;
   int cur = 0;
   for (int shift = 0; shift < nbits; shift += 8) {
     unsigned long long *ki = cur ? b.k1 : b.k0, *ko = cur ? b.k0 : b.k1;
     unsigned *vi = cur ? b.v1 : b.v0, *vo = cur ? b.v0 : b.v1;
-    k_rs_hist<<<nblk, PRIM_THREADS, 0, c->stream>>>(ki, n, shift, b.hist, nblk);
-    c->launches++;
-    scan_exclusive(c, b.hist, b.hist, 256 * nblk, b.tmp, nullptr);
-    k_rs_scatter<<<nblk, PRIM_THREADS, 0, c->stream>>>(ki, vi, n, shift, b.hist, nblk, ko, vo);
-    c->launches++;
+    k_rs_hist<<<nblk, PRIM_THREADS, 0, c->stream>>>(ki, n, d_n_valid, shift, b.hist, nblk, b.ticket);
+    k_rs_scatter<<<nblk, PRIM_THREADS, 0, c->stream>>>(ki, vi, n, d_n_valid, shift, b.hist, nblk, ko, vo);
+    c->launches += 2;
     cur ^= 1;
   }
   return cur;
@@ -175,8 +199,9 @@ struct SegBox {           // per segment
   unsigned mn[3], mx[3];  // ordered-uint encodings of min / max
 };
 
-__global__ void k_seg_init(SegBox *box, int n_seg) {
+__global__ void k_seg_init(SegBox *box, int n_seg, unsigned *ticket) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *ticket = 0u;
   if (i < n_seg) {
     for (int d = 0; d < 3; d++) box[i].mn[d] = 0xffffffffu, box[i].mx[d] = 0u;
   }
@@ -252,9 +277,13 @@ __global__ void k_voxel_keys(const float4 *__restrict__ pts, const int *__restri
   keys[i] = ((unsigned long long)(unsigned)s << 32) | idx;
 }
 
-__global__ void k_run_heads(const unsigned long long *__restrict__ keys, int n, int *__restrict__ head) {
+__global__ void k_run_heads(const unsigned long long *__restrict__ keys, int n, const int *__restrict__ d_n_valid, int *__restrict__ head) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (d_n_valid && i >= *d_n_valid) {  // beyond the device-side count: never sorted, never a run
+    head[i] = 0;
+    return;
+  }
   const unsigned long long k = keys[i];
   head[i] = (k != 0xffffffffffffffffull && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
 }
@@ -264,8 +293,9 @@ __global__ void k_run_heads(const unsigned long long *__restrict__ keys, int n, 
 // (voxel_grid_covariance_mloam_impl.hpp:417-428); otherwise pcl::VoxelGrid averages every field.
 __global__ void k_centroids(const float4 *__restrict__ pts, const unsigned long long *__restrict__ keys,
                             const unsigned *__restrict__ vals, const int *__restrict__ head, const int *__restrict__ slot, int n,
-                            int intensity_last, float4 *__restrict__ out) {
+                            const int *__restrict__ d_n_valid, int intensity_last, float4 *__restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_n_valid) n = min(n, *d_n_valid);
   if (i >= n || !head[i]) return;
   const unsigned long long k = keys[i];
   float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f, last = 0.f;
@@ -285,6 +315,7 @@ struct VoxelWork {
   unsigned long long *k0, *k1;
   unsigned *v0, *v1;
   int *hist, *tmp, *head, *slot;
+  unsigned *ticket;
 };
 static int voxel_pipeline(Ctx *c, const float4 *d_pts, const int *d_seg, const int *d_seg_begin, int n, const int *d_n_valid,
                           int n_seg, float leaf, int intensity_last, VoxelWork w, float4 *d_out, int *d_n_out) {
@@ -295,22 +326,22 @@ static int voxel_pipeline(Ctx *c, const float4 *d_pts, const int *d_seg, const i
   }
   const float inv = 1.0f / leaf;
   const int nb = (n + 255) / 256;
-  k_seg_init<<<(n_seg + 127) / 128, 128, 0, st>>>(w.box, n_seg);
+  k_seg_init<<<(n_seg + 127) / 128, 128, 0, st>>>(w.box, n_seg, w.ticket);
   k_seg_bbox<<<nb, 256, 0, st>>>(d_pts, d_seg, n, d_n_valid, w.box);
   k_voxel_keys<<<nb, 256, 0, st>>>(d_pts, d_seg, d_seg_begin, n, d_n_valid, inv, w.box, w.k0, w.v0);
   c->launches += 3;
   int seg_bits = 0;
   while ((1 << seg_bits) < n_seg) seg_bits++;
-  SortBufs sb{w.k0, w.k1, w.v0, w.v1, w.hist, w.tmp};
+  SortBufs sb{w.k0, w.k1, w.v0, w.v1, w.hist, w.tmp, w.ticket};
   // all-ones keys (non-finite points) must sort last: include the full 64 bits only when a segment id is present
   const int nbits = n_seg > 1 ? 32 + ((seg_bits + 7) / 8) * 8 : 32;
-  const int cur = radix_sort(c, sb, n, nbits);
+  const int cur = radix_sort(c, sb, n, d_n_valid, nbits);
   const unsigned long long *ks = cur ? w.k1 : w.k0;
   const unsigned *vs = cur ? w.v1 : w.v0;
-  k_run_heads<<<nb, 256, 0, st>>>(ks, n, w.head);
+  k_run_heads<<<nb, 256, 0, st>>>(ks, n, d_n_valid, w.head);
   c->launches++;
   scan_exclusive(c, w.head, w.slot, n, w.tmp, d_n_out);
-  k_centroids<<<nb, 256, 0, st>>>(d_pts, ks, vs, w.head, w.slot, n, intensity_last, d_out);
+  k_centroids<<<nb, 256, 0, st>>>(d_pts, ks, vs, w.head, w.slot, n, d_n_valid, intensity_last, d_out);
   c->launches++;
   return MLOAM_OK;
 }
@@ -330,6 +361,7 @@ static int voxel_work_reserve(Ctx *c, DevBuf &buf, int n, int n_seg, VoxelWork *
   const size_t o_v0 = take(4 * (size_t)(n + 1)), o_v1 = take(4 * (size_t)(n + 1));
   const size_t o_hist = take(4 * (size_t)n_hist), o_tmp = take(4 * (size_t)n_tmp);
   const size_t o_head = take(4 * (size_t)(n + 1)), o_slot = take(4 * (size_t)(n + 1));
+  const size_t o_ticket = take(16);
   MLOAM_CUDA_OK(c, buf.reserve(off));
   char *p = buf.as<char>();
   w->box = reinterpret_cast<SegBox *>(p + o_box);
@@ -337,8 +369,15 @@ static int voxel_work_reserve(Ctx *c, DevBuf &buf, int n, int n_seg, VoxelWork *
   w->v0 = reinterpret_cast<unsigned *>(p + o_v0), w->v1 = reinterpret_cast<unsigned *>(p + o_v1);
   w->hist = reinterpret_cast<int *>(p + o_hist), w->tmp = reinterpret_cast<int *>(p + o_tmp);
   w->head = reinterpret_cast<int *>(p + o_head), w->slot = reinterpret_cast<int *>(p + o_slot);
+  w->ticket = reinterpret_cast<unsigned *>(p + o_ticket);
   return MLOAM_OK;
 }
+
+// in-CTA voxel filter (defined with the per-ring filter below)
+constexpr int RV_THREADS = 512;
+constexpr int RV_MAX_P2 = 16384;  // >= RING_MAX (defined below)
+__global__ void k_voxel_small(const float4 *__restrict__ P, int n, const int *__restrict__ d_n_valid, float inv, int intensity_last,
+                              float4 *__restrict__ out, int *__restrict__ n_out);
 
 int voxel_downsample_device(Ctx *c, const float4 *d_in, int n, const int *d_n_in, float leaf, int intensity_last, float4 *d_out,
                             int *d_n_out, int work_slot) {
@@ -347,6 +386,17 @@ int voxel_downsample_device(Ctx *c, const float4 *d_in, int n, const int *d_n_in
     return MLOAM_E_INVALID;
   }
   ProfScope ps(c, "voxel");
+  if (n > 0 && n <= RV_MAX_P2) {
+    static bool opt_in = false;
+    if (!opt_in) {
+      MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_voxel_small, cudaFuncAttributeMaxDynamicSharedMemorySize, RV_MAX_P2 * (int)sizeof(unsigned long long)));
+      opt_in = true;
+    }
+    k_voxel_small<<<1, RV_THREADS, RV_MAX_P2 * sizeof(unsigned long long), c->stream>>>(d_in, n, d_n_in, 1.0f / leaf, intensity_last, d_out, d_n_out);
+    c->launches++;
+    MLOAM_CUDA_OK(c, cudaGetLastError());
+    return MLOAM_OK;
+  }
   VoxelWork w;
   int rc = voxel_work_reserve(c, c->scratch[work_slot], n, 1, &w);
   if (rc) return rc;
@@ -608,8 +658,6 @@ __global__ void k_less_flat_gather(const float4 *__restrict__ P, const int *__re
 // offset in the low bits makes the order inside a voxel the input order, i.e. what a stable sort gives), run heads,
 // ordered float centroid sums — and stage the centroids at the ring's own window of `stage_out`.  Replaces the
 // flag / scan / gather kernels and a 5-pass segmented radix sort (about 40 launches) for the per-ring filter.
-constexpr int RV_THREADS = 512;
-constexpr int RV_MAX_P2 = 16384;  // >= RING_MAX
 
 __device__ __forceinline__ int block_excl_scan_512(int v, int *warp_tot /* smem[17] */, int *total) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -639,20 +687,13 @@ __device__ __forceinline__ int block_excl_scan_512(int v, int *warp_tot /* smem[
   return r;
 }
 
-__global__ void __launch_bounds__(RV_THREADS)
-    k_ring_voxel(const float4 *__restrict__ P, const int *__restrict__ label, int n, const int *__restrict__ scan_start,
-                 const int *__restrict__ scan_end, float inv, float4 *__restrict__ stage_out, int *__restrict__ ring_cnt) {
+// Voxel-grid filter of the points P[s, s + len) whose label is <= 0 (all of them when label == nullptr), by one CTA of
+// RV_THREADS threads; len <= RV_MAX_P2.  Centroids go to out[0..), their number to *out_cnt.
+__device__ void voxel_in_cta(const float4 *__restrict__ P, const int *__restrict__ label, int s, int len, float inv, int intensity_last,
+                             float4 *__restrict__ out, int *__restrict__ out_cnt) {
   extern __shared__ unsigned long long rv_keys[];  // RV_MAX_P2
   __shared__ int warp_tot[17];
   __shared__ unsigned bb[6];  // ordered-uint min xyz, max xyz
-  const int ring = blockIdx.x;
-  const int s = scan_start[ring], e = scan_end[ring];
-  const int len = e - s;
-  // the rings k_ring_pick processes (:155 and the on-chip window check)
-  if (len < 6 || len + 10 > RING_MAX || s - 5 < 0 || e + 5 > n) {
-    if (threadIdx.x == 0) ring_cnt[ring] = 0;
-    return;
-  }
   if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu, bb[3 + threadIdx.x] = 0u;
   __syncthreads();
   // pass 1: bounding box of the finite less-flat points (getMinMax3D) + their number
@@ -661,7 +702,7 @@ __global__ void __launch_bounds__(RV_THREADS)
     unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
     int cnt = 0;
     for (int t = threadIdx.x; t < len; t += RV_THREADS) {
-      if (label[s + t] > 0) continue;
+      if (label && label[s + t] > 0) continue;
       cnt++;
       const float4 p = P[s + t];
       if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
@@ -682,7 +723,7 @@ __global__ void __launch_bounds__(RV_THREADS)
     (void)dummy;
   }
   if (nq == 0) {
-    if (threadIdx.x == 0) ring_cnt[ring] = 0;
+    if (threadIdx.x == 0) *out_cnt = 0;
     return;
   }
   const float mn0 = ord2f(bb[0]), mn1 = ord2f(bb[1]), mn2 = ord2f(bb[2]);
@@ -697,7 +738,7 @@ __global__ void __launch_bounds__(RV_THREADS)
   int carry = 0;
   for (int base = 0; base < len; base += RV_THREADS) {
     const int t = base + threadIdx.x;
-    const bool f = t < len && label[s + t] <= 0;
+    const bool f = t < len && (!label || label[s + t] <= 0);
     int tile_total;
     const int q = carry + block_excl_scan_512(f ? 1 : 0, warp_tot, &tile_total);
     if (f) {
@@ -748,18 +789,46 @@ __global__ void __launch_bounds__(RV_THREADS)
     int tile_total;
     const int slot = carry + block_excl_scan_512(head ? 1 : 0, warp_tot, &tile_total);
     if (head) {
-      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f, last = 0.f;
       int j = k;
       for (; j < nq && (rv_keys[j] >> 14) == (key >> 14); j++) {
         const float4 p = P[s + (int)(rv_keys[j] & 0x3fffull)];
         sx = sx + p.x, sy = sy + p.y, sz = sz + p.z, si = si + p.w;
+        last = p.w;
       }
       const float cnt = (float)(j - k);
-      stage_out[s + slot] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+      out[slot] = make_float4(sx / cnt, sy / cnt, sz / cnt, intensity_last ? last : si / cnt);
     }
     carry += tile_total;
   }
-  if (threadIdx.x == 0) ring_cnt[ring] = carry;
+  if (threadIdx.x == 0) *out_cnt = carry;
+}
+
+__global__ void __launch_bounds__(RV_THREADS)
+    k_ring_voxel(const float4 *__restrict__ P, const int *__restrict__ label, int n, const int *__restrict__ scan_start,
+                 const int *__restrict__ scan_end, float inv, float4 *__restrict__ stage_out, int *__restrict__ ring_cnt) {
+  const int ring = blockIdx.x;
+  const int s = scan_start[ring], e = scan_end[ring];
+  const int len = e - s;
+  // the rings k_ring_pick processes (:155 and the on-chip window check)
+  if (len < 6 || len + 10 > RING_MAX || s - 5 < 0 || e + 5 > n) {
+    if (threadIdx.x == 0) ring_cnt[ring] = 0;
+    return;
+  }
+  voxel_in_cta(P, label, s, len, inv, 0, stage_out + s, ring_cnt + ring);
+}
+
+// Whole-cloud filter of a SMALL cloud (n <= RV_MAX_P2, e.g. the <= 120 x rings less-sharp corner candidates of a sweep):
+// the same in-CTA pipeline, one launch instead of ~28.
+__global__ void __launch_bounds__(RV_THREADS)
+    k_voxel_small(const float4 *__restrict__ P, int n, const int *__restrict__ d_n_valid, float inv, int intensity_last,
+                  float4 *__restrict__ out, int *__restrict__ n_out) {
+  if (d_n_valid) n = min(n, *d_n_valid);
+  if (n <= 0) {
+    if (threadIdx.x == 0) *n_out = 0;
+    return;
+  }
+  voxel_in_cta(P, nullptr, 0, n, inv, intensity_last, out, n_out);
 }
 
 // Concatenate the rings' staged centroids in ring order (the order of :271's `+=`).
