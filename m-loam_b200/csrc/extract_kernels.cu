@@ -74,8 +74,8 @@ static void scan_exclusive(Ctx *c, const int *d_in, int *d_out, int n, int *d_tm
 
 // Stable LSD radix sort, 8-bit digits.  Tile layout: warp w of the block owns keys
 // [blk*TILE + w*256, +256), visited in 8 rounds of 32 consecutive keys -> input order is preserved per digit.
-// hist[d * nblk + b] = keys of block b with digit d.  The block that finishes last turns the table into the exclusive
-// prefix the scatter needs (digit-major, block-minor) — the three scan launches of a pass folded into this one.
+// hist[b * 256 + d] = keys of block b with digit d.  The block that finishes last turns the table into the exclusive
+// prefix the scatter needs (digit-major, block-minor order) — the three scan launches of a pass folded into this one.
 // d_n_valid (nullable): device-side key count; blocks beyond it contribute nothing.
 __global__ void k_rs_hist(const unsigned long long *__restrict__ keys, int n, const int *__restrict__ d_n_valid, int shift,
                           int *__restrict__ hist, int nblk, unsigned *__restrict__ ticket) {
@@ -91,20 +91,22 @@ __global__ void k_rs_hist(const unsigned long long *__restrict__ keys, int n, co
     if (i < n) atomicAdd(&h[(int)((keys[i] >> shift) & 0xffull)], 1);
   }
   __syncthreads();
-  hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+  hist[blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  int *row = hist + threadIdx.x * nblk;  // thread d owns digit d
+  int *col = hist + threadIdx.x;  // thread d owns digit d: entries col[b * 256], coalesced across the block
   int sum = 0;
-  for (int b = 0; b < nblk; b++) sum += __ldcg(row + b);
+#pragma unroll 8
+  for (int b = 0; b < nblk; b++) sum += __ldcg(col + b * 256);
   int run = prim_block_scan(sum, nullptr);
+#pragma unroll 8
   for (int b = 0; b < nblk; b++) {
-    const int t = __ldcg(row + b);
-    row[b] = run;
+    const int t = __ldcg(col + b * 256);
+    col[b * 256] = run;
     run += t;
   }
   if (threadIdx.x == 0) *ticket = 0u;
@@ -155,7 +157,7 @@ __global__ void k_rs_scatter(const unsigned long long *__restrict__ keys, const 
     const int i = wbase + it * 32 + lane;
     if (i < n) {
       const int d = (int)((kk[it] >> shift) & 0xffull);
-      const int pos = offs[d * nblk + blockIdx.x] + cnt[w][d] + rank[it];
+      const int pos = offs[blockIdx.x * 256 + d] + cnt[w][d] + rank[it];
       keys_out[pos] = kk[it];
       vals_out[pos] = vals[i];
     }
