@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
   for (int s = 0; s < a.n_sets; s++) {
     const FeatSetDev fs = a.set[s];
     const int fn = fs.d_n ? min(fs.n, *fs.d_n) : fs.n;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fn; i += gridDim.x * blockDim.x) {
+    // Both sets keep their features at the low indices of a much larger launch bound: the second set is handed out from
+    // the last thread downwards, so that a thread evaluates one feature of either set instead of one of each.
+    const int G = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = (s & 1) ? G - 1 - gid : gid; i < fn; i += G) {
       if (!fs.valid[i]) continue;
       const float4 pf = __ldg(fs.pts + i);
       const D3 p{(double)pf.x, (double)pf.y, (double)pf.z};
@@ -120,18 +123,25 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
       else acc[NE_H + NE_G + 2] += 1.0;
     }
   }
-  // warp tree
-#pragma unroll
-  for (int k = 0; k < NE_PACK; k++) {
-    double v = acc[k];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(MLOAM_FULL_MASK, v, o);
-    acc[k] = v;
-  }
+  // Warp reduction of all 30 components at once (fixed butterfly, 31 exchanges instead of 30 x 5): at offset o a lane
+  // keeps the half of its remaining components selected by its bit o and adds the partner's partial sums of that
+  // half; after offsets 16..1 lane L holds the warp total of component L.
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) {
+  {
+    double v[32];
 #pragma unroll
-    for (int k = 0; k < NE_PACK; k++) sm[wid][k] = acc[k];
+    for (int k = 0; k < 32; k++) v[k] = k < NE_PACK ? acc[k] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const bool upper = (lane & o) != 0;
+#pragma unroll
+      for (int k = 0; k < o; k++) {
+        const double send = upper ? v[k] : v[k + o];
+        const double keep = upper ? v[k + o] : v[k];
+        v[k] = keep + __shfl_xor_sync(MLOAM_FULL_MASK, send, o);
+      }
+    }
+    if (lane < NE_PACK) sm[wid][lane] = v[0];
   }
   __syncthreads();
   if (threadIdx.x < NE_PACK) {
@@ -208,7 +218,10 @@ void eig_report_host(const double *H36, double *w6) {
   eig_sym6(H36, w6, V);
 }
 
-__device__ __forceinline__ bool chol6(double *A) {
+// In-place lower Cholesky factor of a 6x6; inv_diag[j] = 1 / L[j][j].  One square root and one division per column:
+// the off-diagonal entries are scaled by the reciprocal (double division is a ~100-cycle software sequence and this
+// runs on a single thread between two grid-wide kernels).
+__device__ __forceinline__ bool chol6(double *A, double *inv_diag) {
   constexpr int N = 6;
 #pragma unroll
   for (int j = 0; j < N; j++) {
@@ -218,18 +231,19 @@ __device__ __forceinline__ bool chol6(double *A) {
     if (!(d > 0.0)) return false;
     d = sqrt(d);
     A[j * N + j] = d;
-    const double inv_guard = d;
+    const double inv = 1.0 / d;
+    inv_diag[j] = inv;
 #pragma unroll
     for (int i = j + 1; i < N; i++) {
       double s = A[i * N + j];
 #pragma unroll
       for (int k = 0; k < j; k++) s -= A[i * N + k] * A[j * N + k];
-      A[i * N + j] = s / inv_guard;
+      A[i * N + j] = s * inv;
     }
   }
   return true;
 }
-__device__ __forceinline__ void chol6_solve(const double *L, const double *b, double *x) {
+__device__ __forceinline__ void chol6_solve(const double *L, const double *inv_diag, const double *b, double *x) {
   constexpr int N = 6;
   double y[6];
 #pragma unroll
@@ -237,14 +251,14 @@ __device__ __forceinline__ void chol6_solve(const double *L, const double *b, do
     double s = b[i];
 #pragma unroll
     for (int k = 0; k < i; k++) s -= L[i * N + k] * y[k];
-    y[i] = s / L[i * N + i];
+    y[i] = s * inv_diag[i];
   }
 #pragma unroll
   for (int i = N - 1; i >= 0; i--) {
     double s = y[i];
 #pragma unroll
     for (int k = i + 1; k < N; k++) s -= L[k * N + i] * x[k];
-    x[i] = s / L[i * N + i];
+    x[i] = s * inv_diag[i];
   }
 }
 
@@ -286,9 +300,10 @@ __device__ void lm_compute_step(LMState *st) {
       const double l = sqrt(st->diag[j] / st->radius);
       A[j * 6 + j] += l * l;
     }
-    bool ok = chol6(A);
+    double inv_diag[6];
+    bool ok = chol6(A, inv_diag);
     if (ok) {
-      chol6_solve(A, gs, step);
+      chol6_solve(A, inv_diag, gs, step);
 #pragma unroll
       for (int j = 0; j < 6; j++) {
         step[j] = -step[j];
@@ -373,7 +388,8 @@ __device__ void lm_advance(LMState *st, const double *ne, int mode, double eig_t
     if (need_eig && !want_eig) {
       double S[36];
       for (int i = 0; i < 36; i++) S[i] = H[i] - ((i % 7 == 0) ? eig_thre : 0.0);
-      if (chol6(S)) need_eig = false;
+      double inv_diag[6];
+      if (chol6(S, inv_diag)) need_eig = false;
     }
     if (need_eig) {
       double w[6], Vf[36], Vp[36];
