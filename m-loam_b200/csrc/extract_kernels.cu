@@ -450,9 +450,9 @@ __global__ void __launch_bounds__(CURV_THREADS)
   gap_ok[i] = g;
 }
 
-constexpr int RING_THREADS = 256;
-constexpr int RING_MAX = 12288;      // points per ring handled on chip (picked/gap bytes)
-constexpr int SECTOR_MAX = 2048;     // sort capacity per sector (RING_MAX / 6)
+constexpr int RING_THREADS = 512;
+constexpr int RING_MAX = 12288;      // points per ring handled on chip (sort keys, picked / gap bytes)
+constexpr int RING_SORT_MAX = 16384; // power of two >= RING_MAX: capacity of the in-CTA bitonic sort
 constexpr int PICK_SHARP = 12, PICK_LESS = 120, PICK_FLAT = 24;  // per ring: 6 sectors x (2, 20, 4)
 
 struct RingStage {  // per ring picks, indices into the cloud
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(RING_THREADS)
     k_ring_pick(const float *__restrict__ curv, const unsigned char *__restrict__ gap_ok_g, int n, const int *__restrict__ scan_start,
                 const int *__restrict__ scan_end, int *__restrict__ label, int *__restrict__ ring_of, RingStage *__restrict__ stage,
                 int *__restrict__ status) {
-  __shared__ unsigned long long keys[SECTOR_MAX];
+  extern __shared__ unsigned long long keys[];  // RING_SORT_MAX
   __shared__ unsigned char picked[RING_MAX + 16];
   __shared__ unsigned char gap[RING_MAX + 16];
   const int ring = blockIdx.x;
@@ -485,35 +485,43 @@ __global__ void __launch_bounds__(RING_THREADS)
     gap[t] = gap_ok_g[lo + t];
   }
   for (int k = s + threadIdx.x; k < e; k += RING_THREADS) ring_of[k] = ring;  // :258 range [sp_0, ep_5] = [s, e-1]
+  // :160-162 for all six sectors at once: ONE bitonic sort of (sector, curvature, offset in ring).  The sectors tile
+  // [s, e-1] in index order, so sector j's sorted run is keys[sp_j - s, ep_j - s]; ties in curvature go by index (the
+  // reference's std::sort leaves them unspecified).
+  const int len_ring = e - s;  // points s .. e-1; the last sector ends at e-1
+  int P2 = 1;
+  while (P2 < len_ring) P2 <<= 1;
+  for (int t = threadIdx.x; t < P2; t += RING_THREADS) {
+    unsigned long long key = 0xffffffffffffffffull;
+    if (t < len_ring) {
+      int j = 0;
+#pragma unroll
+      for (int q = 1; q < 6; q++)
+        if (s + t >= s + (e - s) * q / 6) j = q;
+      key = ((unsigned long long)j << 46) | ((unsigned long long)__float_as_uint(curv[s + t]) << 14) | (unsigned)t;
+    }
+    keys[t] = key;
+  }
   __syncthreads();
+  for (int k2 = 2; k2 <= P2; k2 <<= 1) {
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (int t = threadIdx.x; t < P2; t += RING_THREADS) {
+        const int ixj = t ^ j2;
+        if (ixj > t) {
+          const unsigned long long a = keys[t], b = keys[ixj];
+          const bool up = (t & k2) == 0;
+          if ((a > b) == up) keys[t] = b, keys[ixj] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
   int n_sharp = 0, n_less = 0, n_flat = 0;  // warp 0 keeps the running pick counts (uniform across its lanes)
   for (int j = 0; j < 6; j++) {
     const int sp = s + (e - s) * j / 6;            // :160
     const int ep = s + (e - s) * (j + 1) / 6 - 1;  // :161
     const int len = ep - sp + 1;
-    int P2 = 1;
-    while (P2 < len) P2 <<= 1;
-    if (P2 > SECTOR_MAX) {
-      if (threadIdx.x == 0) atomicExch(status, 1);
-      return;
-    }
-    // :162 sort ascending by curvature; ties by index (the reference's std::sort leaves ties unspecified)
-    for (int t = threadIdx.x; t < P2; t += RING_THREADS)
-      keys[t] = t < len ? (((unsigned long long)__float_as_uint(curv[sp + t]) << 32) | (unsigned)(sp + t)) : 0xffffffffffffffffull;
-    __syncthreads();
-    for (int k2 = 2; k2 <= P2; k2 <<= 1) {
-      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-        for (int t = threadIdx.x; t < P2; t += RING_THREADS) {
-          const int ixj = t ^ j2;
-          if (ixj > t) {
-            const unsigned long long a = keys[t], b = keys[ixj];
-            const bool up = (t & k2) == 0;
-            if ((a > b) == up) keys[t] = b, keys[ixj] = a;
-          }
-        }
-        __syncthreads();
-      }
-    }
+    const unsigned long long *skeys = keys + (sp - s);  // this sector's run, ascending curvature
     if (threadIdx.x < 32) {
       // The picks are inherently sequential (each one suppresses its +-5 neighbours), but finding the NEXT
       // unsuppressed candidate is not: warp 0 inspects 32 sorted candidates per step and ballots for the first
@@ -525,9 +533,9 @@ __global__ void __launch_bounds__(RING_THREADS)
       while (k >= 0) {
         const int idx = k - lane;
         const bool inb = idx >= 0;
-        const unsigned long long kk = inb ? keys[idx] : 0ull;
-        const float cv = __uint_as_float((unsigned)(kk >> 32));
-        const int ind = (int)(unsigned)(kk & 0xffffffffu);
+        const unsigned long long kk = inb ? skeys[idx] : 0ull;
+        const float cv = __uint_as_float((unsigned)(kk >> 14));
+        const int ind = s + (int)(unsigned)(kk & 0x3fffull);
         const bool pass = inb && ((double)cv > 0.1);  // sorted: once one fails, everything after it fails
         const unsigned m_fail = __ballot_sync(MLOAM_FULL_MASK, !pass);
         const unsigned before_fail = m_fail ? ((1u << (__ffs(m_fail) - 1)) - 1u) : 0xffffffffu;
@@ -572,9 +580,9 @@ __global__ void __launch_bounds__(RING_THREADS)
       while (k < len) {
         const int idx = k + lane;
         const bool inb = idx < len;
-        const unsigned long long kk = inb ? keys[idx] : 0ull;
-        const float cv = __uint_as_float((unsigned)(kk >> 32));
-        const int ind = (int)(unsigned)(kk & 0xffffffffu);
+        const unsigned long long kk = inb ? skeys[idx] : 0ull;
+        const float cv = __uint_as_float((unsigned)(kk >> 14));
+        const int ind = s + (int)(unsigned)(kk & 0x3fffull);
         const bool pass = inb && ((double)cv < 0.1);
         const unsigned m_fail = __ballot_sync(MLOAM_FULL_MASK, !pass);
         const unsigned before_fail = m_fail ? ((1u << (__ffs(m_fail) - 1)) - 1u) : 0xffffffffu;
@@ -905,7 +913,13 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
   if (n == 0) return MLOAM_OK;
   const int nb = (n + 255) / 256;
   k_curvature<<<(n + CURV_THREADS - 1) / CURV_THREADS, CURV_THREADS, 0, st>>>(d_cloud, n, curv, gap, label);
-  k_ring_pick<<<n_scans, RING_THREADS, 0, st>>>(curv, gap, n, d_scan_start, d_scan_end, label, ring_of, stage, status);
+  static bool pick_opt_in = false;
+  if (!pick_opt_in) {
+    MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_ring_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SORT_MAX * (int)sizeof(unsigned long long)));
+    pick_opt_in = true;
+  }
+  k_ring_pick<<<n_scans, RING_THREADS, RING_SORT_MAX * sizeof(unsigned long long), st>>>(curv, gap, n, d_scan_start, d_scan_end, label, ring_of, stage,
+                                                                                        status);
   k_emit_picks<<<n_scans, 128, 0, st>>>(d_cloud, stage, n_scans, out.sharp, out.less_sharp, out.flat, out.counts);
   // :258-271 less-flat candidates + per-ring pcl::VoxelGrid(0.2): one CTA per ring, then the ring-order concatenation
   static bool smem_opt_in = false;
