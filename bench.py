@@ -245,7 +245,13 @@ def main():
         print(json.dumps({"error": "no CUDA device: this framework has no CPU path"}))
         return 2
     torch.cuda.set_device(local_rank)
+    saved_stdout = None
     if world > 1:
+        # NCCL may print its version banner on stdout (NCCL_DEBUG=VERSION on some hosts): the contract is ONE JSON line,
+        # so C-level stdout points at stderr while the communicators are set up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     m = load_mloam()
     p = m.default_params()
@@ -255,6 +261,24 @@ def main():
         uid = [m.Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(world, rank, uid[0])
+        # peer-memory exchange inside the k_linearize tail when every GPU can map every other (NVLink / NVSwitch); the
+        # NCCL all-reduce path stays as the fallback (MLOAM_DISABLE_P2P=1 forces it)
+        can = all(torch.cuda.can_device_access_peer(local_rank, q) for q in range(world) if q != local_rank)
+        flag = torch.tensor([1 if (can and os.environ.get("MLOAM_DISABLE_P2P", "0") in ("", "0")) else 0], device=torch.device("cuda", local_rank))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.comm_p2p_export())
+            ctx.comm_p2p_init(world, rank, handles)
+            config["exchange"] = "peer-memory stores + flags inside the k_linearize tail (NVLink), sum in rank order"
+        else:
+            config["exchange"] = "ncclAllReduce of 30 doubles between the partial-sum and LM-step kernels"
+        dist.barrier()
+        torch.cuda.synchronize()
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     n_frames = 8
     surf_map, corner_map, frames, ext = make_workload(syn, n_gpus, rank, n_frames)

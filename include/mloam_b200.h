@@ -229,6 +229,13 @@ int mloam_odom_solve(mloam_ctx_t *ctx, int n, const unsigned char *h_types, cons
 int mloam_comm_unique_id(void *id128);
 int mloam_comm_init(mloam_ctx_t *ctx, int nranks, int rank, const void *id128);
 int mloam_comm_destroy(mloam_ctx_t *ctx);
+/* Peer-memory exchange: when every GPU of the node can map every other (NVLink / NVSwitch), the all-reduce, the
+ * partial-sum kernel before it and the LM-step kernel after it collapse into the tail of the residual kernel: each
+ * rank stores its 30 packed doubles into every rank's exchange buffer, raises a flag, polls its own buffer and sums
+ * the contributions in rank order.  export: create this rank's buffer, return its cudaIpcMemHandle_t (64 bytes);
+ * init: handles = nranks x 64 bytes gathered by the caller (rank order).  Falls back to NCCL when not initialised. */
+int mloam_comm_p2p_export(mloam_ctx_t *ctx, void *handle64);
+int mloam_comm_p2p_init(mloam_ctx_t *ctx, int nranks, int rank, const void *handles);
 
 #ifdef __cplusplus
 }

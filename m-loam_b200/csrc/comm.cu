@@ -86,9 +86,65 @@ int mloam_comm_init(mloam_ctx_t *h, int nranks, int rank, const void *id128) {
   return MLOAM_OK;
 }
 
+// ---- peer-memory exchange (replaces the NCCL all-reduce on the LM path when every GPU can map every other)
+int mloam_comm_p2p_export(mloam_ctx_t *h, void *handle64) {
+  if (!h || !handle64) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!c->p2p_local) {
+    MLOAM_CUDA_OK(c, cudaMalloc(&c->p2p_local, MLOAM_P2P_BYTES));
+    MLOAM_CUDA_OK(c, cudaMemset(c->p2p_local, 0, MLOAM_P2P_BYTES));
+    MLOAM_CUDA_OK(c, cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t hd;
+  MLOAM_CUDA_OK(c, cudaIpcGetMemHandle(&hd, c->p2p_local));
+  memcpy(handle64, &hd, sizeof(hd));
+  return MLOAM_OK;
+}
+
+int mloam_comm_p2p_init(mloam_ctx_t *h, int nranks, int rank, const void *handles) {
+  if (!h || !handles || nranks < 2 || nranks > MLOAM_P2P_MAX_RANKS || rank < 0 || rank >= nranks) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  if (!c->p2p_local) return fail(c, MLOAM_E_STATE, "comm_p2p_init: call mloam_comm_p2p_export first");
+  for (int q = 0; q < nranks; q++) {
+    if (q == rank) {
+      c->p2p_peer[q] = c->p2p_local;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, static_cast<const char *>(handles) + 64 * (size_t)q, sizeof(hd));
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (int k = 0; k < q; k++)
+        if (k != rank && c->p2p_peer[k]) cudaIpcCloseMemHandle(c->p2p_peer[k]), c->p2p_peer[k] = nullptr;
+      c->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+      return MLOAM_E_CUDA;
+    }
+    c->p2p_peer[q] = ptr;
+  }
+  c->nranks = nranks, c->rank = rank;
+  c->p2p_on = true;
+  return MLOAM_OK;
+}
+
 int mloam_comm_destroy(mloam_ctx_t *h) {
   if (!h) return MLOAM_E_INVALID;
   Ctx *c = &h->c;
+  if (c->p2p_local) {
+    cudaStreamSynchronize(c->stream);
+    for (int q = 0; q < MLOAM_P2P_MAX_RANKS; q++) {
+      if (c->p2p_peer[q] && c->p2p_peer[q] != c->p2p_local) cudaIpcCloseMemHandle(c->p2p_peer[q]);
+      c->p2p_peer[q] = nullptr;
+    }
+    cudaFree(c->p2p_local);
+    c->p2p_local = nullptr;
+    c->p2p_on = false;
+    if (!c->nccl_comm) c->nranks = 1, c->rank = 0;
+  }
   if (c->nccl_comm) {
     cudaStreamSynchronize(c->stream);
     nccl_api()->CommDestroy((ncclComm_t)c->nccl_comm);

@@ -145,6 +145,20 @@ __host__ __device__ inline unsigned hash_cell(unsigned long long k) {
   return h;
 }
 
+// ------------------------------------------------------------------ peer-memory exchange (multi-GPU)
+// Exchange buffer of one rank (cudaMalloc'ed, IPC-mapped into every peer):
+//   [0]      u64 epoch        number of exchanges this rank has completed (local use)
+//   [64]     u32 flags[2][8]  flags[parity][q] = epoch + 1 once rank q's contribution for that epoch has landed here
+//   [256]    f64 slots[2][8][32]  rank q's packed normal equations
+#define MLOAM_P2P_MAX_RANKS 8
+#define MLOAM_P2P_BYTES 8192
+struct P2PView {
+  double *slots[MLOAM_P2P_MAX_RANKS];     // per rank: its buffer's slots[2][8][32]
+  unsigned *flags[MLOAM_P2P_MAX_RANKS];   // per rank: its buffer's flags[2][8]
+  unsigned long long *epoch;              // local
+  int nranks, rank;
+};
+
 // ------------------------------------------------------------------ LM state (device resident)
 // Everything ceres::Solve keeps between iterations for one 6-dof (or 12-dof) block, plus the packed
 // normal equations the reduction writes.  NE_MAX covers 12x12 (78 upper + 12 + cost + rows).

@@ -147,6 +147,12 @@ struct Ctx {
   double ext[7] = {0, 0, 0, 0, 0, 0, 1};
   void *nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // peer-memory exchange of the packed normal equations (comm.cu, solve_kernels.cu lm_tail): every rank's exchange
+  // buffer is mapped into every other rank through CUDA IPC; p2p_on replaces the NCCL all-reduce + two extra launches
+  // by stores / polls over NVLink inside the k_linearize tail
+  void *p2p_local = nullptr;
+  void *p2p_peer[MLOAM_P2P_MAX_RANKS] = {nullptr};
+  bool p2p_on = false;
 };
 
 // RAII-less helper: bracket a kernel (or a few) with events when profiling is on.

@@ -232,7 +232,7 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
               const float4 *d_surf_map, int n_surf_map, const float4 *d_corner_map, int n_corner_map, int rebuild_maps,
               const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
   ScanRef S{};
-  const bool can_graph = c->use_graphs && c->params.max_inner == 1 && !c->prof_on && !c->nccl_comm;
+  const bool can_graph = c->use_graphs && c->params.max_inner == 1 && !c->prof_on && (!c->nccl_comm || c->p2p_on);
   if (can_graph) {
     unsigned long long key = 1469598103934665603ull;
     const void *ptrs[5] = {d_cloud, d_scan_start, d_scan_end, d_surf_map, d_corner_map};

@@ -41,9 +41,11 @@ struct LinArgs {
   double eig_thre;
   unsigned *ticket;        // zero between launches
   LMState *state_rw;
+  P2PView p2p;             // nranks > 1: sum the packed normal equations over the ranks through peer memory
 };
 
-__device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMState *gst, int mode, double eig_thre, int want_eig, double *out_ne);
+__device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMState *gst, int mode, double eig_thre, int want_eig, double *out_ne,
+                                     const P2PView *p2p);
 
 __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__restrict__ partials) {
   __shared__ double sm[LIN_THREADS / 32][NE_PACK];
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  lm_tail(partials, (int)gridDim.x, a.state_rw, a.lm_mode, a.eig_thre, a.want_eig, nullptr);
+  lm_tail(partials, (int)gridDim.x, a.state_rw, a.lm_mode, a.eig_thre, a.want_eig, nullptr, a.p2p.nranks > 1 ? &a.p2p : nullptr);
   if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
@@ -469,8 +471,18 @@ __device__ void lm_advance(LMState *st, const double *ne, int mode, double eig_t
 // (deterministic): warp w sums blocks w, w+8, ... for component `lane`, then the 8 warp sums are added in warp order.
 // The LM state lives in global memory between launches; it is staged through shared memory here because the
 // single-threaded state machine touches it a few hundred times (each a dependent L2 round trip otherwise).
-__device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMState *gst, int mode, double eig_thre, int want_eig, double *out_ne) {
+//
+// Multi-GPU (p2p != nullptr): one LiDAR per GPU, the LM step needs the SUM of every rank's normal equations.  The
+// reduction, the exchange and the step are one kernel: this block stores its 30 doubles into slot[rank] of every
+// rank's exchange buffer (peer stores over NVLink), raises its flag there, polls its own buffer until all ranks'
+// flags carry this exchange's epoch, and adds the slots in rank order — the same order on every rank, so all ranks
+// advance bit-identical states.  Slots and flags are double-buffered by the parity of the epoch: a rank can only be
+// one exchange ahead of the slowest one, so a slot is never overwritten before it has been read.
+__device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMState *gst, int mode, double eig_thre, int want_eig, double *out_ne,
+                                     const P2PView *p2p) {
   __shared__ double ne[NE_PACK];
+  __shared__ unsigned long long p2p_epoch;
+  __shared__ int p2p_timeout;
   __shared__ double wsum[LM_THREADS / 32][32];
   __shared__ LMState s;
   static_assert(sizeof(LMState) % 8 == 0, "LMState is staged as 8-byte words");
@@ -509,10 +521,43 @@ __device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMSta
   }
   __syncthreads();
   if (mode == 0) return;
+  if (p2p) {
+    const int N = p2p->nranks, me = p2p->rank;
+    if (threadIdx.x == 0) p2p_epoch = *p2p->epoch, p2p_timeout = 0;
+    __syncthreads();
+    const unsigned long long ep = p2p_epoch;
+    const int par = (int)(ep & 1ull);
+    const unsigned target = (unsigned)(ep + 1ull);
+    if (threadIdx.x < NE_PACK)
+      for (int q = 0; q < N; q++) reinterpret_cast<volatile double *>(p2p->slots[q])[(par * MLOAM_P2P_MAX_RANKS + me) * 32 + threadIdx.x] = ne[threadIdx.x];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < N) {
+      *reinterpret_cast<volatile unsigned *>(p2p->flags[threadIdx.x] + par * MLOAM_P2P_MAX_RANKS + me) = target;  // notify rank threadIdx.x
+      volatile unsigned *mine = reinterpret_cast<volatile unsigned *>(p2p->flags[me] + par * MLOAM_P2P_MAX_RANKS + threadIdx.x);
+      const long long w0 = clock64();
+      while ((int)(*mine - target) < 0) {
+        if (clock64() - w0 > 6000000000ll) {  // ~3 s: a peer never showed up
+          p2p_timeout = 1;
+          break;
+        }
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < NE_PACK) {
+      double t = 0.0;
+      for (int q = 0; q < N; q++) t += reinterpret_cast<volatile double *>(p2p->slots[me])[(par * MLOAM_P2P_MAX_RANKS + q) * 32 + threadIdx.x];
+      ne[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) *p2p->epoch = ep + 1ull;
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     s.work[0] = 0, s.work[1] = 0;  // re-arm the match work queues
     const long long t1 = clock64();
     lm_advance(&s, ne, mode, eig_thre, want_eig);
+    if (p2p && p2p_timeout) s.done = 1, s.termination = 9;  // exchange failed: the state is not trustworthy
     s.dbg_cycles[0] += t1 - t0, s.dbg_cycles[1] += clock64() - t1, s.dbg_cycles[2] += 1;
   }
   __syncthreads();
@@ -525,7 +570,7 @@ __device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMSta
 
 __global__ void __launch_bounds__(LM_THREADS) k_lm(const double *__restrict__ partials, int n_blocks, LMState *st, int mode, double eig_thre,
                                                   int want_eig, double *__restrict__ out_ne) {
-  lm_tail(partials, n_blocks, st, mode, eig_thre, want_eig, out_ne);
+  lm_tail(partials, n_blocks, st, mode, eig_thre, want_eig, out_ne, nullptr);
 }
 
 __global__ void k_lm_init(LMState *st, const double *pose7, int max_inner, int min_corr) {
@@ -591,7 +636,16 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
     c->ticket_zeroed_for = c->partials.p;
   }
   const double eig_thre = c->lm_eig_thre >= 0.0 ? c->lm_eig_thre : c->params.eig_thre;
-  const bool fused = lm_mode != 0 && !c->nccl_comm && !d_out30;
+  const bool fused = lm_mode != 0 && (!c->nccl_comm || c->p2p_on) && !d_out30;
+  memset(&a.p2p, 0, sizeof(a.p2p));
+  if (fused && c->p2p_on) {
+    for (int q = 0; q < c->nranks; q++) {
+      char *base = static_cast<char *>(c->p2p_peer[q]);
+      a.p2p.flags[q] = reinterpret_cast<unsigned *>(base + 64), a.p2p.slots[q] = reinterpret_cast<double *>(base + 256);
+    }
+    a.p2p.epoch = reinterpret_cast<unsigned long long *>(c->p2p_local);
+    a.p2p.nranks = c->nranks, a.p2p.rank = c->rank;
+  }
   a.lm_mode = fused ? lm_mode : 0, a.want_eig = want_eig, a.eig_thre = eig_thre, a.ticket = ticket;
   a.state_rw = c->lm_state.as<LMState>();
   {

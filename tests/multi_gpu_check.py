@@ -33,6 +33,11 @@ def main():
     uid = [m.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init(world, rank, uid[0])
+    mode = os.environ.get("MLOAM_EXCHANGE", "p2p")
+    if mode == "p2p":  # peer-memory exchange inside the k_linearize tail; MLOAM_EXCHANGE=nccl checks the all-reduce path
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.comm_p2p_export())
+        ctx.comm_p2p_init(world, rank, handles)
 
     scene = syn.make_scene()
     truth = syn.trajectory(3)[2]
@@ -65,7 +70,7 @@ def main():
         o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = 5, 1
         ref, rst = orc.scan2map(surf_map, corner_map, np.concatenate(sf_all), np.concatenate(cs_all), init, o)
         dt, dr = syn.pose_err(pose, ref)
-        print(f"multi-gpu x{world}: pose vs merged-feature oracle dt={dt:.3e} m dr={dr:.3e} rad; "
+        print(f"multi-gpu x{world} [{mode}]: pose vs merged-feature oracle dt={dt:.3e} m dr={dr:.3e} rad; "
               f"matches {st['n_surf']}+{st['n_corner']} (this rank's reduced count) vs oracle {int(rst['n_surf'])}+{int(rst['n_corner'])}")
         if not (dt <= 1e-4 and dr <= 1e-4):
             print("FAIL: pose parity")

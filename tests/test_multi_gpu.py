@@ -75,12 +75,14 @@ def test_bench_workload_is_rank_invariant_where_it_must_be():
 
 
 @pytest.mark.gpu
-def test_two_gpu_frame_parity():
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_frame_parity(exchange):
+    """Both exchanges of the packed normal equations: peer-memory stores inside the k_linearize tail, NCCL all-reduce."""
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (run tests/multi_gpu_check.py under torchrun with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+           "--master-port", "29533" if exchange == "p2p" else "29534", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MLOAM_EXCHANGE=exchange))
     assert out.returncode == 0 and "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
