@@ -444,7 +444,7 @@ def main():
             "ms_per_step": 1e3 * t_max / args.steps, "ms_per_step_stats": step_stats, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
             "data": "synthetic", "config": config, "ms_per_gn_iter": 1e3 * t_max / args.steps / GN_ITERS,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": int(launches), "cuda_graph_replay": os.environ.get("MLOAM_DISABLE_GRAPHS", "0") in ("", "0") and world == 1,
+            "gpu_launches": int(launches), "cuda_graph_replay": os.environ.get("MLOAM_DISABLE_GRAPHS", "0") in ("", "0") and (world == 1 or "peer-memory" in config.get("exchange", "")),
             "clocks": clocks, "roofline": roofline, "stage_ms_per_step": stage_ms, "knn_queries_per_step_by_path": knn_paths,
             "features_per_step": feats / args.steps}
     if cpu is not None:
