@@ -224,6 +224,18 @@ int mloam_odom_solve(mloam_ctx_t *ctx, int n, const unsigned char *h_types, cons
                      const double *pose_pivot7, double *pose_i7, double *ext7, int free_mask, int max_iterations,
                      double huber_a, double sqrt_info, mloam_solve_stats_t *stats);
 
+/* ---- ActiveFeatureSelection::goodFeatureMatching for one feature set (lidar_mapper.h:229-573; Estimator::goodFeatureMatching,
+ * estimator.cpp:1347-1517): match every feature of `h_pts` against map `slot` at pose7, evaluate its 1x6 Jacobian row
+ * (evaluateFeatJacobianMatching, lidar_mapper.h:130-174; sqrt_info from the point's covariance h_cov6[n*6] — PointIWithCov::cov_vec —
+ * or from params.cov_trace when null) and select gf_ratio * n features.
+ * method: 0 wo_gf (all matched), 1 rnd, 2 fps, 3 gd_fix / gd_float (stochastic greedy on log det(H + J^T J)).
+ * The reference's mt19937(random_device) becomes an explicit PCG32 `seed` and its wall-clock cap (MAX_FEATURE_SELECT_TIME)
+ * is dropped; MAX_RANDOM_QUEUE_TIME = 20 is kept.  Outputs: h_sel[<= n] feature indices in selection order, *n_sel,
+ * H36 = sub_mat_H (starts at 1e-6 I), optional h_matched[n] and h_jaco[n*6]. */
+int mloam_good_features(mloam_ctx_t *ctx, int slot, int type, const mloam_point_t *h_pts, int n, const float *h_cov6,
+                        const double *pose7, int method, double gf_ratio, unsigned long long seed, int *h_sel, int *n_sel,
+                        double *H36, unsigned char *h_matched, double *h_jaco);
+
 /* ---- multi-GPU: one LiDAR per GPU, one all-reduce of the packed normal equations per LM evaluation
  * (SURVEY.md §8e).  id128 is an ncclUniqueId (128 bytes) created on rank 0 and shared by the caller. */
 int mloam_comm_unique_id(void *id128);

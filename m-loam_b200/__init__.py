@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
-    "mloam_frame_device", "mloam_set_extrinsic", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init",
+    "mloam_frame_device", "mloam_set_extrinsic", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init",
 ]
 
 
@@ -349,6 +349,21 @@ class Context:
     def set_extrinsic(self, ext7=None):
         e = None if ext7 is None else np.ascontiguousarray(ext7, np.float64)
         self._ck(lib().mloam_set_extrinsic(self._h, _p(e)))
+
+    # ---- good-feature selection
+    def good_features(self, slot: int, kind: str, pts, pose7, method: int, gf_ratio: float, seed: int, cov6=None):
+        pts = _cloud(pts)
+        n = pts.shape[0]
+        pose = np.ascontiguousarray(pose7, np.float64)
+        cv = None if cov6 is None else np.ascontiguousarray(cov6, np.float32)
+        sel = np.zeros(max(n, 1), np.int32)
+        n_sel = C.c_int(0)
+        H = np.zeros((6, 6))
+        matched = np.zeros(max(n, 1), np.uint8)
+        jaco = np.zeros((max(n, 1), 6))
+        self._ck(lib().mloam_good_features(self._h, slot, ord(kind), _p(pts), n, _p(cv), _p(pose), int(method), C.c_double(gf_ratio),
+                                           C.c_ulonglong(seed), _p(sel), C.byref(n_sel), _p(H), _p(matched), _p(jaco)))
+        return {"sel": sel[: n_sel.value].copy(), "H": H, "matched": matched[:n].astype(bool), "jaco": jaco[:n]}
 
     # ---- multi-GPU
     @staticmethod

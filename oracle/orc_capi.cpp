@@ -3,6 +3,7 @@
 // through ctypes.  Clouds are float32 [n,4] (x,y,z,intensity); poses are double[7]
 // [tx ty tz qx qy qz qw].  Never linked into the product library.
 #include "orc_pipeline.hpp"
+#include "orc_gf.hpp"
 #include <cstdio>
 #ifdef _OPENMP
 #include <omp.h>
@@ -238,6 +239,39 @@ void orc_scan2map_ua(const float *surf_map, int n_sm, const float *corner_map, i
   Scan2MapResult r = scan2map(sm, cm, ss, cs, to_pose(pose_init7), o);
   pose_to_param(r.pose, pose_out7);
   if (stats) stats[0] = r.ran, stats[1] = r.n_surf, stats[2] = r.n_corner, stats[3] = r.lm_iterations, stats[4] = r.final_cost;
+}
+
+// ---- ActiveFeatureSelection::goodFeatureMatching for one feature set (lidar_mapper.h:229-573), explicit seed.
+// cov6 nullable (then default_trace).  Outputs: matched[n], jaco[n*6], sel[<= n] (selection order), *n_sel, H[36].
+void orc_good_features(int type, const float *map, int m, const float *scan, int n, const float *cov6, double default_trace,
+                       const double *pose7, int method, double gf_ratio, unsigned long long seed, int n_neigh, const double *opts,
+                       unsigned char *matched, double *jaco, int *sel, int *n_sel, double *H36) {
+  Cloud mc = to_cloud(map, m), sc = to_cloud(scan, n);
+  KdTree tree;
+  tree.setInputCloud(&mc);
+  std::vector<double> tr;
+  if (cov6) {
+    tr.resize(n);
+    for (int i = 0; i < n; i++) tr[i] = (double)cov6[i * 6] + (double)cov6[i * 6 + 3] + (double)cov6[i * 6 + 5];
+  }
+  std::vector<Feature> all;
+  std::vector<unsigned char> mt;
+  std::vector<double> jc;
+  std::vector<int> sl;
+  good_feature_matching((char)type, tree, mc, sc, to_pose(pose7), cov6 ? &tr : nullptr, default_trace, method, gf_ratio, seed, n_neigh,
+                        opts ? mp_from(opts) : MatchParams(), all, mt, jc, sl, H36);
+  for (int i = 0; i < n; i++) matched[i] = mt[i];
+  for (size_t i = 0; i < jc.size(); i++) jaco[i] = jc[i];
+  for (size_t i = 0; i < sl.size(); i++) sel[i] = sl[i];
+  *n_sel = (int)sl.size();
+}
+// selection only, on caller-provided matched / jaco (kernel-level parity of the selection loop)
+void orc_gf_select(int method, double gf_ratio, unsigned long long seed, int n, const unsigned char *matched, const double *jaco,
+                   const float *xyz4, int *sel, int *n_sel, double *H36) {
+  std::vector<int> sl;
+  good_feature_select(method, gf_ratio, seed, n, matched, jaco, xyz4, sl, H36);
+  for (size_t i = 0; i < sl.size(); i++) sel[i] = sl[i];
+  *n_sel = (int)sl.size();
 }
 
 // ---- the whole per-sweep hot path on the CPU: extractCloud -> downsampleCurrentScan -> scan2MapOptimization

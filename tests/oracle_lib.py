@@ -78,7 +78,7 @@ def default_opts() -> np.ndarray:
 
 
 def _p(a):
-    return a.ctypes.data_as(C.c_void_p)
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
 def knn(map_, q, k, brute=False):
@@ -314,3 +314,41 @@ def track_cloud(prev_less_sharp, prev_less_flat, cur_sharp, cur_flat, pose_ini, 
     lib().orc_track_cloud(_p(a), a.shape[0], _p(b), b.shape[0], _p(c), c.shape[0], _p(d), d.shape[0], _p(pose_ini), _p(opts),
                           _p(out), _p(stats))
     return out, {"n_corner": int(stats[0]), "n_surf": int(stats[1]), "lm_iterations": int(stats[2])}
+
+
+GF_WO, GF_RND, GF_FPS, GF_GD = 0, 1, 2, 3
+
+
+def good_features(kind, map_pts, scan, pose7, method, gf_ratio, seed, cov6=None, default_trace=0.0075, n_neigh=5, opts=None):
+    """ActiveFeatureSelection::goodFeatureMatching for one feature set (explicit seed).  Returns a dict with
+    matched (bool[n]), jaco (n,6), sel (int[], selection order), H (6,6)."""
+    import ctypes as C
+
+    mp, sc = cloud(map_pts), cloud(scan)
+    n = sc.shape[0]
+    pose7 = np.ascontiguousarray(pose7, np.float64)
+    cv = None if cov6 is None else np.ascontiguousarray(cov6, np.float32)
+    op = None if opts is None else np.ascontiguousarray(opts, np.float64)
+    matched = np.zeros(max(n, 1), np.uint8)
+    jaco = np.zeros((max(n, 1), 6))
+    sel = np.zeros(max(n, 1), np.int32)
+    n_sel = C.c_int(0)
+    H = np.zeros((6, 6))
+    lib().orc_good_features(ord(kind), _p(mp), mp.shape[0], _p(sc), n, _p(cv), C.c_double(default_trace), _p(pose7), int(method),
+                            C.c_double(gf_ratio), C.c_ulonglong(seed), int(n_neigh), _p(op), _p(matched), _p(jaco), _p(sel),
+                            C.byref(n_sel), _p(H))
+    return {"matched": matched[:n].astype(bool), "jaco": jaco[:n], "sel": sel[: n_sel.value].copy(), "H": H}
+
+
+def gf_select(method, gf_ratio, seed, matched, jaco, xyz4):
+    import ctypes as C
+
+    matched = np.ascontiguousarray(matched, np.uint8)
+    jaco = np.ascontiguousarray(jaco, np.float64)
+    xyz4 = cloud(xyz4)
+    n = matched.shape[0]
+    sel = np.zeros(max(n, 1), np.int32)
+    n_sel = C.c_int(0)
+    H = np.zeros((6, 6))
+    lib().orc_gf_select(int(method), C.c_double(gf_ratio), C.c_ulonglong(seed), n, _p(matched), _p(jaco), _p(xyz4), _p(sel), C.byref(n_sel), _p(H))
+    return sel[: n_sel.value].copy(), H

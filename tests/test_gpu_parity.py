@@ -531,3 +531,50 @@ def test_point_uncertainty_and_scan2map_ua(ctx, c1):
     assert st["n_surf"] == rst["n_surf"] and st["lm_iterations"] == rst["lm_iterations"]
     plain, _ = ctx.scan2map(c1["surf_scan"], c1["corner_scan"], c1["init"])
     assert not np.allclose(pose, plain, atol=1e-9)  # the weights matter
+
+
+# ------------------------------------------------------------------------------------------------ good-feature selection (a23)
+@pytest.mark.parametrize("kind", ["s", "c"])
+@pytest.mark.parametrize("method,ratio", [(orc.GF_WO, 1.0), (orc.GF_RND, 0.2), (orc.GF_FPS, 0.2), (orc.GF_GD, 0.2), (orc.GF_GD, 0.05),
+                                          (orc.GF_GD, 0.8)])
+def test_good_feature_selection_matches_oracle(ctx, c1, kind, method, ratio):
+    """goodFeatureMatching with the explicit seed: same matched set, Jacobian rows to 1e-9, and the SAME features in the SAME
+    selection order as the oracle restatement of the reference's loops (rnd / fps / stochastic greedy)."""
+    slot = 1 if kind == "s" else 0
+    ctx.map_build(1, c1["surf_map"], 0.5)
+    ctx.map_build(0, c1["corner_map"], 0.5)
+    scan = c1["surf_scan"] if kind == "s" else c1["corner_scan"]
+    mp = c1["surf_map"] if kind == "s" else c1["corner_map"]
+    for seed in (3, 12345):
+        out = ctx.good_features(slot, kind, scan, c1["init"], method, ratio, seed)
+        ref = orc.good_features(kind, mp, scan, c1["init"], method, ratio, seed)
+        assert np.array_equal(out["matched"], ref["matched"])
+        assert np.allclose(out["jaco"], ref["jaco"], rtol=1e-9, atol=1e-11)
+        assert np.array_equal(out["sel"], ref["sel"]), (method, ratio, seed, out["sel"][:10], ref["sel"][:10])
+        assert np.allclose(out["H"], ref["H"], rtol=1e-9, atol=1e-12)
+        assert len(set(out["sel"].tolist())) == len(out["sel"]) and out["matched"][out["sel"]].all()
+        if method != orc.GF_WO:
+            assert len(out["sel"]) <= int(scan.shape[0] * ratio)
+
+
+def test_good_feature_greedy_beats_random_and_handles_edges(ctx, c1):
+    ctx.map_build(1, c1["surf_map"], 0.5)
+    scan = c1["surf_scan"]
+    ld = {}
+    for name, m in (("rnd", orc.GF_RND), ("gd", orc.GF_GD)):
+        vals = []
+        for seed in range(4):
+            out = ctx.good_features(1, "s", scan, c1["init"], m, 0.1, seed)
+            vals.append(np.linalg.slogdet(out["H"])[1])
+        ld[name] = np.mean(vals)
+    assert ld["gd"] > ld["rnd"]  # the point of the method: more information from the same number of features
+    # ratio 0 -> nothing selected, H = 1e-6 I; empty scan
+    out = ctx.good_features(1, "s", scan, c1["init"], orc.GF_GD, 0.0, 1)
+    assert len(out["sel"]) == 0 and np.allclose(out["H"], 1e-6 * np.eye(6))
+    out = ctx.good_features(1, "s", np.zeros((0, 4), np.float32), c1["init"], orc.GF_FPS, 0.5, 1)
+    assert len(out["sel"]) == 0
+    # a scan with no map support at all: nothing matches, every method terminates with an empty selection
+    far = scan.copy()
+    far[:, :3] += 1000.0
+    for m in (orc.GF_RND, orc.GF_FPS, orc.GF_GD):
+        assert len(ctx.good_features(1, "s", far, c1["init"], m, 0.3, 5)["sel"]) == 0

@@ -309,3 +309,30 @@ def test_odom_solve_recovers_perturbed_blocks(free_mask):
     c_est = syn.pose_mul(syn.pose_mul(syn.pose_inv(xp), oi), oe)
     c_ini = syn.pose_mul(syn.pose_mul(syn.pose_inv(xp), xi0), xe0)
     assert syn.pose_err(c_est, c_true)[0] < 0.25 * syn.pose_err(c_ini, c_true)[0]
+
+
+def test_good_feature_selection_oracle_properties():
+    """orc_gf.hpp: selection sizes, determinism per seed, no duplicates, only matched features, greedy > random in log det."""
+    rng = np.random.default_rng(5)
+    n = 600
+    matched = rng.random(n) < 0.7
+    jaco = rng.normal(size=(n, 6)) * matched[:, None]
+    xyz = np.concatenate([rng.uniform(-20, 20, (n, 3)), np.zeros((n, 1))], 1).astype(np.float32)
+    sel_all, H_all = orc.gf_select(orc.GF_WO, 1.0, 1, matched, jaco, xyz)
+    assert np.array_equal(sel_all, np.flatnonzero(matched))
+    assert np.allclose(H_all, 1e-6 * np.eye(6) + jaco.T @ jaco)
+    ld = {}
+    for name, m in (("rnd", orc.GF_RND), ("fps", orc.GF_FPS), ("gd", orc.GF_GD)):
+        s1, H1 = orc.gf_select(m, 0.2, 42, matched, jaco, xyz)
+        s2, H2 = orc.gf_select(m, 0.2, 42, matched, jaco, xyz)
+        s3, _ = orc.gf_select(m, 0.2, 43, matched, jaco, xyz)
+        assert np.array_equal(s1, s2) and np.array_equal(H1, H2) and not np.array_equal(s1, s3)
+        assert len(s1) == int(n * 0.2) and len(set(s1.tolist())) == len(s1) and matched[s1].all()
+        ld[name] = np.linalg.slogdet(H1)[1]
+        if m != orc.GF_FPS:  # fps never adds its start point to H (reference quirk, lidar_mapper.h:375-379)
+            assert np.allclose(H1, 1e-6 * np.eye(6) + jaco[s1].T @ jaco[s1])
+    assert ld["gd"] > ld["rnd"]
+    # nothing matched: every method terminates empty
+    none = np.zeros(n, bool)
+    for m in (orc.GF_RND, orc.GF_FPS, orc.GF_GD):
+        assert len(orc.gf_select(m, 0.3, 1, none, np.zeros((n, 6)), xyz)[0]) == 0
