@@ -64,7 +64,10 @@ typedef struct {
   float map_cell;              /* voxel-hash cell edge [m] for the scan-to-map maps (<= 0: auto) */
   float corner_leaf;           /* MAP_CORNER_RES (scan down-sampling before matching) */
   float surf_leaf;             /* MAP_SURF_RES */
-  int reserved[8];
+  int gf_method;               /* FLAGS_gf_method in scan2MapOptimization (:474-532): 0 wo_gf, 1 rnd, 2 fps, 3 gd_fix */
+  float gf_ratio;              /* FLAGS_gf_ratio_ini */
+  unsigned gf_seed;            /* selection seed; outer iteration i, set s (0 corner, 1 surf) uses gf_seed + 2 i + s */
+  int reserved[5];
 } mloam_params_t;
 
 /* Per-solve report (what the reference prints through summary.BriefReport / timers). */

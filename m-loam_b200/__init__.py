@@ -39,7 +39,8 @@ class Params(C.Structure):
         ("min_match_sq_dis", C.c_float), ("min_plane_dis", C.c_float), ("n_neigh", C.c_int), ("check_fov", C.c_int),
         ("point_plane_factor", C.c_int), ("point_edge_factor", C.c_int), ("huber_a", C.c_double), ("eig_thre", C.c_double),
         ("cov_trace", C.c_double), ("max_outer", C.c_int), ("max_inner", C.c_int), ("map_cell", C.c_float),
-        ("corner_leaf", C.c_float), ("surf_leaf", C.c_float), ("reserved", C.c_int * 8),
+        ("corner_leaf", C.c_float), ("surf_leaf", C.c_float), ("gf_method", C.c_int), ("gf_ratio", C.c_float), ("gf_seed", C.c_uint),
+        ("reserved", C.c_int * 5),
     ]
 
 

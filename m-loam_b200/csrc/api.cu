@@ -72,6 +72,7 @@ void mloam_default_params(mloam_params_t *p) {
   p->map_cell = 0.0f;
   p->corner_leaf = 0.2f;             // MAP_CORNER_RES :136
   p->surf_leaf = 0.4f;               // MAP_SURF_RES :137
+  p->gf_method = 0, p->gf_ratio = 1.0f, p->gf_seed = 0;  // wo_gf
 }
 
 int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out) {
@@ -126,7 +127,7 @@ void mloam_ctx_destroy(mloam_ctx_t *h) {
   for (auto &m : c->maps) {
     m.sorted.release(), m.orig.release(), m.table.release(), m.block_mask.release(), m.slot_of.release(), m.rank_of.release(), m.scan_tmp.release();
   }
-  for (int i = 0; i < 2; i++) c->scan_pts[i].release(), c->feat_valid[i].release(), c->feat_coeff[i].release(), c->feat_nn[i].release(), c->knn_pos[i].release(), c->knn_changed[i].release(), c->knn_anchor[i].release(), c->knn_heavy[i].release();
+  for (int i = 0; i < 2; i++) c->scan_pts[i].release(), c->feat_valid[i].release(), c->feat_coeff[i].release(), c->feat_nn[i].release(), c->knn_pos[i].release(), c->knn_changed[i].release(), c->knn_anchor[i].release(), c->knn_heavy[i].release(), c->gf_work[i].release();
   c->partials.release(), c->lm_state.release();
   for (auto &s : c->scratch) s.release();
   if (c->pinned) cudaFreeHost(c->pinned);

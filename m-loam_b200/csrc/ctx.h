@@ -99,6 +99,7 @@ struct Ctx {
   DevBuf knn_pos[2];              // int[n_neigh] per query: neighbour positions handed from k_match_knn to k_match_fit
   DevBuf knn_changed[2];          // unsigned char per query: neighbour list differs from the previous iteration's
   DevBuf knn_anchor[2];           // float4 per query: position of its last real search + tolerated displacement
+  DevBuf gf_work[2];              // good-feature selection scratch per set (Jacobian rows, pool tree, mask, ...)
   DevBuf knn_heavy[2];            // 2 x unsigned char per query: "needed a real search" verdicts of the last two launches
   int knn_parity = 0;             // which half of knn_heavy the next seeded launch reads
   DevBuf partials;                // per-block packed normal equations
@@ -215,6 +216,7 @@ struct FeatSet {
   int is_plane;                // 1: LidarMapPlaneNormFactor, 0: LidarMapEdgeFactor
   const int *d_n;              // nullable device-side count
   const double *sinfo;         // nullable per-feature sqrt_info (with_ua: lidar_map_factor.hpp:34,41 on the point's covariance)
+  const unsigned char *mask;   // nullable: only features with mask[i] != 0 enter (good-feature selection)
 };
 // Accumulate loss-corrected normal equations of both feature sets at pose *d_pose7 (or LMState x / xc when
 // use_state != 0: 1 -> x, 2 -> xc) into c->partials, then run the LM state machine step (`lm_mode`):
@@ -228,6 +230,11 @@ int factor_evaluate_device(Ctx *c, int kind, int n, const double *d_points, cons
 
 // in place: p <- T * p for the first min(n, *d_n) points (pointAssociateToMap, utility.h:103-117); d_pose7 on device
 int transform_points_device(Ctx *c, float4 *d_pts, int n, const int *d_n, const double *d_pose7);
+
+// gf_kernels.cu: good-feature selection of one matched feature set on the device (goodFeatureMatching inside
+// scan2MapOptimization): Jacobian rows + selection, result as a 0/1 mask over the features (set index t: 0 corner, 1 surf)
+int gf_select_set_device(Ctx *c, int t, const FeatSet &fs, const double *d_pose7, double default_sinfo, int method, double gf_ratio,
+                         unsigned long long seed, unsigned char **d_mask_out);
 
 // uct_kernels.cu: per-point sqrt_info from PointIWithCov::cov_vec (float[6] per point)
 int sqrt_info_device(Ctx *c, const float *d_cov6, int n, double *d_sinfo);

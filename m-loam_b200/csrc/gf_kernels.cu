@@ -25,13 +25,14 @@ constexpr int GF_THREADS = 1024;
 constexpr int kGfMaxRandomQueue = 20;  // MAX_RANDOM_QUEUE_TIME, lidar_mapper.h:83
 
 __global__ void k_gf_jaco(const float4 *__restrict__ pts, const unsigned char *__restrict__ valid, const float *__restrict__ coeff, int n,
-                          int is_plane, const float *__restrict__ cov6, double default_sinfo, const double *__restrict__ pose7,
-                          double *__restrict__ jaco) {
+                          const int *__restrict__ d_n, int is_plane, const float *__restrict__ cov6, const double *__restrict__ sinfo,
+                          double default_sinfo, const double *__restrict__ pose7, double *__restrict__ jaco) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_n) n = min(n, *d_n);
   if (i >= n) return;
   double J[6] = {0, 0, 0, 0, 0, 0};
   if (valid[i]) {
-    double si = default_sinfo;
+    double si = sinfo ? sinfo[i] : default_sinfo;
     if (cov6) {  // extractCov -> trace -> sqrt(1/trace) with the clamp of lidar_map_factor.hpp:34,41
       const double tr = (double)cov6[(size_t)i * 6] + (double)cov6[(size_t)i * 6 + 3] + (double)cov6[(size_t)i * 6 + 5];
       const double s = sqrt(1 / tr);
@@ -110,9 +111,11 @@ struct GfArgs {
   double gf_ratio;
   unsigned long long seed;
   int n;
+  const int *d_n;  // nullable device-side feature count (n is then the upper bound the buffers are sized for)
   const unsigned char *matched;
   const double *jaco;
   const float4 *pts;
+  unsigned char *mask;  // nullable out: mask[i] = 1 for selected features, 0 otherwise (i < n)
   int *fen;      // n + 1
   int *visited;  // n   (gd: round stamp per pool element; fps: visited flag)
   float *dist;   // n   (fps)
@@ -128,7 +131,9 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
   __shared__ int red_j[GF_THREADS / 32];
   __shared__ int cand[32];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int n = a.n;
+  const int n = a.d_n ? min(a.n, *a.d_n) : a.n;
+  if (a.mask)
+    for (int i = tid; i < n; i += GF_THREADS) a.mask[i] = 0;
   const int num_use = (int)((size_t)((size_t)n * a.gf_ratio));  // static_cast<size_t>(num_all_features * gf_ratio), :248
   if (tid < 36) H[tid] = (tid % 7 == 0) ? 1e-6 : 0.0;              // sub_mat_H = I * 1e-6 (:504, :519)
   if (tid == 0) s_num_sel = 0, s_stop = 0, s_pick = -1;
@@ -287,6 +292,44 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
   __syncthreads();
   if (tid < 36) a.H[tid] = H[tid];
   if (tid == 0) *a.n_sel = s_num_sel;
+  if (a.mask)
+    for (int k = tid; k < s_num_sel; k += GF_THREADS) a.mask[a.sel[k]] = 1;
+}
+
+// Device-resident selection of one matched feature set (inside scan2MapOptimization): no host round trip.
+int gf_select_set_device(Ctx *c, int t, const FeatSet &fs, const double *d_pose7, double default_sinfo, int method, double gf_ratio,
+                         unsigned long long seed, unsigned char **d_mask_out) {
+  const int n = fs.n;
+  *d_mask_out = nullptr;
+  if (n <= 0) return MLOAM_OK;
+  DevBuf &B = c->gf_work[t];
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_j = take(sizeof(double) * 6 * (size_t)n), o_fen = take(4 * ((size_t)n + 1)), o_vis = take(4 * (size_t)n);
+  const size_t o_dist = take(4 * (size_t)n), o_sel = take(4 * (size_t)n), o_ns = take(16), o_H = take(36 * 8), o_mask = take((size_t)n + 16);
+  MLOAM_CUDA_OK(c, B.reserve(off));
+  char *p = B.as<char>();
+  double *d_jaco = reinterpret_cast<double *>(p + o_j);
+  k_gf_jaco<<<(n + 127) / 128, 128, 0, c->stream>>>(fs.pts, fs.valid, fs.coeff, n, fs.d_n, fs.is_plane ? 1 : 0, nullptr, fs.sinfo, default_sinfo,
+                                                   d_pose7, d_jaco);
+  GfArgs a;
+  a.method = method, a.gf_ratio = gf_ratio, a.seed = seed, a.n = n, a.d_n = fs.d_n;
+  a.matched = fs.valid, a.jaco = d_jaco, a.pts = fs.pts;
+  a.fen = reinterpret_cast<int *>(p + o_fen), a.visited = reinterpret_cast<int *>(p + o_vis), a.dist = reinterpret_cast<float *>(p + o_dist);
+  a.sel = reinterpret_cast<int *>(p + o_sel), a.n_sel = reinterpret_cast<int *>(p + o_ns), a.H = reinterpret_cast<double *>(p + o_H);
+  a.mask = reinterpret_cast<unsigned char *>(p + o_mask);
+  {
+    ProfScope ps(c, "gf_select");
+    k_gf_select<<<1, GF_THREADS, 0, c->stream>>>(a);
+  }
+  c->launches += 2;
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  *d_mask_out = a.mask;
+  return MLOAM_OK;
 }
 
 }  // namespace mloam
@@ -331,9 +374,9 @@ extern "C" int mloam_good_features(mloam_ctx_t *h, int slot, int type, const mlo
   float *d_cov = h_cov6 ? reinterpret_cast<float *>(p + o_cov) : nullptr;
   if (h_cov6) MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_cov, h_cov6, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   k_gf_jaco<<<(n + 127) / 128, 128, 0, c->stream>>>(c->scan_pts[t].as<float4>(), c->feat_valid[t].as<unsigned char>(), c->feat_coeff[t].as<float>(), n,
-                                                   type == 's' ? 1 : 0, d_cov, map_sqrt_info(c->params.cov_trace), d_pose, d_jaco);
+                                                   nullptr, type == 's' ? 1 : 0, d_cov, nullptr, map_sqrt_info(c->params.cov_trace), d_pose, d_jaco);
   GfArgs a;
-  a.method = method, a.gf_ratio = gf_ratio, a.seed = seed, a.n = n;
+  a.method = method, a.gf_ratio = gf_ratio, a.seed = seed, a.n = n, a.d_n = nullptr, a.mask = nullptr;
   a.matched = c->feat_valid[t].as<unsigned char>(), a.jaco = d_jaco, a.pts = c->scan_pts[t].as<float4>();
   a.fen = reinterpret_cast<int *>(p + o_fen), a.visited = reinterpret_cast<int *>(p + o_vis), a.dist = reinterpret_cast<float *>(p + o_dist);
   a.sel = reinterpret_cast<int *>(p + o_sel), a.n_sel = reinterpret_cast<int *>(p + o_ns), a.H = reinterpret_cast<double *>(p + o_H);

@@ -56,6 +56,19 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
       rc = match_pair_device(c, jobs, 2, d_pose, cfg, &st->work[0]);
       if (rc) return rc;
     }
+    // goodFeatureMatching (:503-532 with FLAGS_gf_method != wo_gf): select gf_ratio of the features per set, on the device;
+    // the solve below only sees the selected ones.  Corner first, then surf, as in the reference.
+    sets[0].mask = sets[1].mask = nullptr;
+    if (P.gf_method != 0) {
+      for (int t = 0; t < 2; t++) {
+        if (sets[t].n <= 0) continue;
+        unsigned char *mask = nullptr;
+        rc = gf_select_set_device(c, t, sets[t], d_pose, sinfo, P.gf_method, (double)P.gf_ratio,
+                                  (unsigned long long)P.gf_seed + 2ull * (unsigned long long)outer + (unsigned long long)t, &mask);
+        if (rc) return rc;
+        sets[t].mask = mask;
+      }
+    }
     // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve.  The device
     // only needs the degeneracy decision; scan2map_finish fills in the eigenvalue report of the last iteration.
     c->want_eig = 0;

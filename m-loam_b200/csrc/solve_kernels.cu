@@ -26,6 +26,7 @@ struct FeatSetDev {
   int is_plane;
   const int *d_n;
   const double *sinfo;
+  const unsigned char *mask;
 };
 struct LinArgs {
   FeatSetDev set[2];
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
     // the last thread downwards, so that a thread evaluates one feature of either set instead of one of each.
     const int G = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
     for (int i = (s & 1) ? G - 1 - gid : gid; i < fn; i += G) {
-      if (!fs.valid[i]) continue;
+      if (!fs.valid[i] || (fs.mask && !fs.mask[i])) continue;
       const float4 pf = __ldg(fs.pts + i);
       const D3 p{(double)pf.x, (double)pf.y, (double)pf.z};
       const float *cf = fs.coeff + (size_t)i * 6;
@@ -610,11 +611,11 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
     if (s < n_sets) {
       a.set[s].pts = sets[s].pts, a.set[s].valid = sets[s].valid, a.set[s].coeff = sets[s].coeff;
       a.set[s].n = sets[s].n, a.set[s].is_plane = sets[s].is_plane, a.set[s].d_n = sets[s].d_n;
-      a.set[s].sinfo = sets[s].sinfo;
+      a.set[s].sinfo = sets[s].sinfo, a.set[s].mask = sets[s].mask;
       n_total = sets[s].n > n_total ? sets[s].n : n_total;
     } else {
       a.set[s].pts = nullptr, a.set[s].valid = nullptr, a.set[s].coeff = nullptr, a.set[s].n = 0, a.set[s].is_plane = 0, a.set[s].d_n = nullptr;
-      a.set[s].sinfo = nullptr;
+      a.set[s].sinfo = nullptr, a.set[s].mask = nullptr;
     }
   }
   const int want_eig = c->want_eig;

@@ -21,7 +21,7 @@ static Pose to_pose(const double *x) { return Pose{Q4{x[3], x[4], x[5], x[6]}, V
 // opts layout shared by the pipeline calls
 enum {
   O_MAX_OUTER = 0, O_MAX_INNER, O_HUBER, O_EIG_THRE, O_N_NEIGH, O_CHECK_FOV, O_POINT_PLANE, O_POINT_EDGE,
-  O_COV_TRACE, O_DIST_SQ_THR, O_NEARBY_SCAN, O_MIN_MATCH_SQ, O_MIN_PLANE_DIS, O_COUNT
+  O_COV_TRACE, O_DIST_SQ_THR, O_NEARBY_SCAN, O_MIN_MATCH_SQ, O_MIN_PLANE_DIS, O_GF_METHOD, O_GF_RATIO, O_GF_SEED, O_COUNT
 };
 static MatchParams mp_from(const double *o) {
   MatchParams mp;
@@ -41,6 +41,7 @@ void orc_default_opts(double *o) {
   o[O_N_NEIGH] = d.n_neigh, o[O_CHECK_FOV] = d.check_fov, o[O_POINT_PLANE] = d.point_plane, o[O_POINT_EDGE] = d.point_edge;
   o[O_COV_TRACE] = d.cov_trace, o[O_DIST_SQ_THR] = d.mp.distance_sq_threshold, o[O_NEARBY_SCAN] = d.mp.nearby_scan;
   o[O_MIN_MATCH_SQ] = d.mp.min_match_sq_dis, o[O_MIN_PLANE_DIS] = d.mp.min_plane_dis;
+  o[O_GF_METHOD] = d.gf_method, o[O_GF_RATIO] = d.gf_ratio, o[O_GF_SEED] = (double)d.gf_seed;
 }
 
 // ---- small dense kernels (known-answer tests)
@@ -202,6 +203,7 @@ void orc_scan2map(const float *surf_map, int n_sm, const float *corner_map, int 
   o.eig_thre = opts[O_EIG_THRE], o.n_neigh = (int)opts[O_N_NEIGH], o.check_fov = opts[O_CHECK_FOV] != 0;
   o.point_plane = opts[O_POINT_PLANE] != 0, o.point_edge = opts[O_POINT_EDGE] != 0, o.cov_trace = opts[O_COV_TRACE];
   o.mp = mp_from(opts);
+  o.gf_method = (int)opts[O_GF_METHOD], o.gf_ratio = opts[O_GF_RATIO], o.gf_seed = (uint64_t)opts[O_GF_SEED];
   Cloud sm = to_cloud(surf_map, n_sm), cm = to_cloud(corner_map, n_cm), ss = to_cloud(surf_scan, n_ss),
         cs = to_cloud(corner_scan, n_cs);
   Scan2MapResult r = scan2map(sm, cm, ss, cs, to_pose(pose_init7), o);
@@ -231,6 +233,7 @@ void orc_scan2map_ua(const float *surf_map, int n_sm, const float *corner_map, i
   o.eig_thre = opts[O_EIG_THRE], o.n_neigh = (int)opts[O_N_NEIGH], o.check_fov = opts[O_CHECK_FOV] != 0;
   o.point_plane = opts[O_POINT_PLANE] != 0, o.point_edge = opts[O_POINT_EDGE] != 0, o.cov_trace = opts[O_COV_TRACE];
   o.mp = mp_from(opts);
+  o.gf_method = (int)opts[O_GF_METHOD], o.gf_ratio = opts[O_GF_RATIO], o.gf_seed = (uint64_t)opts[O_GF_SEED];
   std::vector<double> ts(n_ss), tc(n_cs);  // extractCov: float cov_vec -> Matrix3d; trace in double (point_with_cov.hpp:202-214)
   for (int i = 0; i < n_ss; i++) ts[i] = (double)surf_cov6[i * 6] + (double)surf_cov6[i * 6 + 3] + (double)surf_cov6[i * 6 + 5];
   for (int i = 0; i < n_cs; i++) tc[i] = (double)corner_cov6[i * 6] + (double)corner_cov6[i * 6 + 3] + (double)corner_cov6[i * 6 + 5];

@@ -4,6 +4,7 @@
 // (estimator/src/lidarTracker/lidar_tracker.cpp:23-129).
 #pragma once
 #include "orc_match.hpp"
+#include "orc_gf.hpp"
 #include "orc_solver.hpp"
 #include <chrono>
 
@@ -22,6 +23,11 @@ struct Scan2MapOptions {
   // with_ua=true (:541-545,556-560): per scan point covariance traces (extractCov of PointIWithCov); null = with_ua false
   const std::vector<double> *surf_cov_trace = nullptr, *corner_cov_trace = nullptr;
   MatchParams mp;
+  // FLAGS_gf_method / FLAGS_gf_ratio_ini (:474-492): 0 wo_gf, 1 rnd, 2 fps, 3 gd_fix; seed of iteration i, set s (0 corner,
+  // 1 surf) = gf_seed + 2 i + s (orc_gf.hpp makes the reference's random_device explicit)
+  int gf_method = 0;
+  double gf_ratio = 1.0;
+  uint64_t gf_seed = 0;
 };
 struct Scan2MapResult {
   Pose pose;
@@ -62,10 +68,28 @@ inline Scan2MapResult scan2map(const Cloud &surf_map, const Cloud &corner_map, c
     int pid = problem.add_param(para_pose);
     t0 = now_s();
     std::vector<Feature> corner_f, surf_f;
-    if (o.point_edge)  // :503-517, wo_gf branch lidar_mapper.h:257-299: every feature, in order
-      match_from_map('c', kd_corner, corner_map, corner_scan, pose_wmap_curr, corner_f, o.n_neigh, o.check_fov, o.mp);
-    if (o.point_plane)  // :518-532
-      match_from_map('s', kd_surf, surf_map, surf_scan, pose_wmap_curr, surf_f, o.n_neigh, o.check_fov, o.mp);
+    if (o.gf_method == 0) {
+      if (o.point_edge)  // :503-517, wo_gf branch lidar_mapper.h:257-299: every feature, in order
+        match_from_map('c', kd_corner, corner_map, corner_scan, pose_wmap_curr, corner_f, o.n_neigh, o.check_fov, o.mp);
+      if (o.point_plane)  // :518-532
+        match_from_map('s', kd_surf, surf_map, surf_scan, pose_wmap_curr, surf_f, o.n_neigh, o.check_fov, o.mp);
+    } else {  // :503-532 with a good-feature method: residual blocks of the SELECTED features, in selection order (:537,:552)
+      std::vector<Feature> all;
+      std::vector<unsigned char> mt;
+      std::vector<double> jc;
+      std::vector<int> sel;
+      double subH[36];
+      if (o.point_edge) {
+        good_feature_matching('c', kd_corner, corner_map, corner_scan, pose_wmap_curr, o.corner_cov_trace, o.cov_trace, o.gf_method,
+                              o.gf_ratio, o.gf_seed + 2 * (uint64_t)iter_cnt, o.n_neigh, o.mp, all, mt, jc, sel, subH);
+        for (int q : sel) corner_f.push_back(all[q]);
+      }
+      if (o.point_plane) {
+        good_feature_matching('s', kd_surf, surf_map, surf_scan, pose_wmap_curr, o.surf_cov_trace, o.cov_trace, o.gf_method,
+                              o.gf_ratio, o.gf_seed + 2 * (uint64_t)iter_cnt + 1, o.n_neigh, o.mp, all, mt, jc, sel, subH);
+        for (int q : sel) surf_f.push_back(all[q]);
+      }
+    }
     res.t_match += now_s() - t0;
     res.n_surf = (int)surf_f.size(), res.n_corner = (int)corner_f.size();
     for (const Feature &f : surf_f) {  // :537-549

@@ -16,7 +16,7 @@ ORC_DIR = os.path.join(ROOT, "oracle")
 
 F_PLANE, F_EDGE, F_EDGE_VEC, F_ODOM_PLANE, F_ODOM_EDGE = 0, 1, 2, 3, 4
 (O_MAX_OUTER, O_MAX_INNER, O_HUBER, O_EIG_THRE, O_N_NEIGH, O_CHECK_FOV, O_POINT_PLANE, O_POINT_EDGE, O_COV_TRACE,
- O_DIST_SQ_THR, O_NEARBY_SCAN, O_MIN_MATCH_SQ, O_MIN_PLANE_DIS) = range(13)
+ O_DIST_SQ_THR, O_NEARBY_SCAN, O_MIN_MATCH_SQ, O_MIN_PLANE_DIS, O_GF_METHOD, O_GF_RATIO, O_GF_SEED) = range(16)
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")

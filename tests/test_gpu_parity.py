@@ -578,3 +578,25 @@ def test_good_feature_greedy_beats_random_and_handles_edges(ctx, c1):
     far[:, :3] += 1000.0
     for m in (orc.GF_RND, orc.GF_FPS, orc.GF_GD):
         assert len(ctx.good_features(1, "s", far, c1["init"], m, 0.3, 5)["sel"]) == 0
+
+
+@pytest.mark.parametrize("method", [orc.GF_RND, orc.GF_FPS, orc.GF_GD])
+def test_scan2map_with_good_feature_selection(ctx, c1, method):
+    """scan2MapOptimization with FLAGS_gf_method != wo_gf (lidar_mapper_keyframe.cpp:474-560): every outer iteration selects
+    gf_ratio of the features per set on the device and solves on those.  Same selected counts and pose as the oracle."""
+    ctx.map_build(1, c1["surf_map"], 0.5)
+    ctx.map_build(0, c1["corner_map"], 0.5)
+    ctx.set_params(max_outer=3, max_inner=4, gf_method=method, gf_ratio=0.3, gf_seed=5)
+    try:
+        pose, st = ctx.scan2map(c1["surf_scan"], c1["corner_scan"], c1["init"])
+    finally:
+        ctx.set_params(max_outer=2, max_inner=30, gf_method=0, gf_ratio=1.0, gf_seed=0)
+    o = orc.default_opts()
+    o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = 3, 4
+    o[orc.O_GF_METHOD], o[orc.O_GF_RATIO], o[orc.O_GF_SEED] = method, 0.3, 5
+    ref, rst = orc.scan2map(c1["surf_map"], c1["corner_map"], c1["surf_scan"], c1["corner_scan"], c1["init"], o)
+    assert st["n_surf"] == int(rst["n_surf"]) and st["n_corner"] == int(rst["n_corner"])
+    assert 0 < st["n_surf"] <= int(0.3 * c1["surf_scan"].shape[0])
+    dt, dr = syn.pose_err(pose, ref)
+    assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+    assert syn.pose_err(pose, c1["truth"])[0] < syn.pose_err(c1["init"], c1["truth"])[0]
