@@ -434,6 +434,29 @@ class LidarTracker {
   FeatureExtract f_extract_;
 };
 
+// ----------------------------------------------------------------------------------------------- good features
+// ActiveFeatureSelection::goodFeatureMatching (lidar_mapper.h:229-573).  The kd-tree argument of the reference is the
+// map slot here (MLOAM_MAP_SURF / MLOAM_MAP_CORNER, built with MapHandle or scan2MapOptimization); gf_method is the
+// reference's string.  sub_mat_H comes back as the reference leaves it.  The seed replaces std::random_device.
+class ActiveFeatureSelection {
+ public:
+  unsigned long long seed = 0;
+  void goodFeatureMatching(int map_slot, const common::PointICloud &laser_cloud, const Pose &pose_local, std::vector<size_t> &sel_feature_idx,
+                           const char feature_type, const std::string &gf_method, const double gf_ratio, double sub_mat_H[36],
+                           const float *cov_vec6 = nullptr) {
+    mloam_ctx_t *ctx = mloam::ThreadContext::get();
+    const int method = gf_method == "wo_gf" ? 0 : gf_method == "rnd" ? 1 : gf_method == "fps" ? 2 : 3;  // gd_fix / gd_float
+    std::vector<mloam_point_t> pts = mloam::pack(laser_cloud);
+    std::vector<int> sel(pts.size() + 1);
+    int n_sel = 0;
+    double x[7];
+    pose_local.toParam(x);
+    mloam::check(ctx, mloam_good_features(ctx, map_slot, feature_type, pts.data(), (int)pts.size(), cov_vec6, x, method, gf_ratio, seed++,
+                                          sel.data(), &n_sel, sub_mat_H, nullptr, nullptr), "mloam_good_features");
+    sel_feature_idx.assign(sel.begin(), sel.begin() + n_sel);
+  }
+};
+
 // ----------------------------------------------------------------------------------------------- mapper entry
 namespace mloam {
 // scan2MapOptimization (lidar_mapper_keyframe.cpp:423-639): the two submaps are (re)built with setInputCloud every
