@@ -600,3 +600,51 @@ def test_scan2map_with_good_feature_selection(ctx, c1, method):
     dt, dr = syn.pose_err(pose, ref)
     assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
     assert syn.pose_err(pose, c1["truth"])[0] < syn.pose_err(c1["init"], c1["truth"])[0]
+
+
+# ------------------------------------------------------------------------------------------------ committed golden fixtures
+def _golden(name):
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+
+
+def test_golden_reference_nanoflann_knn(ctx):
+    """GPU kNN against the answers of the reference's own kd-tree (tests/golden/knn_nanoflann.npz, generated from
+    /root/reference's nanoflann.hpp by tests/golden/make_golden.py): indices and float distances, exactly."""
+    g = _golden("knn_nanoflann.npz")
+    ctx.map_build(2, g["map"], 0.5)
+    for k in (1, 5, 10):
+        idx, sqd = ctx.knn(2, g["query"], k, 1.0)
+        inside = g[f"sqd{k}"] < 1.0
+        assert inside.sum() > 100
+        assert np.array_equal(idx[inside], g[f"idx{k}"][inside]) and np.array_equal(sqd[inside], g[f"sqd{k}"][inside])
+        assert np.all(idx[~inside] == -1)
+
+
+def test_golden_oracle_vectors_on_gpu(ctx):
+    """The whole path against the committed oracle vectors (no oracle call): feature sets and voxel filters bit-exact,
+    match decisions and neighbour sets exact, good-feature selection exact, pose within the north-star tolerance."""
+    g = _golden("oracle_small.npz")
+    out = ctx.extract_features(g["cloud"], g["ss"], g["se"])
+    for key, name in (("corner_points_sharp", "sharp"), ("corner_points_less_sharp", "less_sharp"), ("surf_points_flat", "flat"),
+                      ("surf_points_less_flat", "less_flat")):
+        assert np.array_equal(out[key].view(np.uint32), g[name].view(np.uint32)), key
+    assert np.array_equal(ctx.voxel_downsample(g["less_sharp"], 0.2, True).view(np.uint32), g["corner_ds"].view(np.uint32))
+    assert np.array_equal(ctx.voxel_downsample(g["less_flat"], 0.4, True).view(np.uint32), g["surf_ds"].view(np.uint32))
+    ctx.map_build(1, g["surf_map"], 0.5)
+    ctx.map_build(0, g["corner_map"], 0.5)
+    valid, coeffs, nn = ctx.match_from_map(1, "s", g["surf_ds"], g["init"])
+    assert np.array_equal(valid, g["surf_valid"]) and np.array_equal(nn[valid], g["surf_nn"][g["surf_valid"]])
+    assert np.array_equal(coeffs[valid], g["surf_coeff"][g["surf_valid"]])
+    valid, _, nn = ctx.match_from_map(0, "c", g["corner_ds"], g["init"])
+    assert np.array_equal(valid, g["corner_valid"]) and np.array_equal(nn[valid], g["corner_nn"][g["corner_valid"]])
+    gf = ctx.good_features(1, "s", g["surf_ds"], g["init"], orc.GF_GD, 0.25, 11)
+    assert np.array_equal(gf["sel"], g["gf_sel"]) and np.allclose(gf["H"], g["gf_H"], rtol=1e-9)
+    ctx.set_params(max_outer=3, max_inner=4)
+    try:
+        pose, st = ctx.scan2map(g["surf_ds"], g["corner_ds"], g["init"])
+    finally:
+        ctx.set_params(max_outer=2, max_inner=30)
+    dt, dr = syn.pose_err(pose, g["pose"])
+    assert dt <= POSE_TOL_T and dr <= POSE_TOL_R and st["n_surf"] == int(g["n_surf"]) and st["n_corner"] == int(g["n_corner"])

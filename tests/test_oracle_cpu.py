@@ -3,6 +3,7 @@
 vectors for this path, so known answers are derived analytically with the conventions of the
 reference's check() printers (eps 1e-6, right-multiplied deltaQ; lidar_map_factor.hpp:72-120)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -336,3 +337,37 @@ def test_good_feature_selection_oracle_properties():
     none = np.zeros(n, bool)
     for m in (orc.GF_RND, orc.GF_FPS, orc.GF_GD):
         assert len(orc.gf_select(m, 0.3, 1, none, np.zeros((n, 6)), xyz)[0]) == 0
+
+
+# ------------------------------------------------------------------------------------------------ committed golden fixtures
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_golden_reference_nanoflann_pins_oracle_knn():
+    """tests/golden/knn_nanoflann.npz holds the answers of the REFERENCE's own kd-tree (nanoflann.hpp compiled in place,
+    see make_golden.py): the oracle's kNN must reproduce indices and float distances exactly — also on hosts without
+    /root/reference."""
+    g = np.load(os.path.join(GOLDEN, "knn_nanoflann.npz"))
+    for k in (1, 5, 10):
+        idx, sqd = orc.knn(g["map"], g["query"], k)
+        assert np.array_equal(idx, g[f"idx{k}"]) and np.array_equal(sqd, g[f"sqd{k}"])
+
+
+def test_golden_oracle_regression_vectors():
+    """The oracle reproduces its committed outputs bit for bit (guards the checker itself against accidental change)."""
+    g = np.load(os.path.join(GOLDEN, "oracle_small.npz"))
+    f = orc.extract_cloud(g["cloud"], g["ss"], g["se"])
+    for key, name in (("corner_points_sharp", "sharp"), ("corner_points_less_sharp", "less_sharp"), ("surf_points_flat", "flat"),
+                      ("surf_points_less_flat", "less_flat")):
+        assert np.array_equal(f[key].view(np.uint32), g[name].view(np.uint32)), key
+    cs, _ = orc.voxel_grid(g["less_sharp"], 0.2, True)
+    sf, _ = orc.voxel_grid(g["less_flat"], 0.4, True)
+    assert np.array_equal(cs.view(np.uint32), g["corner_ds"].view(np.uint32)) and np.array_equal(sf.view(np.uint32), g["surf_ds"].view(np.uint32))
+    vs, cfs, nns = orc.match_from_map("s", g["surf_map"], g["surf_ds"], g["init"])
+    assert np.array_equal(vs, g["surf_valid"]) and np.array_equal(nns, g["surf_nn"]) and np.array_equal(cfs, g["surf_coeff"])
+    o = orc.default_opts()
+    o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = 3, 4
+    pose, st = orc.scan2map(g["surf_map"], g["corner_map"], g["surf_ds"], g["corner_ds"], g["init"], o)
+    assert np.array_equal(pose, g["pose"]) and int(st["n_surf"]) == int(g["n_surf"]) and int(st["n_corner"]) == int(g["n_corner"])
+    gf = orc.good_features("s", g["surf_map"], g["surf_ds"], g["init"], orc.GF_GD, 0.25, 11)
+    assert np.array_equal(gf["sel"], g["gf_sel"])
