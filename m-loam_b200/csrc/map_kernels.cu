@@ -14,8 +14,9 @@
 namespace mloam {
 
 // ------------------------------------------------------------------------------------------- build
-__global__ void k_table_clear(HashEntry *table, unsigned long long *block_mask, unsigned cap) {
+__global__ void k_table_clear(HashEntry *table, unsigned long long *block_mask, unsigned cap, int *cursor) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *cursor = 0;
   if (i < cap) {
     uint4 v;
     v.x = 0xffffffffu, v.y = 0xffffffffu, v.z = 0u, v.w = 0u;
@@ -26,8 +27,8 @@ __global__ void k_table_clear(HashEntry *table, unsigned long long *block_mask, 
 
 // Pass 1: cell key per point, insert-or-find its slot, count.  rank_of = arrival order inside the cell
 // (only the order of points inside a cell depends on it; results never do — kNN ties break on the index).
-__global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_cell, HashEntry *table, unsigned long long *block_mask,
-                             unsigned mask, int *__restrict__ slot_of, int *__restrict__ rank_of) {
+__global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_cell, HashEntry *table, unsigned mask,
+                             int *__restrict__ slot_of, int *__restrict__ rank_of) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const float4 p = pts[i];
@@ -43,8 +44,21 @@ __global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_ce
   }
   slot_of[i] = (int)h;
   rank_of[i] = atomicAdd(&table[h].count, 1);
-  // Coarse occupancy record of the 4x4x4-cell block this cell belongs to: same table, tagged key, the point
-  // count lives in `start` (its `count` stays 0 so the start-offset scan ignores it).
+}
+
+// Pass 2, one acting thread per occupied CELL (the point that arrived first): the cell's run of `sorted` is claimed
+// with one atomicAdd on a cursor (runs need to be contiguous per cell, not ordered across cells — no prefix scan over
+// the 2m-slot table), and the cell is entered once into the occupancy record of its 4x4x4 block: same table, tagged
+// key, point count in `start` (its `count` stays 0), occupied-cell bit in block_mask.
+__global__ void k_map_assign(const float4 *__restrict__ pts, int m, float inv_cell, HashEntry *table, unsigned long long *block_mask,
+                             unsigned mask, const int *__restrict__ slot_of, const int *__restrict__ rank_of, int *cursor) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m || rank_of[i] != 0) return;
+  const int h = slot_of[i];
+  const int cnt = table[h].count;
+  table[h].start = atomicAdd(cursor, cnt);
+  const float4 p = pts[i];
+  const int fx = (int)floorf(p.x * inv_cell), fy = (int)floorf(p.y * inv_cell), fz = (int)floorf(p.z * inv_cell);
   const unsigned long long ckey = coarse_key(fx >> MLOAM_COARSE_SHIFT, fy >> MLOAM_COARSE_SHIFT, fz >> MLOAM_COARSE_SHIFT);
   unsigned hc = hash_cell(ckey) & mask;
   while (true) {
@@ -54,85 +68,8 @@ __global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_ce
     if (prev == MLOAM_EMPTY_KEY || prev == ckey) break;
     hc = (hc + 1) & mask;
   }
-  atomicAdd(&table[hc].start, 1);
-  const unsigned long long bit = 1ull << (((fz & 3) << 4) | ((fy & 3) << 2) | (fx & 3));
-  if (!(block_mask[hc] & bit)) atomicOr(&block_mask[hc], bit);
-}
-
-// Exclusive scan of table[].count into table[].start: block totals -> scan of totals -> apply.
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
-  __shared__ int warp_sums[SCAN_THREADS / 32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(MLOAM_FULL_MASK, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) warp_sums[wid] = inc;
-  __syncthreads();
-  if (wid == 0) {
-    int w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(MLOAM_FULL_MASK, w, o);
-      if (lane >= o) w += t;
-    }
-    if (lane < SCAN_THREADS / 32) warp_sums[lane] = w;
-  }
-  __syncthreads();
-  const int base = wid > 0 ? warp_sums[wid - 1] : 0;
-  if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
-  __syncthreads();
-  return base + inc - v;
-}
-
-__global__ void k_scan_tile_sums(const HashEntry *table, unsigned cap, int *tile_sums) {
-  const unsigned base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  int s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++)
-    if (base + k < cap) s += table[base + k].count;
-  int total;
-  block_exclusive_scan(s, &total);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
-}
-__global__ void k_scan_tiles(int *tile_sums, int n_tiles) {
-  // single block; n_tiles can exceed the block size, so walk in chunks carrying the running total
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n_tiles; base += SCAN_THREADS) {
-    int i = base + threadIdx.x;
-    int v = i < n_tiles ? tile_sums[i] : 0;
-    int total;
-    int ex = block_exclusive_scan(v, &total);
-    if (i < n_tiles) tile_sums[i] = carry + ex;
-    __syncthreads();
-    if (threadIdx.x == 0) carry += total;
-    __syncthreads();
-  }
-}
-__global__ void k_scan_apply(HashEntry *table, unsigned cap, const int *tile_sums) {
-  const unsigned base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  int c[SCAN_ITEMS];
-  int s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) {
-    c[k] = (base + k < cap) ? table[base + k].count : 0;
-    s += c[k];
-  }
-  int ex = block_exclusive_scan(s, nullptr) + tile_sums[blockIdx.x];
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) {
-    // tagged (coarse) and empty records keep their `start` (bit 63 is set in both)
-    if (base + k < cap && !(table[base + k].key & MLOAM_COARSE_TAG)) table[base + k].start = ex;
-    ex += c[k];
-  }
+  atomicAdd(&table[hc].start, cnt);
+  atomicOr(&block_mask[hc], 1ull << (((fz & 3) << 4) | ((fy & 3) << 2) | (fx & 3)));
 }
 
 __global__ void k_map_scatter(const float4 *__restrict__ pts, int m, const HashEntry *__restrict__ table,
@@ -167,22 +104,19 @@ int map_build_device(Ctx *c, int slot, const float4 *d_pts, int m, float cell) {
   MLOAM_CUDA_OK(c, M.block_mask.reserve(sizeof(unsigned long long) * (size_t)cap));
   MLOAM_CUDA_OK(c, M.slot_of.reserve(sizeof(int) * (size_t)(m + 1)));
   MLOAM_CUDA_OK(c, M.rank_of.reserve(sizeof(int) * (size_t)(m + 1)));
-  const int n_tiles = (int)((cap + SCAN_TILE - 1) / SCAN_TILE);
-  MLOAM_CUDA_OK(c, M.scan_tmp.reserve(sizeof(int) * (size_t)n_tiles));
+  MLOAM_CUDA_OK(c, M.scan_tmp.reserve(64));  // the run cursor
   M.capacity = cap, M.m = m, M.cell = cell, M.built = true;
   cudaStream_t st = c->stream;
-  k_table_clear<<<(cap + 255) / 256, 256, 0, st>>>(M.table.as<HashEntry>(), M.block_mask.as<unsigned long long>(), cap);
+  k_table_clear<<<(cap + 255) / 256, 256, 0, st>>>(M.table.as<HashEntry>(), M.block_mask.as<unsigned long long>(), cap, M.scan_tmp.as<int>());
   c->launches++;
   if (m > 0) {
     const int nb = (m + 255) / 256;
-    k_map_insert<<<nb, 256, 0, st>>>(d_pts, m, 1.0f / cell, M.table.as<HashEntry>(), M.block_mask.as<unsigned long long>(), cap - 1,
-                                     M.slot_of.as<int>(), M.rank_of.as<int>());
-    k_scan_tile_sums<<<n_tiles, SCAN_THREADS, 0, st>>>(M.table.as<HashEntry>(), cap, M.scan_tmp.as<int>());
-    k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(M.scan_tmp.as<int>(), n_tiles);
-    k_scan_apply<<<n_tiles, SCAN_THREADS, 0, st>>>(M.table.as<HashEntry>(), cap, M.scan_tmp.as<int>());
+    k_map_insert<<<nb, 256, 0, st>>>(d_pts, m, 1.0f / cell, M.table.as<HashEntry>(), cap - 1, M.slot_of.as<int>(), M.rank_of.as<int>());
+    k_map_assign<<<nb, 256, 0, st>>>(d_pts, m, 1.0f / cell, M.table.as<HashEntry>(), M.block_mask.as<unsigned long long>(), cap - 1,
+                                     M.slot_of.as<int>(), M.rank_of.as<int>(), M.scan_tmp.as<int>());
     k_map_scatter<<<nb, 256, 0, st>>>(d_pts, m, M.table.as<HashEntry>(), M.slot_of.as<int>(), M.rank_of.as<int>(),
                                       M.sorted.as<float4>(), M.orig.as<float4>());
-    c->launches += 5;
+    c->launches += 3;
   }
   MLOAM_CUDA_OK(c, cudaGetLastError());
   return MLOAM_OK;
