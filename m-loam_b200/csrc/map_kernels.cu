@@ -50,13 +50,47 @@ __global__ void k_map_insert(const float4 *__restrict__ pts, int m, float inv_ce
 // with one atomicAdd on a cursor (runs need to be contiguous per cell, not ordered across cells — no prefix scan over
 // the 2m-slot table), and the cell is entered once into the occupancy record of its 4x4x4 block: same table, tagged
 // key, point count in `start` (its `count` stays 0), occupied-cell bit in block_mask.
-__global__ void k_map_assign(const float4 *__restrict__ pts, int m, float inv_cell, HashEntry *table, unsigned long long *block_mask,
-                             unsigned mask, const int *__restrict__ slot_of, const int *__restrict__ rank_of, int *cursor) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m || rank_of[i] != 0) return;
-  const int h = slot_of[i];
-  const int cnt = table[h].count;
-  table[h].start = atomicAdd(cursor, cnt);
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int *total) {
+  __shared__ int warp_sums[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(MLOAM_FULL_MASK, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < 8 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      int t = __shfl_up_sync(MLOAM_FULL_MASK, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane < 8) warp_sums[lane] = w;
+  }
+  __syncthreads();
+  const int base = wid > 0 ? warp_sums[wid - 1] : 0;
+  *total = warp_sums[7];
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(256)
+    k_map_assign(const float4 *__restrict__ pts, int m, float inv_cell, HashEntry *table, unsigned long long *block_mask, unsigned mask,
+                 const int *__restrict__ slot_of, const int *__restrict__ rank_of, int *cursor) {
+  __shared__ int block_base;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i < m && rank_of[i] == 0;
+  int h = 0, cnt = 0;
+  if (act) h = slot_of[i], cnt = table[h].count;
+  // one cursor atomic per CTA: block-wide exclusive scan of the cells' counts (a per-cell atomic on one address serialises)
+  int total;
+  const int excl = block_exclusive_scan_256(cnt, &total);
+  if (threadIdx.x == 0) block_base = total > 0 ? atomicAdd(cursor, total) : 0;
+  __syncthreads();
+  if (!act) return;
+  table[h].start = block_base + excl;
   const float4 p = pts[i];
   const int fx = (int)floorf(p.x * inv_cell), fy = (int)floorf(p.y * inv_cell), fz = (int)floorf(p.z * inv_cell);
   const unsigned long long ckey = coarse_key(fx >> MLOAM_COARSE_SHIFT, fy >> MLOAM_COARSE_SHIFT, fz >> MLOAM_COARSE_SHIFT);
