@@ -127,6 +127,16 @@ int mloam_comm_p2p_init(mloam_ctx_t *h, int nranks, int rank, const void *handle
     c->p2p_peer[q] = ptr;
   }
   c->nranks = nranks, c->rank = rank;
+  P2PView v;
+  memset(&v, 0, sizeof(v));
+  for (int q = 0; q < nranks; q++) {
+    char *base = static_cast<char *>(c->p2p_peer[q]);
+    v.flags[q] = reinterpret_cast<unsigned *>(base + 64), v.slots[q] = reinterpret_cast<double *>(base + 256);
+  }
+  v.epoch = reinterpret_cast<unsigned long long *>(c->p2p_local);
+  v.nranks = nranks, v.rank = rank;
+  if (!c->p2p_view) MLOAM_CUDA_OK(c, cudaMalloc(&c->p2p_view, sizeof(P2PView)));
+  MLOAM_CUDA_OK(c, cudaMemcpy(c->p2p_view, &v, sizeof(v), cudaMemcpyHostToDevice));
   c->p2p_on = true;
   return MLOAM_OK;
 }
@@ -142,6 +152,7 @@ int mloam_comm_destroy(mloam_ctx_t *h) {
     }
     cudaFree(c->p2p_local);
     c->p2p_local = nullptr;
+    if (c->p2p_view) cudaFree(c->p2p_view), c->p2p_view = nullptr;
     c->p2p_on = false;
     if (!c->nccl_comm) c->nranks = 1, c->rank = 0;
   }

@@ -153,6 +153,7 @@ struct Ctx {
   // by stores / polls over NVLink inside the k_linearize tail
   void *p2p_local = nullptr;
   void *p2p_peer[MLOAM_P2P_MAX_RANKS] = {nullptr};
+  void *p2p_view = nullptr;        // device copy of the P2PView the kernels read
   bool p2p_on = false;
 };
 

@@ -42,7 +42,7 @@ struct LinArgs {
   double eig_thre;
   unsigned *ticket;        // zero between launches
   LMState *state_rw;
-  P2PView p2p;             // nranks > 1: sum the packed normal equations over the ranks through peer memory
+  const P2PView *p2p;      // device copy of the peer-memory view, or null: sum the packed normal equations over the ranks
 };
 
 __device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMState *gst, int mode, double eig_thre, int want_eig, double *out_ne,
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  lm_tail(partials, (int)gridDim.x, a.state_rw, a.lm_mode, a.eig_thre, a.want_eig, nullptr, a.p2p.nranks > 1 ? &a.p2p : nullptr);
+  lm_tail(partials, (int)gridDim.x, a.state_rw, a.lm_mode, a.eig_thre, a.want_eig, nullptr, a.p2p);
   if (threadIdx.x == 0) *a.ticket = 0u;
 }
 
@@ -638,15 +638,7 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
   }
   const double eig_thre = c->lm_eig_thre >= 0.0 ? c->lm_eig_thre : c->params.eig_thre;
   const bool fused = lm_mode != 0 && (!c->nccl_comm || c->p2p_on) && !d_out30;
-  memset(&a.p2p, 0, sizeof(a.p2p));
-  if (fused && c->p2p_on) {
-    for (int q = 0; q < c->nranks; q++) {
-      char *base = static_cast<char *>(c->p2p_peer[q]);
-      a.p2p.flags[q] = reinterpret_cast<unsigned *>(base + 64), a.p2p.slots[q] = reinterpret_cast<double *>(base + 256);
-    }
-    a.p2p.epoch = reinterpret_cast<unsigned long long *>(c->p2p_local);
-    a.p2p.nranks = c->nranks, a.p2p.rank = c->rank;
-  }
+  a.p2p = (fused && c->p2p_on) ? static_cast<const P2PView *>(c->p2p_view) : nullptr;
   a.lm_mode = fused ? lm_mode : 0, a.want_eig = want_eig, a.eig_thre = eig_thre, a.ticket = ticket;
   a.state_rw = c->lm_state.as<LMState>();
   {
