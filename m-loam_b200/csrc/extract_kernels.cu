@@ -3,11 +3,12 @@
 // lidar_mapper_keyframe.cpp:359-364; algorithm mirrored in-tree at voxel_grid_covariance_mloam_impl.hpp:84-250).
 //
 //   k_curvature      11-tap stencil over the flat ring-major array (:133-142) + consecutive-gap flags (:194-197)
-//   k_ring_pick      one CTA per ring: per-sector bitonic sort of (curvature, index) in shared memory (:162),
+//   k_ring_pick      one CTA per ring: one bitonic sort of (sector, curvature, offset) in shared memory (:160-162),
 //                    then the data-dependent sharp / less-sharp / flat picks with +-5 suppression (:165-256)
-//   k_less_flat_*    label <= 0 compaction (:258-264)
-//   voxel pipeline   segment bbox -> voxel index -> stable radix sort -> run heads -> ordered centroid sums,
-//                    segments = rings for the per-ring filter (:266-271), one segment for whole-cloud filters
+//   k_ring_voxel     one CTA per ring: label <= 0 compaction (:258-264) + per-ring pcl::VoxelGrid(0.2) (:266-271) with an
+//                    in-CTA sort; k_ring_voxel_emit concatenates the rings
+//   voxel pipeline   whole-cloud filters: bbox -> voxel index -> stable radix sort (two launches per 8-bit pass) -> run
+//                    heads -> ordered centroid sums; clouds of <= 2048 points take the in-CTA path (k_voxel_small)
 //
 // Float arithmetic follows the reference's evaluation order; integer/index results are exact.
 #include "ctx.h"
@@ -464,8 +465,7 @@ struct RingStage {  // per ring picks, indices into the cloud
 
 __global__ void __launch_bounds__(RING_THREADS)
     k_ring_pick(const float *__restrict__ curv, const unsigned char *__restrict__ gap_ok_g, int n, const int *__restrict__ scan_start,
-                const int *__restrict__ scan_end, int *__restrict__ label, int *__restrict__ ring_of, RingStage *__restrict__ stage,
-                int *__restrict__ status) {
+                const int *__restrict__ scan_end, int *__restrict__ label, RingStage *__restrict__ stage, int *__restrict__ status) {
   extern __shared__ unsigned long long keys[];  // RING_SORT_MAX
   __shared__ unsigned char picked[RING_MAX + 16];
   __shared__ unsigned char gap[RING_MAX + 16];
@@ -484,7 +484,6 @@ __global__ void __launch_bounds__(RING_THREADS)
     picked[t] = 0;
     gap[t] = gap_ok_g[lo + t];
   }
-  for (int k = s + threadIdx.x; k < e; k += RING_THREADS) ring_of[k] = ring;  // :258 range [sp_0, ep_5] = [s, e-1]
   // :160-162 for all six sectors at once: ONE bitonic sort of (sector, curvature, offset in ring).  The sectors tile
   // [s, e-1] in index order, so sector j's sorted run is keys[sp_j - s, ep_j - s]; ties in curvature go by index (the
   // reference's std::sort leaves them unspecified).
@@ -640,28 +639,6 @@ __global__ void k_emit_picks(const float4 *__restrict__ P, const RingStage *__re
   for (int k = threadIdx.x; k < S.n_sharp; k += blockDim.x) sharp[off[0] + k] = P[S.sharp[k]];
   for (int k = threadIdx.x; k < S.n_less; k += blockDim.x) less[off[1] + k] = P[S.less[k]];
   for (int k = threadIdx.x; k < S.n_flat; k += blockDim.x) flat[off[2] + k] = P[S.flat[k]];
-}
-
-__global__ void k_ring_of_init(int *ring_of, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) ring_of[i] = -1;
-}
-// :258-264: every point of a processed ring window with label <= 0
-__global__ void k_less_flat_flags(const int *__restrict__ ring_of, const int *__restrict__ label, int n, int *__restrict__ flag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = (ring_of[i] >= 0 && label[i] <= 0) ? 1 : 0;
-}
-__global__ void k_less_flat_gather(const float4 *__restrict__ P, const int *__restrict__ ring_of, const int *__restrict__ flag,
-                                   const int *__restrict__ pos, const int *__restrict__ scan_start, int n, float4 *__restrict__ out,
-                                   int *__restrict__ seg, int *__restrict__ seg_begin) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int r = ring_of[i];
-  if (r >= 0 && i == scan_start[r]) seg_begin[r] = pos[i];
-  if (flag[i]) {
-    out[pos[i]] = P[i];
-    seg[pos[i]] = r;
-  }
 }
 
 // ------------------------------------------------------------------------------------------ per-ring voxel grid
@@ -883,7 +860,7 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
   }
   ProfScope ps(c, "extract");
   cudaStream_t st = c->stream;
-  // scratch[4]: curv | label | ring_of | flag | pos | gap | stage | seg | seg_begin | status | less-flat points
+  // scratch[4]: curv | label | gap | stage | per-ring counts | status | staged less-flat centroids
   DevBuf &B = c->scratch[4];
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -892,22 +869,19 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
     return o;
   };
   const size_t N1 = (size_t)n + 16;
-  const size_t o_curv = take(4 * N1), o_label = take(4 * N1), o_ring = take(4 * N1), o_flag = take(4 * N1), o_pos = take(4 * N1);
-  const size_t o_gap = take(N1), o_stage = take(sizeof(RingStage) * 128), o_seg = take(4 * N1), o_segb = take(4 * 130);
-  const size_t o_status = take(16), o_lf = take(16 * N1), o_tmp = take(4 * (N1 / PRIM_TILE + 2));
+  const size_t o_curv = take(4 * N1), o_label = take(4 * N1);
+  const size_t o_gap = take(N1), o_stage = take(sizeof(RingStage) * 128), o_segb = take(4 * 130);
+  const size_t o_status = take(16), o_lf = take(16 * N1);
   MLOAM_CUDA_OK(c, B.reserve(off));
   char *p = B.as<char>();
   float *curv = reinterpret_cast<float *>(p + o_curv);
-  int *label = reinterpret_cast<int *>(p + o_label), *ring_of = reinterpret_cast<int *>(p + o_ring);
-  int *flag = reinterpret_cast<int *>(p + o_flag), *pos = reinterpret_cast<int *>(p + o_pos);
+  int *label = reinterpret_cast<int *>(p + o_label);
   unsigned char *gap = reinterpret_cast<unsigned char *>(p + o_gap);
   RingStage *stage = reinterpret_cast<RingStage *>(p + o_stage);
-  int *seg = reinterpret_cast<int *>(p + o_seg), *seg_begin = reinterpret_cast<int *>(p + o_segb);
+  int *seg_begin = reinterpret_cast<int *>(p + o_segb);  // per-ring centroid counts
   int *status = reinterpret_cast<int *>(p + o_status);
-  int *n_lf = status + 1;
   c->d_extract_status = status;
   float4 *lf = reinterpret_cast<float4 *>(p + o_lf);
-  int *tmp = reinterpret_cast<int *>(p + o_tmp);
   MLOAM_CUDA_OK(c, cudaMemsetAsync(out.counts, 0, 4 * sizeof(int), st));
   MLOAM_CUDA_OK(c, cudaMemsetAsync(status, 0, sizeof(int), st));
   if (n == 0) return MLOAM_OK;
@@ -918,8 +892,7 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
     MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_ring_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SORT_MAX * (int)sizeof(unsigned long long)));
     pick_opt_in = true;
   }
-  k_ring_pick<<<n_scans, RING_THREADS, RING_SORT_MAX * sizeof(unsigned long long), st>>>(curv, gap, n, d_scan_start, d_scan_end, label, ring_of, stage,
-                                                                                        status);
+  k_ring_pick<<<n_scans, RING_THREADS, RING_SORT_MAX * sizeof(unsigned long long), st>>>(curv, gap, n, d_scan_start, d_scan_end, label, stage, status);
   k_emit_picks<<<n_scans, 128, 0, st>>>(d_cloud, stage, n_scans, out.sharp, out.less_sharp, out.flat, out.counts);
   // :258-271 less-flat candidates + per-ring pcl::VoxelGrid(0.2): one CTA per ring, then the ring-order concatenation
   static bool smem_opt_in = false;

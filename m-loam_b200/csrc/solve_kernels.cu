@@ -3,11 +3,13 @@
 // (lidar_mapper_keyframe.cpp:537-596, lidar_tracker.cpp:70-120).
 //
 //   k_linearize : one thread per feature -> (r, 1x6 row) in double, Huber corrector, per-thread packed
-//                 upper-triangular J^T J (21) + J^T r (6) + cost + row counts, warp-shuffle tree ->
-//                 shared-memory cross-warp sum -> one partial per block (deterministic: no atomics).
-//   k_lm        : one warp sums the block partials in fixed order; lane 0 advances the LM state machine
-//                 (Jacobi scaling, LM diagonal, 6x6 Cholesky, step acceptance, radius update, tolerances,
-//                 degeneracy remap) entirely in device memory — the host only polls a done flag.
+//                 upper-triangular J^T J (21) + J^T r (6) + cost + row counts, 31-exchange butterfly over the 30
+//                 components -> shared-memory cross-warp sum -> one partial per block (deterministic: no atomics).
+//                 The block that finishes last (ticket) runs lm_tail: fixed-order sum of the block partials, optional
+//                 peer-memory exchange with the other GPUs' sums, and the LM state machine (Jacobi scaling, LM diagonal,
+//                 6x6 Cholesky, step acceptance, radius update, tolerances, degeneracy remap) on a shared-memory copy of
+//                 the device-resident state — the host only reads the final state back.
+//   k_lm        : the same tail as a stand-alone kernel (NCCL path, mloam_normal_equations).
 #include "ctx.h"
 #include "factors.cuh"
 
