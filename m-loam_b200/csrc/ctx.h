@@ -138,6 +138,7 @@ struct Ctx {
     ScanRef S{};
   };
   std::vector<GraphEntry> graphs;
+  bool smem_opt_in[3] = {false, false, false};  // >48 KB dynamic shared memory enabled for k_voxel_small / k_ring_pick / k_ring_voxel
   int use_graphs = 1;
   int use_seeds = 1;               // seed the kNN of re-association iterations > 0 with the previous neighbour lists
   int s2m_ran = 0;

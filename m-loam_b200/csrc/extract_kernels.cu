@@ -392,7 +392,7 @@ int voxel_downsample_device(Ctx *c, const float4 *d_in, int n, const int *d_n_in
   }
   ProfScope ps(c, "voxel");
   if (n > 0 && n <= RV_SMALL_MAX) {
-    static bool opt_in = false;
+    bool &opt_in = c->smem_opt_in[0];  // function attributes are per device: remembered per context, not per process
     if (!opt_in) {
       MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_voxel_small, cudaFuncAttributeMaxDynamicSharedMemorySize, RV_MAX_P2 * (int)sizeof(unsigned long long)));
       opt_in = true;
@@ -887,7 +887,7 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
   if (n == 0) return MLOAM_OK;
   const int nb = (n + 255) / 256;
   k_curvature<<<(n + CURV_THREADS - 1) / CURV_THREADS, CURV_THREADS, 0, st>>>(d_cloud, n, curv, gap, label);
-  static bool pick_opt_in = false;
+  bool &pick_opt_in = c->smem_opt_in[1];
   if (!pick_opt_in) {
     MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_ring_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SORT_MAX * (int)sizeof(unsigned long long)));
     pick_opt_in = true;
@@ -895,7 +895,7 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
   k_ring_pick<<<n_scans, RING_THREADS, RING_SORT_MAX * sizeof(unsigned long long), st>>>(curv, gap, n, d_scan_start, d_scan_end, label, stage, status);
   k_emit_picks<<<n_scans, 128, 0, st>>>(d_cloud, stage, n_scans, out.sharp, out.less_sharp, out.flat, out.counts);
   // :258-271 less-flat candidates + per-ring pcl::VoxelGrid(0.2): one CTA per ring, then the ring-order concatenation
-  static bool smem_opt_in = false;
+  bool &smem_opt_in = c->smem_opt_in[2];
   if (!smem_opt_in) {
     MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_ring_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, RV_MAX_P2 * (int)sizeof(unsigned long long)));
     smem_opt_in = true;
