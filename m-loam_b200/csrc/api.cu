@@ -100,6 +100,9 @@ int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out
       cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_maps, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(&c->pinned, kPinnedBytes) != cudaSuccess || c->lm_state.reserve(sizeof(LMState) + 64) != cudaSuccess ||
       c->scratch[7].reserve(4096) != cudaSuccess) {
     delete h;
@@ -136,6 +139,9 @@ void mloam_ctx_destroy(mloam_ctx_t *h) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_maps) cudaEventDestroy(c->ev_maps);
+  if (c->stream3) cudaStreamSynchronize(c->stream3), cudaStreamDestroy(c->stream3);
+  if (c->ev_fork3) cudaEventDestroy(c->ev_fork3);
+  if (c->ev_join3) cudaEventDestroy(c->ev_join3);
   delete h;
 }
 

@@ -83,6 +83,8 @@ struct Ctx {
   bool own_stream = true;
   cudaStream_t stream2 = nullptr;        // side stream: submap upload + build run concurrently with extraction
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t stream3 = nullptr;        // side stream: corner-scan voxel filter next to the surf-scan one
+  cudaEvent_t ev_fork3 = nullptr, ev_join3 = nullptr;
   cudaEvent_t ev_maps = nullptr;         // recorded on stream2 after the host API's submap H2D copies
   bool maps_pending = false;             // the map-build branch must wait on ev_maps (external to a captured graph)
   mloam_params_t params;

@@ -220,10 +220,25 @@ int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start,
     if (rc) return rc;
   }
   // downsampleCurrentScan, lidar_mapper_keyframe.cpp:356-364 (VoxelGridCovarianceMLOAM<PointI>: xyz mean, last intensity)
-  rc = voxel_downsample_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, P.corner_leaf, 1, F.corner_ds, F.n_corner_ds, 5);
-  if (rc) return rc;
+  // The two filters are independent chains of small kernels: the corner one runs on a second side stream next to the
+  // surf one (own scratch slot), also inside a captured graph; with stage profiling on they stay serial.
+  const bool fork_voxel = !c->prof_on;
+  if (fork_voxel) {
+    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_fork3, c->stream));
+    MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream3, c->ev_fork3, 0));
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->stream3;
+    rc = voxel_downsample_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, P.corner_leaf, 1, F.corner_ds, F.n_corner_ds, 3);
+    c->stream = main_stream;
+    if (rc) return rc;
+    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_join3, c->stream3));
+  } else {
+    rc = voxel_downsample_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, P.corner_leaf, 1, F.corner_ds, F.n_corner_ds, 3);
+    if (rc) return rc;
+  }
   rc = voxel_downsample_device(c, F.ex.less_flat, n, F.ex.counts + 3, P.surf_leaf, 1, F.surf_ds, F.n_surf_ds, 5);
   if (rc) return rc;
+  if (fork_voxel) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join3, 0));
   if (forked) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join the map-build branch
   ScanRef S{F.surf_ds, n, F.n_surf_ds, F.corner_ds, less_cap, F.n_corner_ds};
   *S_out = S;
