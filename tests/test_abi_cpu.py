@@ -24,6 +24,22 @@ def test_struct_layouts_match_defaults(mloam):
     assert abs(p.min_match_sq_dis - 1.0) < 1e-7 and abs(p.min_plane_dis - 0.2) < 1e-7
     assert abs(p.huber_a - 0.1) < 1e-15 and p.eig_thre == 100.0 and abs(p.cov_trace - 0.0075) < 1e-15
     assert abs(p.corner_leaf - 0.2) < 1e-7 and abs(p.surf_leaf - 0.4) < 1e-7
+    # the fields carved out of the reserved tail sit where the C struct puts them (a shifted layout would scramble these)
+    assert p.gf_method == 0 and abs(p.gf_ratio - 1.0) < 1e-7 and p.gf_seed == 0 and all(v == 0 for v in p.reserved)
+    import ctypes
+
+    # sizes of the C structs (gcc, include/mloam_b200.h): the ctypes mirrors must agree byte for byte
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "sz.c")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu", sizeof(mloam_params_t), sizeof(mloam_solve_stats_t), '
+                    'sizeof(mloam_features_t));return 0;}\n' % os.path.join(mloam.ROOT, "include", "mloam_b200.h"))
+        subprocess.check_call(["gcc", src, "-o", os.path.join(d, "sz")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "sz")]).split()]
+    assert sizes == [ctypes.sizeof(mloam.Params), ctypes.sizeof(mloam.SolveStats), ctypes.sizeof(mloam.Features)]
 
 
 def test_no_device_fails_loudly(mloam):
