@@ -86,3 +86,62 @@ def test_two_gpu_frame_parity(exchange):
            "--master-port", "29533" if exchange == "p2p" else "29534", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MLOAM_EXCHANGE=exchange))
     assert out.returncode == 0 and "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_peer_exchange_protocol_model():
+    """Model of lm_tail's peer-memory exchange (solve_kernels.cu): per rank an exchange buffer with slots[2][N] and
+    flags[2][N], double-buffered by epoch parity; a rank publishes its contribution into every rank's slot[parity][me],
+    raises flag[parity][me] = epoch + 1 there, waits for all flags of its own buffer, sums the slots in rank order and
+    only then moves on.  Run by N threads with random stalls: every rank must compute the identical (bit-identical) sum at
+    every epoch and no slot may be overwritten before every reader has consumed it (ranks drift by at most one epoch)."""
+    import random
+    import threading
+    import time
+
+    for n_ranks in (2, 4, 8):
+        epochs = 60
+        rng = np.random.default_rng(7)
+        contrib = rng.normal(size=(epochs, n_ranks, 30))  # what rank r contributes at epoch e
+        slots = np.zeros((n_ranks, 2, n_ranks, 30))       # slots[owner][parity][from]
+        flags = np.zeros((n_ranks, 2, n_ranks), np.int64)
+        sums = np.zeros((n_ranks, epochs, 30))
+        max_lead = [0]
+        progress = [0] * n_ranks
+        errors = []
+
+        def rank_main(me):
+            rnd = random.Random(100 + me)
+            for e in range(epochs):
+                par, target = e & 1, e + 1
+                if rnd.random() < 0.3:
+                    time.sleep(rnd.random() * 2e-3)
+                for q in range(n_ranks):          # peer stores
+                    slots[q, par, me] = contrib[e, me]
+                for q in range(n_ranks):          # then the flags (the kernel fences in between)
+                    flags[q, par, me] = target
+                t0 = time.time()
+                while not all(flags[me, par, q] >= target for q in range(n_ranks)):
+                    if time.time() - t0 > 20:
+                        errors.append(f"rank {me} timed out at epoch {e}")
+                        return
+                    time.sleep(0)
+                acc = np.zeros(30)
+                for q in range(n_ranks):          # rank order: identical on every rank
+                    acc = acc + slots[me, par, q]
+                sums[me, e] = acc
+                progress[me] = e + 1
+                max_lead[0] = max(max_lead[0], max(progress) - min(progress))
+
+        threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(n_ranks)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert not errors, errors
+        expect = np.zeros((epochs, 30))
+        for e in range(epochs):
+            acc = np.zeros(30)
+            for q in range(n_ranks):
+                acc = acc + contrib[e, q]
+            expect[e] = acc
+        for r in range(n_ranks):
+            assert np.array_equal(sums[r], expect), f"rank {r} summed stale or torn slots"
+        assert max_lead[0] <= 2  # published (epoch e+1) while the slowest still reads epoch e at most
