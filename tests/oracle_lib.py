@@ -81,6 +81,10 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def map_sqrt_info(cov_trace: float) -> float:
+    return float(lib().orc_map_sqrt_info(C.c_double(cov_trace)))
+
+
 def knn(map_, q, k, brute=False):
     map_, q = cloud(map_), cloud(q)
     idx = np.empty((q.shape[0], k), np.int32)

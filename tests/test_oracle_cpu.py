@@ -371,3 +371,52 @@ def test_golden_oracle_regression_vectors():
     assert np.array_equal(pose, g["pose"]) and int(st["n_surf"]) == int(g["n_surf"]) and int(st["n_corner"]) == int(g["n_corner"])
     gf = orc.good_features("s", g["surf_map"], g["surf_ds"], g["init"], orc.GF_GD, 0.25, 11)
     assert np.array_equal(gf["sel"], g["gf_sel"])
+
+
+def test_solver_restatement_converges_to_independent_optimum():
+    """The ceres::Solve restatement (orc_solver.hpp) + the factor restatements against an INDEPENDENT solver: with the
+    correspondences of one association fixed, scipy's trust-region least squares with the Huber loss minimises the same
+    objective (ceres::HuberLoss(a): rho(s) = s | 2a sqrt(s) - a^2  ==  scipy loss='huber', f_scale=a) written directly
+    in numpy.  Both must land on the same pose."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+
+    scene = syn.make_scene()
+    traj = syn.trajectory(6)
+    surf_map, corner_map = syn.make_submap(scene, 30000)
+    cloud, ss, se = syn.make_sweep(scene, traj[4], 16, 512, seed=21)
+    f = orc.extract_cloud(cloud, ss, se)
+    cs, _ = orc.voxel_grid(f["corner_points_less_sharp"], 0.2, True)
+    sf, _ = orc.voxel_grid(f["surf_points_less_flat"], 0.4, True)
+    init = syn.perturb_pose(traj[4], np.random.Generator(np.random.PCG64(2)))
+    o = orc.default_opts()
+    o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = 1, 60  # one association, LM to convergence
+    pose, st = orc.scan2map(surf_map, corner_map, sf, cs, init, o)
+    assert st["n_surf"] > 300 and st["n_corner"] > 50
+
+    vs, cfs, _ = orc.match_from_map("s", surf_map, sf, init)
+    vc, cfc, _ = orc.match_from_map("c", corner_map, cs, init)
+    ps, ws, ds = sf[vs][:, :3].astype(np.float64), cfs[vs][:, :3], cfs[vs][:, 3]
+    pc, la, lb = cs[vc][:, :3].astype(np.float64), cfc[vc][:, :3], cfc[vc][:, 3:6]
+    sinfo = orc.map_sqrt_info(0.0075)
+    t0, R0 = init[:3], Rotation.from_quat(init[3:7])  # x, y, z, w
+
+    def residuals(x):
+        R = (R0 * Rotation.from_rotvec(x[3:6])).as_matrix()
+        t = t0 + x[:3]
+        rs = sinfo * (np.einsum("ij,ij->i", ws, ps @ R.T + t) + ds)            # plane: s (w.(Rp+t) + d)
+        lp = pc @ R.T + t
+        rc = sinfo * np.linalg.norm(np.cross(lp - la, lp - lb), axis=1) / np.linalg.norm(la - lb, axis=1)  # edge: s |..x..| / |a-b|
+        return np.concatenate([rs, rc])
+
+    sol = least_squares(residuals, np.zeros(6), loss="huber", f_scale=0.1, xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=400)
+    R_ref = (R0 * Rotation.from_rotvec(sol.x[3:6]))
+    pose_ref = np.concatenate([t0 + sol.x[:3], R_ref.as_quat()])
+    dt, dr = syn.pose_err(pose, pose_ref)
+    # Ceres' default function tolerance (1e-6 relative cost change) stops the LM a few 1e-5 m short of the exact optimum
+    assert dt < 1e-4 and dr < 1e-4, (dt, dr)
+    assert dt < 0.05 * syn.pose_err(init, pose_ref)[0]
+    # and the objective value agrees: 1/2 sum rho
+    r = residuals(sol.x)
+    rho = np.where(np.abs(r) <= 0.1, r * r, 2 * 0.1 * np.abs(r) - 0.01)
+    assert abs(0.5 * rho.sum() - st["final_cost"]) < 1e-6 * max(1.0, st["final_cost"])
