@@ -109,8 +109,15 @@ int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out
     return MLOAM_E_CUDA;
   }
   c->pinned_cap = kPinnedBytes;
+  memset(c->pinned, 0, kPinnedBytes);
   cudaMemset(c->scratch[7].p, 0, 4096);
   if (const char *e = getenv("MLOAM_DISABLE_GRAPHS")) c->use_graphs = (e[0] == '0' || e[0] == '\0') ? 1 : 0;
+  if (const char *e = getenv("MLOAM_KNN_TRACE")) c->knn_trace_on = e[0] == '1';
+  if (const char *e = getenv("MLOAM_KNN_MB")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= 4) c->knn_min_blocks = v;
+  }
+  if (const char *e = getenv("MLOAM_KNN_TMA_MIN")) c->knn_tma_min = (unsigned)strtoul(e, nullptr, 10);
   if (const char *e = getenv("MLOAM_DISABLE_SEEDS")) c->use_seeds = (e[0] == '0' || e[0] == '\0') ? 1 : 0;
   *out = h;
   return MLOAM_OK;
@@ -128,7 +135,7 @@ void mloam_ctx_destroy(mloam_ctx_t *h) {
   prof_collect(c);
   for (auto e : c->evt_pool) cudaEventDestroy(e);
   for (auto &m : c->maps) {
-    m.sorted.release(), m.orig.release(), m.table.release(), m.block_mask.release(), m.slot_of.release(), m.rank_of.release(), m.scan_tmp.release();
+    m.sorted.release(), m.orig.release(), m.cells.release(), m.rank_of.release(), m.tile_sums.release(), m.hdr.release();
   }
   for (int i = 0; i < 2; i++) c->scan_pts[i].release(), c->feat_valid[i].release(), c->feat_coeff[i].release(), c->feat_nn[i].release(), c->knn_pos[i].release(), c->knn_changed[i].release(), c->knn_anchor[i].release(), c->knn_heavy[i].release(), c->gf_work[i].release();
   c->partials.release(), c->lm_state.release();
@@ -240,6 +247,14 @@ int mloam_map_build(mloam_ctx_t *h, int slot, const mloam_point_t *h_pts, int m,
   MLOAM_CUDA_OK(c, stage.reserve(sizeof(float4) * (size_t)(m + 1)));
   MLOAM_CUDA_OK(c, cudaMemcpyAsync(stage.p, h_pts, sizeof(float4) * (size_t)m, cudaMemcpyHostToDevice, c->stream));
   return map_build_device(c, slot, stage.as<float4>(), m, pick_cell(c, cell));
+}
+
+// Diagnosis only (not part of include/mloam_b200.h): per-query words of the last traced k_match_knn launch.
+int mloam_debug_knn_trace(mloam_ctx_t *h, unsigned *out, int n_queries) {
+  if (!h || !out || n_queries <= 0 || h->c.knn_trace.cap < 16 * (size_t)n_queries) return MLOAM_E_INVALID;  // n_queries may include the timeline tail
+  cudaSetDevice(h->c.device);
+  if (cudaStreamSynchronize(h->c.stream) != cudaSuccess) return MLOAM_E_CUDA;
+  return cudaMemcpy(out, h->c.knn_trace.p, 16 * (size_t)n_queries, cudaMemcpyDeviceToHost) == cudaSuccess ? MLOAM_OK : MLOAM_E_CUDA;
 }
 
 int mloam_map_size(mloam_ctx_t *h, int slot) {

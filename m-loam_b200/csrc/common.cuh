@@ -103,47 +103,53 @@ __host__ __device__ inline void pose_plus(const double *x, const double *delta, 
 }
 
 
-// ------------------------------------------------------------------ voxel-hash map
-struct HashEntry {
-  unsigned long long key;  // packed cell coordinate, ~0 = empty
-  int start;               // first point of the cell in `sorted`
-  int count;
+// ------------------------------------------------------------------ direct-indexed voxel grid map
+// The submap lives in HBM as (a) `sorted`: the points grouped by cell, cells in x-fastest linear order, w = original
+// index (int bits), and (b) `cell_start`: one exclusive prefix per cell of a DENSE grid over the map's bounding box
+// (n_cells + 1 entries).  A cell lookup is one 4-byte load at a computed address — no keys, no probing, no chains —
+// and because x is the fastest index the points of x-adjacent cells are contiguous: the 3x3x3 neighbourhood of a
+// query is 9 contiguous point runs.  Grid origin / dimensions / cell edge are decided ON THE DEVICE by the build
+// (bounding box of the finite points; the cell edge doubles until the grid fits the slot's capacity), so a rebuild
+// needs no host round trip and stays capturable in a CUDA graph.
+struct GridHdr {
+  int ox, oy, oz;          // cell coordinates of the grid origin
+  int nx, ny, nz;
+  int n_cells;             // nx * ny * nz  (<= capacity)
+  int level;               // cell = requested cell * 2^level
+  float cell, inv_cell;
+  int n_sorted;            // finite points placed in `sorted` (non-finite input points are dropped like PCL does)
+  int n_occupied;          // cells holding at least one point (statistics)
+  int bb_min[3], bb_max[3];  // bounding box accumulators (order-preserving int encoding of the float coordinates)
+  int ticket;              // last-block ticket of the prefix-scan kernels
+  int pad[1];
 };
-static_assert(sizeof(HashEntry) == 16, "HashEntry must be one 16-byte load");
 
 struct MapView {
   const float4 *sorted;    // cell-major points: xyz + original index (int bits) in w
-  const float4 *orig;      // original order (ring walks of the scan-to-scan matcher)
-  const HashEntry *table;
-  const unsigned long long *block_mask;  // per table slot: occupied cells of a 4x4x4 block (valid for block records)
-  unsigned mask;           // capacity - 1 (power of two)
-  float cell, inv_cell;
-  int m;
+  const float4 *orig;      // original order (ring walks of the scan-to-scan matcher); null unless the slot keeps it
+  const unsigned *cell_start;
+  const GridHdr *hdr;
+  int m;                   // input points (original indices run over [0, m))
 };
 
-#define MLOAM_EMPTY_KEY 0xffffffffffffffffull
-#define MLOAM_CELL_BIAS (1 << 20)
-
-__host__ __device__ inline unsigned long long pack_cell(int ix, int iy, int iz) {
-  return ((unsigned long long)((unsigned)(ix + MLOAM_CELL_BIAS) & 0x1fffffu) << 42) |
-         ((unsigned long long)((unsigned)(iy + MLOAM_CELL_BIAS) & 0x1fffffu) << 21) |
-         (unsigned long long)((unsigned)(iz + MLOAM_CELL_BIAS) & 0x1fffffu);
+// The header fields a query needs, loaded once per kernel.
+struct GridP {
+  int ox, oy, oz, nx, ny, nz;
+  float cell, inv_cell;
+};
+__device__ __forceinline__ GridP load_grid(const MapView &mv) {
+  GridP g;
+  if (!mv.hdr) {  // unused set of a two-set launch
+    g.ox = g.oy = g.oz = 0, g.nx = g.ny = g.nz = 0, g.cell = 1.0f, g.inv_cell = 1.0f;
+    return g;
+  }
+  const int4 a = __ldg(reinterpret_cast<const int4 *>(mv.hdr));           // ox oy oz nx
+  const int4 b = __ldg(reinterpret_cast<const int4 *>(mv.hdr) + 1);       // ny nz n_cells level
+  const float2 c = __ldg(reinterpret_cast<const float2 *>(mv.hdr) + 4);   // cell inv_cell
+  g.ox = a.x, g.oy = a.y, g.oz = a.z, g.nx = a.w, g.ny = b.x, g.nz = b.y, g.cell = c.x, g.inv_cell = c.y;
+  return g;
 }
-// Coarse occupancy: blocks of 4x4x4 cells share one tagged record (bit 63) holding their point count.
-#define MLOAM_COARSE_SHIFT 2
-#define MLOAM_COARSE_TAG 0x8000000000000000ull
-__host__ __device__ inline unsigned long long coarse_key(int cx, int cy, int cz) {
-  return pack_cell(cx, cy, cz) | MLOAM_COARSE_TAG;
-}
-__host__ __device__ inline unsigned hash_cell(unsigned long long k) {
-  // classic 3-prime spatial hash on the 21-bit cell coordinates (3 IMAD + folds; the table load is <= 0.5 so
-  // linear probing stays short), block records are displaced by the tag bit
-  const unsigned x = (unsigned)(k >> 42) & 0x1fffffu, y = (unsigned)(k >> 21) & 0x1fffffu, z = (unsigned)k & 0x1fffffu;
-  unsigned h = (x * 73856093u) ^ (y * 19349663u) ^ (z * 83492791u);
-  h ^= (unsigned)(k >> 63) * 0x9e3779b9u;
-  h ^= h >> 15;
-  return h;
-}
+static_assert(sizeof(GridHdr) % 16 == 0, "GridHdr is read with vector loads");
 
 // ------------------------------------------------------------------ peer-memory exchange (multi-GPU)
 // Exchange buffer of one rank (cudaMalloc'ed, IPC-mapped into every peer):

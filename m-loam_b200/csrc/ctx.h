@@ -43,23 +43,39 @@ struct DevBuf {
   }
 };
 
+constexpr size_t kMapStatsOffset = 8192;  // pinned: 64 B per map slot, the GridHdr head of the slot's last build (auto cell)
+
 struct MapStorage {
-  DevBuf sorted, orig, table, block_mask, slot_of, rank_of, scan_tmp;
-  unsigned capacity = 0;  // hash slots (power of two)
+  DevBuf sorted, orig, cells, rank_of, tile_sums, hdr;
+  unsigned capacity = 0;  // cells the dense grid may use (4 B each)
   int m = 0;
-  float cell = 0.f;
+  float cell = 0.f;       // requested cell edge of the last build (the device may have coarsened it: GridHdr::level)
+  float auto_cell = 0.25f;  // map_cell <= 0: cell edge picked from the occupancy statistics of the previous build
   bool built = false;
   MapView view() const {
     MapView v;
     v.sorted = sorted.as<float4>();
     v.orig = orig.as<float4>();
-    v.table = table.as<HashEntry>();
-    v.block_mask = block_mask.as<unsigned long long>();
-    v.mask = capacity - 1;
-    v.cell = cell;
-    v.inv_cell = 1.0f / cell;
+    v.cell_start = cells.as<unsigned>();
+    v.hdr = hdr.as<GridHdr>();
     v.m = m;
     return v;
+  }
+  // Sticky auto cell: a cell edge that gives a few points per occupied cell lets the 3x3x3 neighbourhood of a query
+  // hold its K neighbours (knn.cuh ring 1).  Decided from the header the previous build of this slot copied to pinned
+  // memory (possibly one build stale — it only steers speed, never results).  Power-of-two edges only.
+  float auto_cell_pick(const void *pinned, int slot) {
+    if (built && pinned) {
+      const GridHdr *h = reinterpret_cast<const GridHdr *>(reinterpret_cast<const char *>(pinned) + kMapStatsOffset + 64 * slot);
+      if (h->n_occupied > 0 && h->n_sorted > 0 && h->cell > 0.f) {
+        const float avg = (float)h->n_sorted / (float)h->n_occupied;
+        float cur = h->cell;
+        if (avg < 2.5f && cur < 1.0f) cur *= 2.0f;
+        else if (avg > 40.0f && cur > 0.125f) cur *= 0.5f;
+        auto_cell = cur;
+      }
+    }
+    return auto_cell;
   }
 };
 
@@ -103,6 +119,8 @@ struct Ctx {
   DevBuf knn_anchor[2];           // float4 per query: position of its last real search + tolerated displacement
   DevBuf gf_work[2];              // good-feature selection scratch per set (Jacobian rows, pool tree, mask, ...)
   DevBuf knn_heavy[2];            // 2 x unsigned char per query: "needed a real search" verdicts of the last two launches
+  DevBuf knn_heavy_list;          // 3 rotating counters + 2 lists of feature indices that needed a real search (match_kernels.cu HeavyQ)
+  int knn_rot = 0;                // launch ordinal inside the current solve (rotation of the heavy lists / counters)
   int knn_parity = 0;             // which half of knn_heavy the next seeded launch reads
   DevBuf partials;                // per-block packed normal equations
   DevBuf lm_state;                // LMState
@@ -142,6 +160,10 @@ struct Ctx {
   std::vector<GraphEntry> graphs;
   bool smem_opt_in[3] = {false, false, false};  // >48 KB dynamic shared memory enabled for k_voxel_small / k_ring_pick / k_ring_voxel
   int use_graphs = 1;
+  unsigned knn_tma_min = 8;        // kNN staging: runs of >= this many points use TMA bulk copies, shorter ones 16 B loads (MLOAM_KNN_TMA_MIN)
+  DevBuf knn_trace;                // MLOAM_KNN_TRACE=1: 4 words per query of the last k_match_knn launch (diagnosis, tools/knn_micro.py)
+  bool knn_trace_on = false;
+  int knn_min_blocks = 4;          // k_match_knn variant: resident CTAs per SM it is compiled for (MLOAM_KNN_MB = 2 | 3 | 4)
   int use_seeds = 1;               // seed the kNN of re-association iterations > 0 with the previous neighbour lists
   int s2m_ran = 0;
   int lm_min_corr = 0;              // lm_init_state: minimum matched features for a Solve (tracker: 10)

@@ -27,7 +27,8 @@ inline double map_sqrt_info(double cov_trace) {  // lidar_map_factor.hpp:34,41
 }
 
 inline float pick_cell(const Ctx *c, float requested) {
-  float cell = requested > 0.f ? requested : (c->params.map_cell > 0.f ? c->params.map_cell : 0.26f);  // 4 x 0.26 m blocks cover the 1 m match radius (knn.cuh)
+  // <= 0: map_build_device picks the slot's sticky auto cell (ctx.h MapStorage::auto_cell_pick)
+  float cell = requested > 0.f ? requested : (c->params.map_cell > 0.f ? c->params.map_cell : 0.f);
   return cell;
 }
 

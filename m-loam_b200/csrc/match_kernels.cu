@@ -3,13 +3,15 @@
 //
 //   k_match_knn  one WARP per feature: pointAssociateToMap + exact K-nearest search in the voxel-hash map
 //                (knn.cuh) + the distance gate sqdist[K-1] < MIN_MATCH_SQ_DIS.  Corner and surf features share one
-//                launch and one dynamic work queue (an atomic head that k_lm re-arms), so long queries — features
-//                in sparse regions — do not stall a wave.  Output: K neighbour positions per feature (20 B).
+//                launch; the features that needed a real search in the previous iteration are scheduled first (HeavyQ),
+//                so long queries — features in sparse regions — do not form the tail of the launch.  Output: K neighbour positions per feature (20 B).
 //   k_match_fit  one THREAD per feature: gathers the K neighbours (5 x 16 B), fits the line (mean + scatter +
 //                3x3 eigen) or the plane (5x3 column-pivoted QR), applies the lambda / plane-distance / FOV gates
 //                and writes valid + coefficients.  Running the fit one-thread-per-feature instead of redundantly
 //                in all 32 lanes of the search warp removes ~1/3 of the matcher's warp instructions and halves its
 //                register footprint.
+#include <cstdlib>
+
 #include "ctx.h"
 #include "fit.cuh"
 #include "knn.cuh"
@@ -31,65 +33,66 @@ struct KnnSet {
   unsigned char *heavy_out;       // this launch's verdict, for the next one
 };
 
-#ifndef MLOAM_KNN_MINBLOCKS
-#define MLOAM_KNN_MINBLOCKS 2  // 128 registers, no spills: measured faster than 3 CTAs/SM with local-memory spills
-#endif
-template <int K>
-__global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
-    k_match_knn(KnnSet a, KnnSet b, const double *__restrict__ pose7, float min_match_sq_dis, int *__restrict__ work,
-                unsigned *__restrict__ path_stats) {
-  __shared__ RunBuf rbuf[MWARPS];
+// Scheduling of the searches inside a launch.  Queries differ by 10x in cost (a kept neighbour list: ~2.5k cycles, a
+// real search: 10-30k) and a launch is only as fast as its slowest warp, so the few features that needed a real search
+// in the previous re-association iteration are listed (atomic append — a few dozen per launch, not one atomic per
+// query: 20k increments of ONE address cost ~1 ns each at the L2 and were the longest part of the launch) and taken
+// first, one per warp; everything else is a static stride.  cnt[3] rotates: a launch reads cnt_in, appends to cnt_out
+// and clears cnt_zero for the launch after the next.
+struct HeavyQ {
+  const int *list_in;   // nullable (first iteration): global feature indices (corner set first)
+  const int *cnt_in;
+  int *list_out;
+  int *cnt_out;
+  int *cnt_zero;
+};
+
+// MB: resident CTAs per SM the kernel is compiled for (register budget 65536 / (256 * MB)).  The search is a chain of
+// dependent warp-wide operations (prefix loads -> point loads -> REDUX / ballot / shuffle rounds): issue slots are only
+// filled when many warps are resident, so the default trades a few spilled registers for twice the warps.
+template <int K, int MB>
+__global__ void __launch_bounds__(MWARPS * 32, MB)
+    k_match_knn(KnnSet a, KnnSet b, const double *__restrict__ pose7, float min_match_sq_dis, HeavyQ hq,
+                unsigned *__restrict__ path_stats, unsigned tma_min, unsigned *__restrict__ trace) {
+  __shared__ KnnSmem ksm[MWARPS];
   const int lane = threadIdx.x & 31;
+  KnnSmem &ks = ksm[threadIdx.x >> 5];
+  unsigned long long t_enter = 0ull;
+  if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_enter));
+  knn_smem_init(ks, lane, tma_min);
+  __shared__ GridP s_grid[2];
+  __shared__ PoseD s_pose;
+  if (threadIdx.x == 0) s_grid[0] = load_grid(a.map), s_grid[1] = load_grid(b.map), s_pose = pose_from_param(pose7);
+  __syncthreads();
   const int na = a.d_n ? min(a.n, *a.d_n) : a.n;
   const int nb = b.d_n ? min(b.n, *b.d_n) : b.n;
   const int n = na + nb;
-  const PoseD T = pose_from_param(pose7);
-  // Feature indices come from a dynamic queue (an atomic head, `work`) or a static stride.  Both the index and the
-  // feature point are fetched two queries ahead, so neither the atomic nor the point load sits on a query's critical path.
-  // With heavy_in the queue runs over 2n virtual indices: pass 0 takes the features that needed a real search last
-  // time (tens of thousands of cycles each), pass 1 the cheap rest — long queries start first instead of forming the
-  // tail of the launch.
-  const bool two_pass = a.heavy_in != nullptr || b.heavy_in != nullptr;
-  const int n_virtual = two_pass ? 2 * n : n;
-  const int stride = gridDim.x * MWARPS;
-  auto fetch = [&](int v, int *skip) {
-    float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
-    *skip = 0;
-    if (v < n_virtual) {
-      const int idx = v >= n ? v - n : v;
-      const bool ina = idx < na;
-      pt = __ldg(ina ? a.pts + idx : b.pts + (idx - na));
-      if (two_pass) {
-        const unsigned char *hin = ina ? a.heavy_in : b.heavy_in;
-        const int heavy = hin ? (int)hin[ina ? idx : idx - na] : 0;
-        *skip = (heavy != 0) != (v < n);  // pass 0 (v < n): heavy ones; pass 1: the others
+  // Schedule: first the listed heavy features of the previous launch (one per warp), then a static stride over the rest.
+  const int gw = blockIdx.x * MWARPS + (threadIdx.x >> 5), n_warps = gridDim.x * MWARPS;
+  if (hq.cnt_zero && gw == 0 && lane == 0) *hq.cnt_zero = 0;
+  const bool listed = hq.list_in != nullptr;
+  const int n_heavy = listed ? min(__ldg(hq.cnt_in), n) : 0;
+  const int it_a = n_heavy > gw ? (n_heavy - gw + n_warps - 1) / n_warps : 0;
+  const int it_b = n > gw ? (n - gw + n_warps - 1) / n_warps : 0;
+#pragma unroll 1
+  for (int it = 0; it < it_a + it_b; it++) {
+    int i;
+    if (it < it_a) {
+      i = __ldg(hq.list_in + gw + it * n_warps);
+    } else {
+      i = gw + (it - it_a) * n_warps;
+      if (listed) {  // listed ones have been done above
+        const unsigned char *hin = i < na ? a.heavy_in : b.heavy_in;
+        if (hin && hin[i < na ? i : i - na]) continue;
       }
     }
-    return pt;
-  };
-  int v = blockIdx.x * MWARPS + (threadIdx.x >> 5), v_next = v + stride;
-  if (work) {
-    int t0 = 0, t1 = 0;
-    if (lane == 0) t0 = atomicAdd(work, 1), t1 = atomicAdd(work, 1);
-    v = __shfl_sync(MLOAM_FULL_MASK, t0, 0), v_next = __shfl_sync(MLOAM_FULL_MASK, t1, 0);
-  }
-  int skip, skip_next;
-  float4 p = fetch(v, &skip), p_next = fetch(v_next, &skip_next);
-  while (v < n_virtual) {
-    int v_after = v_next + stride;
-    if (work && lane == 0) v_after = (v_next < n_virtual) ? atomicAdd(work, 1) : n_virtual;  // in flight during this query
-    const int i = v >= n ? v - n : v;
-    if (skip) {
-      if (work) v_after = __shfl_sync(MLOAM_FULL_MASK, v_after, 0);
-      v = v_next, p = p_next, skip = skip_next;
-      v_next = v_after, p_next = fetch(v_after, &skip_next);
-      continue;
-    }
+    const float4 p = __ldg(i < na ? a.pts + i : b.pts + (i - na));
     const bool in_a = i < na;
     const int j = in_a ? i : i - na;
-    const long long t_query = path_stats ? clock64() : 0ll;
+    const long long t_query = (path_stats || trace) ? clock64() : 0ll;
     int path = 3;  // 0 keep (matched), 1 keep (rejected), 2 ball, 3 blind
-    const float3 sel = associate(T, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
+    const float3 sel = associate(s_pose, p.x, p.y, p.z);  // pointAssociateToMap, utility.h:103-117
+    const GridP &g = s_grid[in_a ? 0 : 1];
     Best best;  // selection width K + 1: lane K holds the nearest scanned point outside the K-set (feeds the anchor's slack)
     int *const pos_out = (in_a ? a.pos : b.pos) + (size_t)j * K;
     const int seeded = in_a ? a.seeded : b.seeded;
@@ -150,24 +153,28 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
       float explored = 0.0f;
       bool found = false;
       if (r2 < min_match_sq_dis)
-        found = warp_knn_seeded<K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, r2,
-                                          0.1f * (in_a ? a.map.cell : b.map.cell), lane, best, &explored);
+        found = warp_knn_seeded<K, K + 1>(in_a ? a.map : b.map, g, ks, sel.x, sel.y, sel.z, r2, 0.1f * g.cell,
+                                             lane, best, &explored);
       if (!found) {
-        KnnDbg dbg = {0, 0, 0, 0, 0, 0, 0};
-        const long long t_blind = path_stats ? clock64() : 0ll;
-        warp_knn<K, true, K + 1>(in_a ? a.map : b.map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, min_match_sq_dis, lane, best,
-                                 &explored, 0.05f, path_stats ? &dbg : nullptr);
+        KnnDbg dbg = {0, 0, 0, 0, 0, 0};
+        const long long t_blind = (path_stats || trace) ? clock64() : 0ll;
+        warp_knn<K, true, K + 1>(in_a ? a.map : b.map, g, ks, sel.x, sel.y, sel.z, min_match_sq_dis, lane, best, &explored, 0.05f,
+                                 (path_stats || trace) ? &dbg : nullptr);
+        if (trace && lane == 0) {
+          unsigned *tr = trace + 4 * (size_t)((in_a ? 0 : na) + j);
+          tr[1] = (unsigned)dbg.t_ring1, tr[2] = (unsigned)dbg.t_ball, tr[3] = ((unsigned)dbg.ring1_pts << 20) | ((unsigned)(dbg.ball_pts & 0xfff) << 8) | (unsigned)(dbg.ball_steps & 0xff);
+        }
         if (path_stats && lane == 0) {
           unsigned long long *q = reinterpret_cast<unsigned long long *>(path_stats + 24);
-          atomicAdd(q + 0, (unsigned long long)dbg.t_coarse), atomicAdd(q + 1, (unsigned long long)dbg.t_ring1);
-          atomicAdd(q + 2, (unsigned long long)dbg.t_finish), atomicAdd(q + 3, (unsigned long long)dbg.ring1_pts);
-          atomicAdd(q + 4, (unsigned long long)dbg.finish_pts), atomicAdd(q + 5, (unsigned long long)dbg.finish_blocks);
-          atomicAdd(q + 6, (unsigned long long)dbg.finish_cells), atomicAdd(q + 7, dbg.t_finish ? 1ull : 0ull);
+          atomicAdd(q + 0, 0ull), atomicAdd(q + 1, (unsigned long long)dbg.t_ring1);
+          atomicAdd(q + 2, (unsigned long long)dbg.t_ball), atomicAdd(q + 3, (unsigned long long)dbg.ring1_pts);
+          atomicAdd(q + 4, (unsigned long long)dbg.ball_pts), atomicAdd(q + 5, (unsigned long long)dbg.ball_steps);
+          atomicAdd(q + 6, (unsigned long long)dbg.ball_rows), atomicAdd(q + 7, dbg.t_ball ? 1ull : 0ull);
           const long long dt_blind = clock64() - t_blind;
           if (dt_blind > 90000) {  // a record of one very slow blind query (benign race: any of them will do)
             long long *rec = reinterpret_cast<long long *>(path_stats + 40);
-            rec[0] = dt_blind, rec[1] = dbg.t_coarse, rec[2] = dbg.t_ring1, rec[3] = dbg.t_finish, rec[4] = dbg.ring1_pts;
-            rec[5] = dbg.finish_pts, rec[6] = dbg.finish_cells, rec[7] = dbg.finish_blocks, rec[8] = (in_a ? 0 : 1) * 1000000 + j;
+            rec[0] = dt_blind, rec[1] = 0, rec[2] = dbg.t_ring1, rec[3] = dbg.t_ball, rec[4] = dbg.ring1_pts;
+            rec[5] = dbg.ball_pts, rec[6] = dbg.ball_rows, rec[7] = dbg.ball_steps, rec[8] = (in_a ? 0 : 1) * 1000000 + j;
             rec[9] = (long long)(t_blind - t_query);
           }
         }
@@ -208,11 +215,18 @@ __global__ void __launch_bounds__(MWARPS * 32, MLOAM_KNN_MINBLOCKS)
       atomicMax(reinterpret_cast<unsigned long long *>(path_stats + 16),
                 (dt << 32) | ((unsigned long long)path << 30) | ((unsigned long long)(in_a ? 0 : 1) << 29) | (unsigned)(j & 0x1fffffff));
     }
+    if (trace && lane == 0) trace[4 * (size_t)((in_a ? 0 : na) + j)] = (unsigned)(clock64() - t_query) | ((unsigned)path << 30);
     unsigned char *const hout = in_a ? a.heavy_out : b.heavy_out;
-    if (hout && lane == 0) hout[j] = path >= 2 ? 1 : 0;
-    if (work) v_after = __shfl_sync(MLOAM_FULL_MASK, v_after, 0);
-    v = v_next, p = p_next, skip = skip_next;
-    v_next = v_after, p_next = fetch(v_after, &skip_next);
+    if (hout && lane == 0) {
+      hout[j] = path >= 2 ? 1 : 0;
+      if (path >= 2 && hq.list_out) hq.list_out[atomicAdd(hq.cnt_out, 1)] = i;
+    }
+  }
+  if (trace && lane == 0) {  // per-warp timeline after the per-query words: [enter, first query, exit] in ns
+    unsigned long long t_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_exit));
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(trace + 4 * (size_t)(a.n + b.n + 1)) + 2 * (size_t)(blockIdx.x * MWARPS + (threadIdx.x >> 5));
+    w[0] = t_enter, w[1] = t_exit;
   }
 }
 
@@ -376,16 +390,55 @@ int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_
     n_upper += J.n;
   }
   if (n_upper <= 0) return MLOAM_OK;
+  // heavy list of the launch: 2 lists x n_upper ints + 3 rotating counters (zeroed with the buffer; k_lm_init re-zeroes
+  // them at the start of every solve, where the rotation restarts)
+  HeavyQ hq{nullptr, nullptr, nullptr, nullptr, nullptr};
+  {
+    DevBuf &hl = c->knn_heavy_list;
+    const size_t ints = 2 * ((size_t)n_upper + 64) + 16;
+    if (hl.cap < sizeof(int) * ints) {
+      MLOAM_CUDA_OK(c, hl.reserve(sizeof(int) * ints));
+      MLOAM_CUDA_OK(c, cudaMemsetAsync(hl.p, 0, hl.cap, c->stream));
+    }
+    int *cnt = hl.as<int>();                 // [0..2] counters
+    int *lists = hl.as<int>() + 16;
+    const size_t half_l = (size_t)n_upper + 64;
+    if (!flip) {                              // a non-seeded launch starts a solve: the rotation restarts with clean counters
+      c->knn_rot = 0;
+      MLOAM_CUDA_OK(c, cudaMemsetAsync(cnt, 0, 3 * sizeof(int), c->stream));
+    }
+    const int k = c->knn_rot;
+    if (flip) hq.list_in = lists + half_l * (size_t)(k & 1), hq.cnt_in = cnt + k % 3;
+    hq.list_out = lists + half_l * (size_t)((k + 1) & 1), hq.cnt_out = cnt + (k + 1) % 3, hq.cnt_zero = cnt + (k + 2) % 3;
+    c->knn_rot = k + 1;
+  }
   if (flip) c->knn_parity ^= 1;
   cudaStream_t st = c->stream;
   {
     ProfScope ps(c, "match");
     // with stage profiling on: how many queries took the keep (matched / rejected), ball and blind paths
-    unsigned *path_stats = c->prof_on ? reinterpret_cast<unsigned *>(c->scratch[7].as<char>() + kKnnPathStatsOffset) : nullptr;
+    unsigned *path_stats = (c->prof_on && !getenv("MLOAM_KNN_NO_STATS")) ? reinterpret_cast<unsigned *>(c->scratch[7].as<char>() + kKnnPathStatsOffset) : nullptr;
+    unsigned *trace = nullptr;
+    if (c->knn_trace_on) {
+      MLOAM_CUDA_OK(c, c->knn_trace.reserve(16 * (size_t)(n_upper + 1) + 16 * 8 * 4 * 148 + 64));
+      MLOAM_CUDA_OK(c, cudaMemsetAsync(c->knn_trace.p, 0, 16 * (size_t)(n_upper + 1) + 16 * 8 * 4 * 148, st));
+      trace = c->knn_trace.as<unsigned>();
+    }
+    const int mb = c->knn_min_blocks;
     int nb = (n_upper + MWARPS - 1) / MWARPS;
-    if (nb > MLOAM_KNN_MINBLOCKS * c->sm_count) nb = MLOAM_KNN_MINBLOCKS * c->sm_count;  // 3 CTAs x 8 warps resident per SM; warps pull / stride over features
-    if (K == 5) k_match_knn<5><<<nb, MWARPS * 32, 0, st>>>(ks[0], ks[1], d_pose7, cfg.min_match_sq_dis, d_work, path_stats);
-    else k_match_knn<10><<<nb, MWARPS * 32, 0, st>>>(ks[0], ks[1], d_pose7, cfg.min_match_sq_dis, d_work, path_stats);
+    if (nb > mb * c->sm_count) nb = mb * c->sm_count;  // all CTAs resident; warps pull / stride over the features
+#define MLOAM_LAUNCH_KNN(KK, MBB) \
+  k_match_knn<KK, MBB><<<nb, MWARPS * 32, 0, st>>>(ks[0], ks[1], d_pose7, cfg.min_match_sq_dis, hq, path_stats, c->knn_tma_min, trace)
+    if (K == 5) {
+      if (mb == 2) MLOAM_LAUNCH_KNN(5, 2);
+      else if (mb == 3) MLOAM_LAUNCH_KNN(5, 3);
+      else MLOAM_LAUNCH_KNN(5, 4);
+    } else {
+      if (mb == 2) MLOAM_LAUNCH_KNN(10, 2);
+      else if (mb == 3) MLOAM_LAUNCH_KNN(10, 3);
+      else MLOAM_LAUNCH_KNN(10, 4);
+    }
+#undef MLOAM_LAUNCH_KNN
     c->launches++;
   }
   {

@@ -267,6 +267,11 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
     const int ints[7] = {n, n_scans, n_surf_map, n_corner_map, rebuild_maps, c->has_ext ? 1 : 0, c->maps_pending ? 1 : 0};
     key = fnv1a(key, ptrs, sizeof(ptrs));
     key = fnv1a(key, ints, sizeof(ints));
+    if (rebuild_maps && !(c->params.map_cell > 0.f)) {  // the auto cell edges are kernel arguments of the captured build
+      const float cells[2] = {c->maps[MLOAM_MAP_SURF].auto_cell_pick(c->pinned, MLOAM_MAP_SURF),
+                              c->maps[MLOAM_MAP_CORNER].auto_cell_pick(c->pinned, MLOAM_MAP_CORNER)};
+      key = fnv1a(key, cells, sizeof(cells));
+    }
     key = fnv1a(key, &c->params, sizeof(c->params));
     key = fnv1a(key, c->ext, sizeof(c->ext));
     key = fnv1a(key, &c->stream, sizeof(c->stream));

@@ -74,16 +74,19 @@ __device__ __forceinline__ void walk(const float4 *__restrict__ scan, int m, int
 template <bool SURF>
 __global__ void __launch_bounds__(TWARPS * 32)
     k_match_scan(MapView map, const float4 *__restrict__ pts, int n, const double *__restrict__ pose7, float dist_sq_thr, float nearby,
-                 unsigned char *__restrict__ valid, float *__restrict__ coeff, int *__restrict__ nn) {
-  __shared__ RunBuf rbuf[TWARPS];
+                 unsigned char *__restrict__ valid, float *__restrict__ coeff, int *__restrict__ nn, unsigned tma_min) {
+  __shared__ KnnSmem ksm[TWARPS];
   const int lane = threadIdx.x & 31;
+  KnnSmem &ks = ksm[threadIdx.x >> 5];
+  knn_smem_init(ks, lane, tma_min);
+  const GridP g = load_grid(map);
   PoseD T = pose_from_param(pose7);
   T.q = qnormalized(T.q);  // Pose(q, t) normalises (pose.cpp:34-41; lidar_tracker.cpp:54-55)
   for (int i = blockIdx.x * TWARPS + (threadIdx.x >> 5); i < n; i += gridDim.x * TWARPS) {
     const float4 p = __ldg(pts + i);
     const float3 sel = associate(T, p.x, p.y, p.z);  // TransformToStart, b_distortion = false (utility.h:55-77)
     Best best;
-    warp_knn<1, true>(map, rbuf[threadIdx.x >> 5], sel.x, sel.y, sel.z, dist_sq_thr, lane, best);
+    warp_knn<1, true>(map, g, ks, sel.x, sel.y, sel.z, dist_sq_thr, lane, best);
     const unsigned long long k0 = best_key(best, 0);
     bool ok = k0 != MLOAM_KEY_NONE && key_d2(k0) < dist_sq_thr;  // :158 / :296
     float out[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -137,8 +140,8 @@ int match_from_scan_device(Ctx *c, int slot, int type, const float4 *d_pts, int 
   int nb = (n + TWARPS - 1) / TWARPS;
   if (nb > 8 * c->sm_count) nb = 8 * c->sm_count;
   const float thr = c->params.distance_sq_threshold, nearby = c->params.nearby_scan;
-  if (type == 's') k_match_scan<true><<<nb, TWARPS * 32, 0, c->stream>>>(mv, d_pts, n, d_pose7, thr, nearby, d_valid, d_coeff, d_nn3);
-  else k_match_scan<false><<<nb, TWARPS * 32, 0, c->stream>>>(mv, d_pts, n, d_pose7, thr, nearby, d_valid, d_coeff, d_nn3);
+  if (type == 's') k_match_scan<true><<<nb, TWARPS * 32, 0, c->stream>>>(mv, d_pts, n, d_pose7, thr, nearby, d_valid, d_coeff, d_nn3, c->knn_tma_min);
+  else k_match_scan<false><<<nb, TWARPS * 32, 0, c->stream>>>(mv, d_pts, n, d_pose7, thr, nearby, d_valid, d_coeff, d_nn3, c->knn_tma_min);
   c->launches++;
   MLOAM_CUDA_OK(c, cudaGetLastError());
   return MLOAM_OK;

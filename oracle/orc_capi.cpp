@@ -32,7 +32,27 @@ static MatchParams mp_from(const double *o) {
   return mp;
 }
 
+#include <dlfcn.h>
+
 extern "C" {
+
+// Timed CPU arm only: route KdTree through the reference's nanoflann (oracle/_ref/libref_knn.so).  path == null / ""
+// switches back to the restatement's own tree.  Returns 1 when the backend is active.
+int orc_use_ref_tree(const char *so_path) {
+  RefTreeApi &api = ref_tree_api();
+  api = RefTreeApi();
+  if (!so_path || !so_path[0]) return 0;
+  void *h = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) return 0;
+  api.create = reinterpret_cast<void *(*)(const float *, int)>(dlsym(h, "ref_tree_create"));
+  api.knn = reinterpret_cast<int (*)(void *, float, float, float, int, int *, float *)>(dlsym(h, "ref_tree_knn"));
+  api.destroy = reinterpret_cast<void (*)(void *)>(dlsym(h, "ref_tree_destroy"));
+  if (!api.create || !api.knn || !api.destroy) {
+    api = RefTreeApi();
+    return 0;
+  }
+  return 1;
+}
 
 int orc_num_opts() { return O_COUNT; }
 void orc_default_opts(double *o) {

@@ -30,12 +30,36 @@ inline float dist2f(const PointI &a, float qx, float qy, float qz) {
   return dx * dx + dy * dy + dz * dz;
 }
 
+// Optional backend for the TIMED CPU arm (bench.py --impl reference / cpu_baseline): the reference's own vendored
+// nanoflann (oracle/_ref/libref_knn.so, compiled in place from /root/reference) builds and searches the tree.  Same
+// exact answers (tests pin both to each other); ties between equal distances are re-ordered by index afterwards.
+struct RefTreeApi {
+  void *(*create)(const float *pts, int m) = nullptr;
+  int (*knn)(void *tree, float qx, float qy, float qz, int k, int *idx, float *sqd) = nullptr;
+  void (*destroy)(void *tree) = nullptr;
+};
+inline RefTreeApi &ref_tree_api() {
+  static RefTreeApi api;
+  return api;
+}
+
 class KdTree {
  public:
+  KdTree() = default;
+  KdTree(const KdTree &) = delete;
+  KdTree &operator=(const KdTree &) = delete;
+  ~KdTree() {
+    if (ref_) ref_tree_api().destroy(ref_);
+  }
   // pcl::KdTreeFLANN::setInputCloud call sites: lidar_tracker.cpp:33-34, lidar_mapper_keyframe.cpp:433-434,
   // estimator.cpp:1129-1130,1231-1233
   void setInputCloud(const Cloud *cloud) {
     cloud_ = cloud;
+    if (ref_) ref_tree_api().destroy(ref_), ref_ = nullptr;
+    if (ref_tree_api().create && !cloud->empty()) {
+      ref_ = ref_tree_api().create(&(*cloud)[0].x, (int)cloud->size());
+      return;
+    }
     const int n = (int)cloud->size();
     order_.resize(n);
     std::iota(order_.begin(), order_.end(), 0);
@@ -46,6 +70,12 @@ class KdTree {
   // nearestKSearch (call sites feature_extract.hpp:155,293,406,570,666,813).  Writes min(K, size) hits and
   // returns that count.
   int nearestKSearch(float qx, float qy, float qz, int K, int *idx, float *sqd) const {
+    if (ref_) {
+      const int got = ref_tree_api().knn(ref_, qx, qy, qz, K, idx, sqd);
+      for (int i = 1; i < got; i++)  // equal distances: ascending index (insertion sort over tie runs)
+        for (int j = i; j > 0 && sqd[j - 1] == sqd[j] && idx[j - 1] > idx[j]; j--) std::swap(idx[j - 1], idx[j]);
+      return got;
+    }
     Best best;
     best.K = K < kMaxK ? K : kMaxK;
     if (!nodes_.empty()) search(0, qx, qy, qz, best);
@@ -61,6 +91,7 @@ class KdTree {
     float bmin[3], bmax[3];
   };
   const Cloud *cloud_ = nullptr;
+  void *ref_ = nullptr;
   std::vector<int> order_;
   std::vector<Node> nodes_;
   static constexpr int kLeaf = 15;

@@ -21,6 +21,26 @@ typedef nanoflann::KDTreeSingleIndexAdaptor<nanoflann::L2_Simple_Adaptor<float, 
 }  // namespace
 
 extern "C" {
+// Persistent tree for the timed CPU arm: build once per setInputCloud, query per feature (what pcl::KdTreeFLANN does).
+struct RefTree {
+  PC pc;
+  Tree tree;
+  RefTree(const float *p, int m) : pc{p, (size_t)m}, tree(3, pc, nanoflann::KDTreeSingleIndexAdaptorParams(15)) { tree.buildIndex(); }
+};
+void *ref_tree_create(const float *map, int m) { return new RefTree(map, m); }
+void ref_tree_destroy(void *t) { delete static_cast<RefTree *>(t); }
+int ref_tree_knn(void *t, float qx, float qy, float qz, int k, int *idx, float *sqd) {
+  size_t ids[64];
+  float ds[64];
+  if (k > 64) k = 64;
+  nanoflann::KNNResultSet<float> rs(k);
+  rs.init(ids, ds);
+  const float qq[3] = {qx, qy, qz};
+  static_cast<RefTree *>(t)->tree.findNeighbors(rs, qq, nanoflann::SearchParams());
+  const int got = (int)rs.size();
+  for (int j = 0; j < got; j++) idx[j] = (int)ids[j], sqd[j] = ds[j];
+  return got;
+}
 // map: float32 [m,4]; q: float32 [nq,4]; idx/sqd: [nq,k]. Missing slots: idx -1 / +inf.
 void ref_knn(const float *map, int m, const float *q, int nq, int k, int *idx, float *sqd) {
   PC pc{map, (size_t)m};
