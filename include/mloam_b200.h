@@ -67,7 +67,9 @@ typedef struct {
   int gf_method;               /* FLAGS_gf_method in scan2MapOptimization (:474-532): 0 wo_gf, 1 rnd, 2 fps, 3 gd_fix */
   float gf_ratio;              /* FLAGS_gf_ratio_ini */
   unsigned gf_seed;            /* selection seed; outer iteration i, set s (0 corner, 1 surf) uses gf_seed + 2 i + s */
-  int reserved[5];
+  int max_ring_points;         /* upper bound of the points of one ring (0: up to 12288); sizes the in-CTA sort of extractCloud so that
+                                  several rings share an SM — set it to the sensor's horizontal resolution */
+  int reserved[4];
 } mloam_params_t;
 
 /* Per-solve report (what the reference prints through summary.BriefReport / timers). */
@@ -202,6 +204,13 @@ int mloam_frame_device(mloam_ctx_t *ctx, const mloam_point_t *d_cloud, int n, co
  * (features reach scan2MapOptimization in the base frame, laser id in intensity; visualization.cpp:48,94-100).
  * NULL resets to identity (no transform). */
 int mloam_set_extrinsic(mloam_ctx_t *ctx, const double *ext7);
+/* Several LiDARs in ONE context (one GPU): mloam_frame* then takes the sweeps of all n_lidars LiDARs concatenated
+ * (LiDAR-major; n_scans = n_lidars x rings per LiDAR, scan_start / scan_end index the concatenation).  extractCloud runs as one
+ * batch over all rings (estimator.cpp:249-263 runs it per LiDAR under OpenMP), every LiDAR's features are moved to the base
+ * frame with its extrinsic ext7[l] (sensor -> base) and tagged intensity = l (transformCloudFeature, visualization.cpp:40-52),
+ * concatenated LiDAR by LiDAR (pubPointCloud, :93-104) and enter downsampleCurrentScan + scan2MapOptimization as ONE feature list
+ * (lidar_mapper_keyframe.cpp:356-639).  n_lidars = 1 restores the single-LiDAR path. */
+int mloam_set_lidars(mloam_ctx_t *ctx, int n_lidars, const double *ext7);
 
 /* ---- FeatureExtract::matchCornerFromScan / matchSurfFromScan (feature_extract.hpp:131-376) against the map slot
  * built (mloam_map_build, cell ~1.3 m) from the previous sweep's less-sharp / less-flat features, which must be in

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
-    "mloam_frame_device", "mloam_set_extrinsic", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init",
+    "mloam_frame_device", "mloam_set_extrinsic", "mloam_set_lidars", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init",
 ]
 
 
@@ -40,7 +40,7 @@ class Params(C.Structure):
         ("point_plane_factor", C.c_int), ("point_edge_factor", C.c_int), ("huber_a", C.c_double), ("eig_thre", C.c_double),
         ("cov_trace", C.c_double), ("max_outer", C.c_int), ("max_inner", C.c_int), ("map_cell", C.c_float),
         ("corner_leaf", C.c_float), ("surf_leaf", C.c_float), ("gf_method", C.c_int), ("gf_ratio", C.c_float), ("gf_seed", C.c_uint),
-        ("reserved", C.c_int * 5),
+        ("max_ring_points", C.c_int), ("reserved", C.c_int * 4),
     ]
 
 
@@ -346,6 +346,10 @@ class Context:
         self._ck(lib().mloam_odom_solve(self._h, types.shape[0], _p(types), _p(points), _p(coeffs), _p(pv), _p(xi), _p(xe), int(free_mask),
                                         int(max_iterations), C.c_double(huber_a), C.c_double(sqrt_info), C.byref(st)))
         return xi, xe, st.as_dict()
+
+    def set_lidars(self, n_lidars: int, ext7=None):
+        e = None if ext7 is None else np.ascontiguousarray(ext7, np.float64).reshape(-1)
+        self._ck(lib().mloam_set_lidars(self._h, n_lidars, _p(e)))
 
     def set_extrinsic(self, ext7=None):
         e = None if ext7 is None else np.ascontiguousarray(ext7, np.float64)

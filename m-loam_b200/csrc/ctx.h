@@ -43,6 +43,9 @@ struct DevBuf {
   }
 };
 
+#define MLOAM_MAX_RINGS 1024  // rings of one (possibly multi-LiDAR) extraction
+#define MLOAM_MAX_LIDARS 16
+
 constexpr size_t kMapStatsOffset = 8192;  // pinned: 64 B per map slot, the GridHdr head of the slot's last build (auto cell)
 
 struct MapStorage {
@@ -140,6 +143,8 @@ struct Ctx {
   std::vector<cudaEvent_t> evt_pool;
 
   // NCCL (multi-GPU); opaque here
+  void *d_ring_stage = nullptr;     // RingStage[n_scans] of the last extraction (extract_kernels.cu)
+  int *d_ring_cnt = nullptr;        // per-ring less-flat centroid counts of the last extraction
   int *d_extract_status = nullptr;  // device flag of the last extraction (1: ring window overflow / bad ScanInfo)
   // CUDA-graph cache of whole frames (pipeline.cu frame_run)
   struct ScanRef {
@@ -169,6 +174,8 @@ struct Ctx {
   int lm_min_corr = 0;              // lm_init_state: minimum matched features for a Solve (tracker: 10)
   double lm_eig_thre = -1.0;        // < 0: use params.eig_thre; the tracker disables evalDegenracy with 0
   int want_eig = 1;                // k_lm mode 1: always run the 6x6 eigen-solver (1) or only when degenerate (0)
+  int n_lidars = 1;                // LiDARs batched into one frame of this context (mloam_set_lidars)
+  double lidar_ext[MLOAM_MAX_LIDARS][7];  // their sensor -> base extrinsics
   bool has_ext = false;            // sensor -> base extrinsic applied to extracted features (frame path)
   double ext[7] = {0, 0, 0, 0, 0, 0, 1};
   void *nccl_comm = nullptr;
@@ -275,6 +282,11 @@ struct ExtractOut {
 };
 int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
                    ExtractOut out, float *d_curv_or_null, int *d_label_or_null);
+// After a batched extraction over the concatenated sweeps of n_lidars LiDARs: move the less-sharp / less-flat features of LiDAR l into
+// the base frame with its float 3x4 extrinsic d_ext12[l] and set intensity = l (transformCloudFeature, visualization.cpp:40-52).
+// d_off: scratch for 2 x (n_lidars + 1) ints.
+int merge_lidars_device(Ctx *c, ExtractOut out, int n_cap_less, int n_cap_lflat, int n_lidars, int rings_per_lidar, const float *d_ext12,
+                        int *d_off);
 // d_n_in (nullable): device-side input count (n is then the upper bound the kernels are sized for).
 int voxel_downsample_device(Ctx *c, const float4 *d_in, int n, const int *d_n_in, float leaf, int intensity_last, float4 *d_out,
                             int *d_n_out, int work_slot = 5);

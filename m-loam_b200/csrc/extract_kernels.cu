@@ -465,8 +465,8 @@ struct RingStage {  // per ring picks, indices into the cloud
 
 __global__ void __launch_bounds__(RING_THREADS)
     k_ring_pick(const float *__restrict__ curv, const unsigned char *__restrict__ gap_ok_g, int n, const int *__restrict__ scan_start,
-                const int *__restrict__ scan_end, int *__restrict__ label, RingStage *__restrict__ stage, int *__restrict__ status) {
-  extern __shared__ unsigned long long keys[];  // RING_SORT_MAX
+                const int *__restrict__ scan_end, int *__restrict__ label, RingStage *__restrict__ stage, int *__restrict__ status, int smem_keys) {
+  extern __shared__ unsigned long long keys[];  // smem_keys (<= RING_SORT_MAX), sized by the launcher from params.max_ring_points
   __shared__ unsigned char picked[RING_MAX + 16];
   __shared__ unsigned char gap[RING_MAX + 16];
   const int ring = blockIdx.x;
@@ -490,6 +490,10 @@ __global__ void __launch_bounds__(RING_THREADS)
   const int len_ring = e - s;  // points s .. e-1; the last sector ends at e-1
   int P2 = 1;
   while (P2 < len_ring) P2 <<= 1;
+  if (P2 > smem_keys) {  // ring longer than the launch was sized for (params.max_ring_points)
+    if (threadIdx.x == 0) atomicExch(status, 1);
+    return;
+  }
   for (int t = threadIdx.x; t < P2; t += RING_THREADS) {
     unsigned long long key = 0xffffffffffffffffull;
     if (t < len_ring) {
@@ -795,12 +799,12 @@ __device__ void voxel_in_cta(const float4 *__restrict__ P, const int *__restrict
 
 __global__ void __launch_bounds__(RV_THREADS)
     k_ring_voxel(const float4 *__restrict__ P, const int *__restrict__ label, int n, const int *__restrict__ scan_start,
-                 const int *__restrict__ scan_end, float inv, float4 *__restrict__ stage_out, int *__restrict__ ring_cnt) {
+                 const int *__restrict__ scan_end, float inv, float4 *__restrict__ stage_out, int *__restrict__ ring_cnt, int smem_keys) {
   const int ring = blockIdx.x;
   const int s = scan_start[ring], e = scan_end[ring];
   const int len = e - s;
-  // the rings k_ring_pick processes (:155 and the on-chip window check)
-  if (len < 6 || len + 10 > RING_MAX || s - 5 < 0 || e + 5 > n) {
+  // the rings k_ring_pick processes (:155, the on-chip window check and the sort capacity of this launch)
+  if (len < 6 || len + 10 > RING_MAX || s - 5 < 0 || e + 5 > n || len > smem_keys) {
     if (threadIdx.x == 0) ring_cnt[ring] = 0;
     return;
   }
@@ -852,11 +856,62 @@ int transform_points_device(Ctx *c, float4 *d_pts, int n, const int *d_n, const 
   return MLOAM_OK;
 }
 
+// ------------------------------------------------------------------------------------------ multi-LiDAR merge
+// One batched extraction over the concatenated sweeps of L LiDARs (rings l * R .. (l + 1) * R - 1 belong to LiDAR l)
+// produces the feature clouds in ring order, i.e. LiDAR by LiDAR.  The odometry node hands them to the mapper in the
+// base frame, laser id in the intensity (transformCloudFeature, visualization.cpp:40-52; pubPointCloud :93-104):
+// pcl::transformPointCloud with the float matrix of Pose(qbl, tbl), then `+=` per LiDAR.
+__global__ void k_lidar_offsets(const RingStage *__restrict__ stage, const int *__restrict__ ring_cnt, int rings_per_lidar, int n_lidars,
+                                int *__restrict__ off /* [2][n_lidars + 1]: less-sharp, less-flat */) {
+  const int l = threadIdx.x;
+  if (l > n_lidars) return;
+  int a = 0, b = 0;
+  for (int q = 0; q < l * rings_per_lidar; q++) a += stage[q].n_less, b += ring_cnt[q];
+  off[l] = a, off[n_lidars + 1 + l] = b;
+}
+
+__global__ void k_merge_transform(float4 *__restrict__ pts, const int *__restrict__ off, int n_lidars, const float *__restrict__ ext12) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= off[n_lidars]) return;
+  int l = 0;
+  while (l + 1 < n_lidars && i >= off[l + 1]) l++;
+  const float *m = ext12 + 12 * l;
+  const float4 p = pts[i];
+  // pcl::transformPointCloud (PCL 1.8 transforms.hpp): x' = m00 x + m01 y + m02 z + m03, float, left to right
+  float4 o;
+  o.x = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+  o.y = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+  o.z = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
+  o.w = (float)l;  // p.intensity = n
+  pts[i] = o;
+}
+
+int merge_lidars_device(Ctx *c, ExtractOut out, int n_cap_less, int n_cap_lflat, int n_lidars, int rings_per_lidar, const float *d_ext12, int *d_off) {
+  if (n_lidars < 1 || n_lidars > MLOAM_MAX_LIDARS || !c->d_ring_stage) {
+    c->err = "merge_lidars: 1..16 LiDARs, after an extraction";
+    return MLOAM_E_INVALID;
+  }
+  cudaStream_t st = c->stream;
+  k_lidar_offsets<<<1, 32, 0, st>>>(static_cast<const RingStage *>(c->d_ring_stage), c->d_ring_cnt, rings_per_lidar, n_lidars, d_off);
+  if (n_cap_less > 0) k_merge_transform<<<(n_cap_less + 255) / 256, 256, 0, st>>>(out.less_sharp, d_off, n_lidars, d_ext12);
+  if (n_cap_lflat > 0) k_merge_transform<<<(n_cap_lflat + 255) / 256, 256, 0, st>>>(out.less_flat, d_off + n_lidars + 1, n_lidars, d_ext12);
+  c->launches += 3;
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  return MLOAM_OK;
+}
+
 int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
                    ExtractOut out, float *d_curv_or_null, int *d_label_or_null) {
-  if (n < 0 || n_scans <= 0 || n_scans > 128) {
-    c->err = "extract: n_scans must be in 1..128";
+  if (n < 0 || n_scans <= 0 || n_scans > MLOAM_MAX_RINGS) {
+    c->err = "extract: n_scans must be in 1..1024 (rings of all LiDARs of a batched extraction)";
     return MLOAM_E_INVALID;
+  }
+  // in-CTA sort capacity per ring: params.max_ring_points (0: the on-chip maximum).  A tight bound lets several ring CTAs
+  // share an SM (the sort keys are the kernels' shared-memory footprint), which is what a multi-LiDAR batch needs.
+  int smem_keys = RING_SORT_MAX;
+  if (c->params.max_ring_points > 0) {
+    smem_keys = 64;
+    while (smem_keys < c->params.max_ring_points && smem_keys < RING_SORT_MAX) smem_keys <<= 1;
   }
   ProfScope ps(c, "extract");
   cudaStream_t st = c->stream;
@@ -870,7 +925,7 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
   };
   const size_t N1 = (size_t)n + 16;
   const size_t o_curv = take(4 * N1), o_label = take(4 * N1);
-  const size_t o_gap = take(N1), o_stage = take(sizeof(RingStage) * 128), o_segb = take(4 * 130);
+  const size_t o_gap = take(N1), o_stage = take(sizeof(RingStage) * (size_t)n_scans), o_segb = take(4 * ((size_t)n_scans + 2));
   const size_t o_status = take(16), o_lf = take(16 * N1);
   MLOAM_CUDA_OK(c, B.reserve(off));
   char *p = B.as<char>();
@@ -881,6 +936,7 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
   int *seg_begin = reinterpret_cast<int *>(p + o_segb);  // per-ring centroid counts
   int *status = reinterpret_cast<int *>(p + o_status);
   c->d_extract_status = status;
+  c->d_ring_stage = stage, c->d_ring_cnt = seg_begin;  // per-ring pick / centroid counts (multi-LiDAR merge)
   float4 *lf = reinterpret_cast<float4 *>(p + o_lf);
   MLOAM_CUDA_OK(c, cudaMemsetAsync(out.counts, 0, 4 * sizeof(int), st));
   MLOAM_CUDA_OK(c, cudaMemsetAsync(status, 0, sizeof(int), st));
@@ -892,7 +948,7 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
     MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_ring_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, RING_SORT_MAX * (int)sizeof(unsigned long long)));
     pick_opt_in = true;
   }
-  k_ring_pick<<<n_scans, RING_THREADS, RING_SORT_MAX * sizeof(unsigned long long), st>>>(curv, gap, n, d_scan_start, d_scan_end, label, stage, status);
+  k_ring_pick<<<n_scans, RING_THREADS, (size_t)smem_keys * sizeof(unsigned long long), st>>>(curv, gap, n, d_scan_start, d_scan_end, label, stage, status, smem_keys);
   k_emit_picks<<<n_scans, 128, 0, st>>>(d_cloud, stage, n_scans, out.sharp, out.less_sharp, out.flat, out.counts);
   // :258-271 less-flat candidates + per-ring pcl::VoxelGrid(0.2): one CTA per ring, then the ring-order concatenation
   bool &smem_opt_in = c->smem_opt_in[2];
@@ -900,8 +956,8 @@ int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start
     MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_ring_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, RV_MAX_P2 * (int)sizeof(unsigned long long)));
     smem_opt_in = true;
   }
-  k_ring_voxel<<<n_scans, RV_THREADS, RV_MAX_P2 * sizeof(unsigned long long), st>>>(d_cloud, label, n, d_scan_start, d_scan_end, 1.0f / 0.2f, lf,
-                                                                                    seg_begin);
+  k_ring_voxel<<<n_scans, RV_THREADS, (size_t)smem_keys * sizeof(unsigned long long), st>>>(d_cloud, label, n, d_scan_start, d_scan_end, 1.0f / 0.2f,
+                                                                                              lf, seg_begin, smem_keys);
   k_ring_voxel_emit<<<n_scans, 128, 0, st>>>(lf, seg_begin, d_scan_start, n_scans, out.less_flat, out.counts + 3);
   c->launches += 5;
   if (d_curv_or_null) MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_curv_or_null, curv, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));

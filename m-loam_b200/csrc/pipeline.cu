@@ -209,7 +209,25 @@ int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start,
   rc = extract_device(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, F.ex, nullptr, nullptr);
   if (rc) return rc;
   const int less_cap = n < 120 * n_scans ? n : 120 * n_scans;  // <= 20 less-sharp picks x 6 sectors per ring
-  if (c->has_ext) {  // features are handed to the mapper in the base frame
+  if (c->n_lidars > 1) {
+    // batched sweeps of several LiDARs: features of LiDAR l go to the base frame with its extrinsic, intensity = l
+    // (transformCloudFeature, visualization.cpp:40-52), LiDAR after LiDAR as pubPointCloud's `+=` (:93-104)
+    if (n_scans % c->n_lidars != 0) return fail(c, MLOAM_E_INVALID, "frame: n_scans must be n_lidars x rings per LiDAR");
+    float *stage = reinterpret_cast<float *>(reinterpret_cast<char *>(c->pinned) + 12288);
+    for (int l = 0; l < c->n_lidars; l++) {
+      const double *e = c->lidar_ext[l];
+      const M33 R = qmat(qnormalized(Q4{e[3], e[4], e[5], e[6]}));  // Pose(q, t): q normalised, T_ = [R | t] (pose.cpp:34-41), cast<float>
+      for (int r = 0; r < 3; r++) {
+        for (int k = 0; k < 3; k++) stage[12 * l + 4 * r + k] = (float)R.m[3 * r + k];
+        stage[12 * l + 4 * r + 3] = (float)e[r];
+      }
+    }
+    float *d_ext12 = reinterpret_cast<float *>(c->scratch[7].as<char>() + 1024);
+    int *d_off = reinterpret_cast<int *>(c->scratch[7].as<char>() + 2048);
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ext12, stage, sizeof(float) * 12 * c->n_lidars, cudaMemcpyHostToDevice, c->stream));
+    rc = merge_lidars_device(c, F.ex, less_cap, n, c->n_lidars, n_scans / c->n_lidars, d_ext12, d_off);
+    if (rc) return rc;
+  } else if (c->has_ext) {  // features are handed to the mapper in the base frame
     double *stage = reinterpret_cast<double *>(c->pinned) + 32;
     for (int k = 0; k < 7; k++) stage[k] = c->ext[k];
     double *d_ext = c->scratch[7].as<double>() + 32;
@@ -274,6 +292,8 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
     }
     key = fnv1a(key, &c->params, sizeof(c->params));
     key = fnv1a(key, c->ext, sizeof(c->ext));
+    key = fnv1a(key, &c->n_lidars, sizeof(c->n_lidars));
+    key = fnv1a(key, c->lidar_ext, sizeof(double) * 7 * (size_t)c->n_lidars);
     key = fnv1a(key, &c->stream, sizeof(c->stream));
     Ctx::GraphEntry *e = nullptr;
     for (auto &g : c->graphs)
@@ -390,7 +410,7 @@ int mloam_scan2map_ua(mloam_ctx_t *h, const mloam_point_t *h_surf_scan, int n_su
 // ------------------------------------------------------------------------------------------ extractCloud
 int mloam_extract_features(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *h_scan_start, const int *h_scan_end,
                            int n_scans, mloam_features_t *out) {
-  if (!h || !out || n < 0 || n_scans <= 0 || n_scans > 128 || (n > 0 && !h_cloud) || !h_scan_start || !h_scan_end)
+  if (!h || !out || n < 0 || n_scans <= 0 || n_scans > MLOAM_MAX_RINGS || (n > 0 && !h_cloud) || !h_scan_start || !h_scan_end)
     return MLOAM_E_INVALID;
   Ctx *c = &h->c;
   cudaSetDevice(c->device);
@@ -484,7 +504,7 @@ int mloam_frame_device(mloam_ctx_t *h, const mloam_point_t *d_cloud, int n, cons
 int mloam_frame(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *h_scan_start, const int *h_scan_end, int n_scans,
                 const mloam_point_t *h_surf_map, int n_surf_map, const mloam_point_t *h_corner_map, int n_corner_map, int rebuild_maps,
                 const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
-  if (!h || !pose_init7 || !pose_out7 || n <= 0 || !h_cloud || !h_scan_start || !h_scan_end || n_scans <= 0 || n_scans > 128)
+  if (!h || !pose_init7 || !pose_out7 || n <= 0 || !h_cloud || !h_scan_start || !h_scan_end || n_scans <= 0 || n_scans > MLOAM_MAX_RINGS)
     return MLOAM_E_INVALID;
   Ctx *c = &h->c;
   cudaSetDevice(c->device);
@@ -514,6 +534,15 @@ int mloam_frame(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *
   const int rc = frame_run(c, d_cloud, n, d_ss, d_se, n_scans, d_sm, n_surf_map, d_cm, n_corner_map, rebuild_maps, pose_init7, pose_out7, stats);
   c->maps_pending = false;
   return rc;
+}
+
+int mloam_set_lidars(mloam_ctx_t *h, int n_lidars, const double *ext7) {
+  if (!h || n_lidars < 1 || n_lidars > MLOAM_MAX_LIDARS || (n_lidars > 1 && !ext7)) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  c->n_lidars = n_lidars;
+  for (int l = 0; l < n_lidars; l++)
+    for (int k = 0; k < 7; k++) c->lidar_ext[l][k] = ext7 ? ext7[7 * l + k] : (k == 6 ? 1.0 : 0.0);
+  return MLOAM_OK;
 }
 
 int mloam_set_extrinsic(mloam_ctx_t *h, const double *ext7) {

@@ -324,6 +324,65 @@ void orc_frame(const float *cloud, int n, const int *scan_start, const int *scan
   }
 }
 
+// ---- the same for a multi-LiDAR frame (odometry node -> mapper hand-over): the concatenated sweeps of n_lidars LiDARs
+// (LiDAR-major, n_scans = n_lidars x rings; scan_start / scan_end index the concatenation).  Per LiDAR n
+// (estimator.cpp:249-263, OpenMP over the LiDARs): extractCloud on its rings; transformCloudFeature (visualization.cpp:40-52):
+// pcl::transformPointCloud with Pose(qbl, tbl).T_.cast<float>() — PCL 1.8 transforms.hpp evaluates
+// x' = m00 x + m01 y + m02 z + m03 in float — and intensity = n; `+=` LiDAR by LiDAR (pubPointCloud :93-104, ESTIMATE_EXTRINSIC
+// == 0); then the mapper: downsampleCurrentScan + scan2MapOptimization on the merged clouds.  ext7: n_lidars x [t q].
+// threads > 1: the per-LiDAR extraction under OpenMP like the reference; the mapper part is single-threaded like the reference.
+void orc_frame_multi(const float *cloud, int n, const int *scan_start, const int *scan_end, int n_scans, int n_lidars, const double *ext7,
+                     const float *surf_map, int n_sm, const float *corner_map, int n_cm, float corner_leaf, float surf_leaf,
+                     const double *pose_init7, const double *opts, double *pose_out7, double *stats) {
+  const int R = n_scans / n_lidars;
+  std::vector<CloudFeature> feats(n_lidars);
+  double t0 = now_s();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int l = 0; l < n_lidars; l++) {
+    // the LiDAR's own cloud: points [first ring begin - 5, last ring end + 6) of the concatenation (ScanInfo = ring_begin + 5 / ring_end - 6)
+    const int lo = scan_start[l * R] - 5, hi = (l + 1 < n_lidars) ? scan_start[(l + 1) * R] - 5 : n;
+    Cloud c = to_cloud(cloud + 4 * (size_t)lo, hi - lo);
+    ScanInfo si;
+    for (int r = 0; r < R; r++) si.scan_start_ind.push_back(scan_start[l * R + r] - lo), si.scan_end_ind.push_back(scan_end[l * R + r] - lo);
+    extract_cloud(c, si, R, feats[l]);
+  }
+  Cloud corner, surf;
+  for (int l = 0; l < n_lidars; l++) {
+    const double *e = ext7 + 7 * l;
+    const Pose T = make_pose(Q4{e[3], e[4], e[5], e[6]}, V3{e[0], e[1], e[2]});  // Pose(q, t) normalises q (pose.cpp:34-41)
+    const M3 Rm = qmat(T.q);
+    float m[12];
+    for (int r = 0; r < 3; r++) {
+      for (int k = 0; k < 3; k++) m[4 * r + k] = (float)Rm(r, k);
+      m[4 * r + 3] = (float)(r == 0 ? T.t.x : (r == 1 ? T.t.y : T.t.z));
+    }
+    auto xf = [&](const Cloud &in, Cloud &out) {
+      for (const PointI &p : in) {
+        PointI o;
+        o.x = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+        o.y = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+        o.z = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
+        o.intensity = (float)l;
+        out.push_back(o);
+      }
+    };
+    xf(feats[l].corner_points_less_sharp, corner);
+    xf(feats[l].surf_points_less_flat, surf);
+  }
+  double t1 = now_s();
+  Cloud cs, ss;
+  voxel_grid(corner, corner_leaf, cs, true);  // lidar_mapper_keyframe.cpp:359-364
+  voxel_grid(surf, surf_leaf, ss, true);
+  double t2 = now_s();
+  double st16[16];
+  orc_scan2map(surf_map, n_sm, corner_map, n_cm, ss.empty() ? nullptr : &ss[0].x, (int)ss.size(),
+               cs.empty() ? nullptr : &cs[0].x, (int)cs.size(), pose_init7, opts, pose_out7, st16, nullptr);
+  if (stats) {
+    for (int i = 0; i < 16; i++) stats[i] = st16[i];
+    stats[16] = t1 - t0, stats[17] = t2 - t1, stats[18] = (double)ss.size(), stats[19] = (double)cs.size();
+  }
+}
+
 // ---- Estimator::optimizeMap residual blocks for one frame / one LiDAR (estimator.cpp:687-848): LidarPureOdom factors on
 // (pose_pivot [constant], pose_i, ext_n); free_mask bit 0 frees pose_i, bit 1 frees ext.  ceres::Solve(max_it),
 // HuberLoss(huber_a).  stats[3]: lm_iterations, final_cost, termination

@@ -269,6 +269,36 @@ def frame(cloud_, scan_start, scan_end, surf_map, corner_map, pose_init, opts=No
     return out, st
 
 
+def frame_multi(cloud_, scan_start, scan_end, n_lidars, ext7, surf_map, corner_map, pose_init, opts=None, corner_leaf=0.2, surf_leaf=0.4):
+    """Multi-LiDAR frame: per-LiDAR extractCloud -> transformCloudFeature -> merged downsample -> scan2MapOptimization."""
+    pts, sm, cm = cloud(cloud_), cloud(surf_map), cloud(corner_map)
+    ss = np.ascontiguousarray(scan_start, np.int32)
+    se = np.ascontiguousarray(scan_end, np.int32)
+    ext = np.ascontiguousarray(ext7, np.float64).reshape(-1)
+    opts = default_opts() if opts is None else np.ascontiguousarray(opts, np.float64)
+    pose_init = np.ascontiguousarray(pose_init, np.float64)
+    out = np.empty(7)
+    stats = np.zeros(20)
+    lib().orc_frame_multi(_p(pts), pts.shape[0], _p(ss), _p(se), ss.shape[0], n_lidars, _p(ext), _p(sm), sm.shape[0], _p(cm), cm.shape[0],
+                          C.c_float(corner_leaf), C.c_float(surf_leaf), _p(pose_init), _p(opts), _p(out), _p(stats))
+    names = ["ran", "n_surf", "n_corner", "lm_iterations", "final_cost", "degenerate", "t_kdtree", "t_match", "t_solver"]
+    st = {k: stats[i] for i, k in enumerate(names)}
+    st.update(t_extract=stats[16], t_downsample=stats[17], n_surf_in=int(stats[18]), n_corner_in=int(stats[19]))
+    return out, st
+
+
+def use_ref_tree(on: bool = True) -> bool:
+    """Timed CPU arm only: build / search the kd-trees with the reference's nanoflann (oracle/_ref/libref_knn.so)."""
+    path = os.path.join(ORC_DIR, "_ref", "libref_knn.so")
+    L = lib()
+    L.orc_use_ref_tree.restype = C.c_int
+    L.orc_use_ref_tree.argtypes = [C.c_char_p]
+    if on and os.path.exists(path):
+        return bool(L.orc_use_ref_tree(path.encode()))
+    L.orc_use_ref_tree(None)
+    return False
+
+
 def point_uncertainty(pts, pose7, cov_pose, cov_meas):
     pts = cloud(pts)
     pose7 = np.ascontiguousarray(pose7, np.float64)

@@ -262,3 +262,36 @@ def scan_info_from_cloud(cloud: np.ndarray, n_rings: int):
     counts = np.bincount(ring, minlength=n_rings)
     begin = np.concatenate([[0], np.cumsum(counts)[:-1]])
     return (begin + 5).astype(np.int32), (begin + counts - 6).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------- multi-LiDAR rigs
+# body_T_laser of estimator/config/config_realvehicle_hercules.yaml:56-59 ("PS-calib", rows are [qx qy qz qw tx ty tz]): the RV rig
+RV_EXTRINSICS = np.array([[0, 0, 0, 1, 0, 0, 0],
+                          [-0.0169, 0.0575, 0.0195, 0.998, 0.5355, 0.0393, -1.131],
+                          [-0.1118, 0.1894, 0.6845, 0.6951, 0.5116, 0.6440, -0.904],
+                          [0.0745, 0.1312, -0.7449, 0.6496, 0.4406, -0.628, -1.0295]])
+
+
+def rig_extrinsics(n_lidars: int) -> np.ndarray:
+    """[n_lidars, 7] sensor -> base parameter blocks [t q].  Up to 4 LiDARs: the RV rig (first rows of the RV
+    config); more: LiDAR 0 = identity, the others on a 1.2 m ring with +-20 deg tilt."""
+    if n_lidars <= 4:
+        return np.stack([pose7(r[4:7], r[0:4]) for r in RV_EXTRINSICS[:n_lidars]])
+    out = [pose7([0, 0, 0], [0, 0, 0, 1])]
+    for k in range(1, n_lidars):
+        a = 2 * math.pi * k / n_lidars
+        tilt = math.radians(20.0) * (1 if k % 2 else -1)
+        out.append(pose7([0.6 * math.cos(a), 0.6 * math.sin(a), 0.0], quat_from_rpy(tilt * math.sin(a), tilt * math.cos(a), a)))
+    return np.stack(out)
+
+
+def make_multi_sweep(scene: Scene, pose: np.ndarray, n_lidars: int, n_rings: int, horizon: int, seed: int, ext: np.ndarray | None = None):
+    """The sweeps of all LiDARs of a rig at base pose `pose`, concatenated LiDAR-major.
+    Returns (cloud [N,4], scan_start int32[n_lidars*n_rings], scan_end, ext [n_lidars,7]); ScanInfo indexes the concatenation."""
+    ext = rig_extrinsics(n_lidars) if ext is None else ext
+    clouds, starts, ends, base = [], [], [], 0
+    for l in range(n_lidars):
+        c, ss, se = make_sweep(scene, pose, n_rings, horizon, seed=seed, lidar_id=l, ext=ext[l])
+        clouds.append(c), starts.append(ss + base), ends.append(se + base)
+        base += c.shape[0]
+    return (np.ascontiguousarray(np.concatenate(clouds)), np.concatenate(starts).astype(np.int32), np.concatenate(ends).astype(np.int32), ext)

@@ -351,6 +351,52 @@ def test_frame_c2_full_size(ctx):
     assert et < 0.05 and er < 2e-3
 
 
+# ------------------------------------------------------------------------------------------------ several LiDARs on one GPU
+@pytest.mark.parametrize("n_lidars,rings,horizon,map_pts,outer", [(2, 16, 1024, 100_000, 5), (4, 64, 2048, 5_000_000, 10)])
+def test_frame_multi_lidar_one_gpu(ctx, n_lidars, rings, horizon, map_pts, outer):
+    """BASELINE config C4 on ONE GPU (4 x 64-ring LiDARs of the RV rig, 5M-point submap, 10 GN iterations) and a small 2-LiDAR
+    case: batched extractCloud over all rings, per-LiDAR extrinsic + laser id, merged downsample, one scan2MapOptimization —
+    against the oracle's per-LiDAR restatement (orc_frame_multi)."""
+    scene = syn.make_scene()
+    traj = syn.trajectory(8)
+    surf_map, corner_map = syn.make_submap(scene, map_pts)
+    cloud, ss, se, ext = syn.make_multi_sweep(scene, traj[6], n_lidars, rings, horizon, seed=21)
+    init = syn.perturb_pose(traj[6], np.random.Generator(np.random.PCG64(23)))
+    ctx.set_params(max_outer=outer, max_inner=1, n_scans=rings, map_cell=0.25, max_ring_points=horizon)
+    ctx.set_lidars(n_lidars, ext)
+    try:
+        pose, st = ctx.frame(cloud, ss, se, surf_map, corner_map, init)
+        pose_b, _ = ctx.frame(cloud, ss, se, surf_map, corner_map, init)
+        pose_c, _ = ctx.frame(cloud, ss, se, surf_map, corner_map, init)  # third call replays the captured graph
+    finally:
+        ctx.set_lidars(1)
+        ctx.set_params(max_outer=2, max_inner=30, n_scans=64, map_cell=0.0, max_ring_points=0)
+    assert np.array_equal(pose, pose_b) and np.array_equal(pose, pose_c)
+    o = orc.default_opts()
+    o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = outer, 1
+    ref, rst = orc.frame_multi(cloud, ss, se, n_lidars, ext, surf_map, corner_map, init, o)
+    assert st["n_surf_in"] == rst["n_surf_in"] and st["n_corner_in"] == rst["n_corner_in"]
+    assert st["n_surf"] == int(rst["n_surf"]) and st["n_corner"] == int(rst["n_corner"])
+    dt, dr = syn.pose_err(pose, ref)
+    assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+    et, er = syn.pose_err(pose, traj[6])
+    assert et < 0.05 and er < 2e-3
+
+
+def test_extract_128_rings(ctx):
+    """C5 geometry: 128 rings x 2048 (elevations -25 .. +15 deg) — extractCloud is ring-count agnostic (feature_extract.cpp:152)."""
+    scene = syn.make_scene()
+    cloud, ss, se = syn.make_sweep(scene, syn.trajectory(3)[2], 128, 2048, seed=9)
+    ctx.set_params(n_scans=128, max_ring_points=2048)
+    try:
+        got = ctx.extract_features(cloud, ss, se)
+    finally:
+        ctx.set_params(n_scans=64, max_ring_points=0)
+    ref = orc.extract_cloud(cloud, ss, se)
+    for k in ("corner_points_sharp", "corner_points_less_sharp", "surf_points_flat", "surf_points_less_flat"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
 # ------------------------------------------------------------------------------------------------ scan-to-scan (tracker)
 @pytest.fixture(scope="module")
 def two_sweeps():
