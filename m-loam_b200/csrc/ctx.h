@@ -46,7 +46,7 @@ struct DevBuf {
 #define MLOAM_MAX_RINGS 1024  // rings of one (possibly multi-LiDAR) extraction
 #define MLOAM_MAX_LIDARS 16
 
-constexpr size_t kMapStatsOffset = 8192;  // pinned: 64 B per map slot, the GridHdr head of the slot's last build (auto cell)
+constexpr size_t kMapStatsOffset = 16384;  // pinned: 64 B per map slot, the GridHdr head of the slot's last build (auto cell)
 
 struct MapStorage {
   DevBuf sorted, orig, cells, rank_of, tile_sums, hdr;
@@ -174,6 +174,7 @@ struct Ctx {
   int lm_min_corr = 0;              // lm_init_state: minimum matched features for a Solve (tracker: 10)
   double lm_eig_thre = -1.0;        // < 0: use params.eig_thre; the tracker disables evalDegenracy with 0
   int want_eig = 1;                // k_lm mode 1: always run the 6x6 eigen-solver (1) or only when degenerate (0)
+  bool lidar_merge = false;        // mloam_set_lidars was given extrinsics: features go through the rig merge (also for one LiDAR)
   int n_lidars = 1;                // LiDARs batched into one frame of this context (mloam_set_lidars)
   double lidar_ext[MLOAM_MAX_LIDARS][7];  // their sensor -> base extrinsics
   bool has_ext = false;            // sensor -> base extrinsic applied to extracted features (frame path)

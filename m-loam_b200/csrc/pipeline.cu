@@ -209,7 +209,7 @@ int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start,
   rc = extract_device(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, F.ex, nullptr, nullptr);
   if (rc) return rc;
   const int less_cap = n < 120 * n_scans ? n : 120 * n_scans;  // <= 20 less-sharp picks x 6 sectors per ring
-  if (c->n_lidars > 1) {
+  if (c->n_lidars > 1 || c->lidar_merge) {
     // batched sweeps of several LiDARs: features of LiDAR l go to the base frame with its extrinsic, intensity = l
     // (transformCloudFeature, visualization.cpp:40-52), LiDAR after LiDAR as pubPointCloud's `+=` (:93-104)
     if (n_scans % c->n_lidars != 0) return fail(c, MLOAM_E_INVALID, "frame: n_scans must be n_lidars x rings per LiDAR");
@@ -293,6 +293,7 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
     key = fnv1a(key, &c->params, sizeof(c->params));
     key = fnv1a(key, c->ext, sizeof(c->ext));
     key = fnv1a(key, &c->n_lidars, sizeof(c->n_lidars));
+    key = fnv1a(key, &c->lidar_merge, sizeof(c->lidar_merge));
     key = fnv1a(key, c->lidar_ext, sizeof(double) * 7 * (size_t)c->n_lidars);
     key = fnv1a(key, &c->stream, sizeof(c->stream));
     Ctx::GraphEntry *e = nullptr;
@@ -540,6 +541,7 @@ int mloam_set_lidars(mloam_ctx_t *h, int n_lidars, const double *ext7) {
   if (!h || n_lidars < 1 || n_lidars > MLOAM_MAX_LIDARS || (n_lidars > 1 && !ext7)) return MLOAM_E_INVALID;
   Ctx *c = &h->c;
   c->n_lidars = n_lidars;
+  c->lidar_merge = ext7 != nullptr;  // also for ONE LiDAR with an extrinsic: same float transform + laser id as in a rig
   for (int l = 0; l < n_lidars; l++)
     for (int k = 0; k < 7; k++) c->lidar_ext[l][k] = ext7 ? ext7[7 * l + k] : (k == 6 ? 1.0 : 0.0);
   return MLOAM_OK;

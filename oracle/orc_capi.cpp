@@ -34,6 +34,8 @@ static MatchParams mp_from(const double *o) {
 
 #include <dlfcn.h>
 
+std::vector<int> g_gf_groups_surf, g_gf_groups_corner;  // see orc_set_gf_groups
+
 extern "C" {
 
 // Timed CPU arm only: route KdTree through the reference's nanoflann (oracle/_ref/libref_knn.so).  path == null / ""
@@ -224,6 +226,7 @@ void orc_scan2map(const float *surf_map, int n_sm, const float *corner_map, int 
   o.point_plane = opts[O_POINT_PLANE] != 0, o.point_edge = opts[O_POINT_EDGE] != 0, o.cov_trace = opts[O_COV_TRACE];
   o.mp = mp_from(opts);
   o.gf_method = (int)opts[O_GF_METHOD], o.gf_ratio = opts[O_GF_RATIO], o.gf_seed = (uint64_t)opts[O_GF_SEED];
+  o.gf_groups_surf = g_gf_groups_surf, o.gf_groups_corner = g_gf_groups_corner;
   Cloud sm = to_cloud(surf_map, n_sm), cm = to_cloud(corner_map, n_cm), ss = to_cloud(surf_scan, n_ss),
         cs = to_cloud(corner_scan, n_cs);
   Scan2MapResult r = scan2map(sm, cm, ss, cs, to_pose(pose_init7), o);
@@ -331,9 +334,44 @@ void orc_frame(const float *cloud, int n, const int *scan_start, const int *scan
 // x' = m00 x + m01 y + m02 z + m03 in float — and intensity = n; `+=` LiDAR by LiDAR (pubPointCloud :93-104, ESTIMATE_EXTRINSIC
 // == 0); then the mapper: downsampleCurrentScan + scan2MapOptimization on the merged clouds.  ext7: n_lidars x [t q].
 // threads > 1: the per-LiDAR extraction under OpenMP like the reference; the mapper part is single-threaded like the reference.
+static void prepare_multi(const float *cloud, int n, const int *scan_start, const int *scan_end, int n_scans, int n_lidars, const double *ext7,
+                          float corner_leaf, float surf_leaf, Cloud &cs, Cloud &ss, double *t_extract, double *t_down);
+
+// features of one LiDAR group as they enter scan2MapOptimization (per-LiDAR extractCloud, extrinsic + laser id, merged
+// down-sampling); out_* have capacity n points.  Used to restate the sharded (one group per GPU) multi-GPU frame.
+void orc_prepare_multi(const float *cloud, int n, const int *scan_start, const int *scan_end, int n_scans, int n_lidars, const double *ext7,
+                       float corner_leaf, float surf_leaf, float *corner_out, int *n_corner, float *surf_out, int *n_surf) {
+  Cloud cs, ss;
+  prepare_multi(cloud, n, scan_start, scan_end, n_scans, n_lidars, ext7, corner_leaf, surf_leaf, cs, ss, nullptr, nullptr);
+  *n_corner = (int)cs.size(), *n_surf = (int)ss.size();
+  if (!cs.empty()) std::memcpy(corner_out, cs.data(), sizeof(PointI) * cs.size());
+  if (!ss.empty()) std::memcpy(surf_out, ss.data(), sizeof(PointI) * ss.size());
+}
+
+// good-feature selection per feature GROUP (one group per GPU in the sharded frame): sizes of the consecutive groups of the
+// surf / corner scans of the NEXT orc_scan2map call; n_groups = 0 switches back to one selection over the whole scan.
+void orc_set_gf_groups(int n_groups, const int *surf_sizes, const int *corner_sizes) {
+  g_gf_groups_surf.assign(surf_sizes, surf_sizes + n_groups);
+  g_gf_groups_corner.assign(corner_sizes, corner_sizes + n_groups);
+}
+
 void orc_frame_multi(const float *cloud, int n, const int *scan_start, const int *scan_end, int n_scans, int n_lidars, const double *ext7,
                      const float *surf_map, int n_sm, const float *corner_map, int n_cm, float corner_leaf, float surf_leaf,
                      const double *pose_init7, const double *opts, double *pose_out7, double *stats) {
+  Cloud cs, ss;
+  double te = 0, td = 0;
+  prepare_multi(cloud, n, scan_start, scan_end, n_scans, n_lidars, ext7, corner_leaf, surf_leaf, cs, ss, &te, &td);
+  double st16[16];
+  orc_scan2map(surf_map, n_sm, corner_map, n_cm, ss.empty() ? nullptr : &ss[0].x, (int)ss.size(),
+               cs.empty() ? nullptr : &cs[0].x, (int)cs.size(), pose_init7, opts, pose_out7, st16, nullptr);
+  if (stats) {
+    for (int i = 0; i < 16; i++) stats[i] = st16[i];
+    stats[16] = te, stats[17] = td, stats[18] = (double)ss.size(), stats[19] = (double)cs.size();
+  }
+}
+
+static void prepare_multi(const float *cloud, int n, const int *scan_start, const int *scan_end, int n_scans, int n_lidars, const double *ext7,
+                          float corner_leaf, float surf_leaf, Cloud &cs, Cloud &ss, double *t_extract, double *t_down) {
   const int R = n_scans / n_lidars;
   std::vector<CloudFeature> feats(n_lidars);
   double t0 = now_s();
@@ -370,17 +408,11 @@ void orc_frame_multi(const float *cloud, int n, const int *scan_start, const int
     xf(feats[l].surf_points_less_flat, surf);
   }
   double t1 = now_s();
-  Cloud cs, ss;
   voxel_grid(corner, corner_leaf, cs, true);  // lidar_mapper_keyframe.cpp:359-364
   voxel_grid(surf, surf_leaf, ss, true);
   double t2 = now_s();
-  double st16[16];
-  orc_scan2map(surf_map, n_sm, corner_map, n_cm, ss.empty() ? nullptr : &ss[0].x, (int)ss.size(),
-               cs.empty() ? nullptr : &cs[0].x, (int)cs.size(), pose_init7, opts, pose_out7, st16, nullptr);
-  if (stats) {
-    for (int i = 0; i < 16; i++) stats[i] = st16[i];
-    stats[16] = t1 - t0, stats[17] = t2 - t1, stats[18] = (double)ss.size(), stats[19] = (double)cs.size();
-  }
+  if (t_extract) *t_extract = t1 - t0;
+  if (t_down) *t_down = t2 - t1;
 }
 
 // ---- Estimator::optimizeMap residual blocks for one frame / one LiDAR (estimator.cpp:687-848): LidarPureOdom factors on

@@ -28,6 +28,9 @@ struct Scan2MapOptions {
   int gf_method = 0;
   double gf_ratio = 1.0;
   uint64_t gf_seed = 0;
+  // sharded frame (one LiDAR group per GPU): the selection runs per consecutive group of the scans with the same seeds;
+  // empty = one selection over the whole scan (the reference)
+  std::vector<int> gf_groups_surf, gf_groups_corner;
 };
 struct Scan2MapResult {
   Pose pose;
@@ -79,16 +82,31 @@ inline Scan2MapResult scan2map(const Cloud &surf_map, const Cloud &corner_map, c
       std::vector<double> jc;
       std::vector<int> sel;
       double subH[36];
-      if (o.point_edge) {
-        good_feature_matching('c', kd_corner, corner_map, corner_scan, pose_wmap_curr, o.corner_cov_trace, o.cov_trace, o.gf_method,
-                              o.gf_ratio, o.gf_seed + 2 * (uint64_t)iter_cnt, o.n_neigh, o.mp, all, mt, jc, sel, subH);
-        for (int q : sel) corner_f.push_back(all[q]);
-      }
-      if (o.point_plane) {
-        good_feature_matching('s', kd_surf, surf_map, surf_scan, pose_wmap_curr, o.surf_cov_trace, o.cov_trace, o.gf_method,
-                              o.gf_ratio, o.gf_seed + 2 * (uint64_t)iter_cnt + 1, o.n_neigh, o.mp, all, mt, jc, sel, subH);
-        for (int q : sel) surf_f.push_back(all[q]);
-      }
+      auto select = [&](char type, const KdTree &kd, const Cloud &map, const Cloud &scan, const std::vector<double> *cov,
+                        const std::vector<int> &groups, uint64_t seed, std::vector<Feature> &out) {
+        if (groups.empty()) {
+          good_feature_matching(type, kd, map, scan, pose_wmap_curr, cov, o.cov_trace, o.gf_method, o.gf_ratio, seed, o.n_neigh, o.mp, all, mt,
+                                jc, sel, subH);
+          for (int q : sel) out.push_back(all[q]);
+          return;
+        }
+        size_t off = 0;
+        for (int gsz : groups) {  // per group, as each GPU of the sharded frame selects among its own features
+          Cloud part(scan.begin() + off, scan.begin() + off + gsz);
+          std::vector<double> cpart;
+          if (cov) cpart.assign(cov->begin() + off, cov->begin() + off + gsz);
+          good_feature_matching(type, kd, map, part, pose_wmap_curr, cov ? &cpart : nullptr, o.cov_trace, o.gf_method, o.gf_ratio, seed,
+                                o.n_neigh, o.mp, all, mt, jc, sel, subH);
+          for (int q : sel) {
+            Feature f = all[q];
+            f.idx += (int)off;
+            out.push_back(f);
+          }
+          off += gsz;
+        }
+      };
+      if (o.point_edge) select('c', kd_corner, corner_map, corner_scan, o.corner_cov_trace, o.gf_groups_corner, o.gf_seed + 2 * (uint64_t)iter_cnt, corner_f);
+      if (o.point_plane) select('s', kd_surf, surf_map, surf_scan, o.surf_cov_trace, o.gf_groups_surf, o.gf_seed + 2 * (uint64_t)iter_cnt + 1, surf_f);
     }
     res.t_match += now_s() - t0;
     res.n_surf = (int)surf_f.size(), res.n_corner = (int)corner_f.size();

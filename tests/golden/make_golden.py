@@ -62,7 +62,11 @@ def main():
         sharp=f["corner_points_sharp"], less_sharp=f["corner_points_less_sharp"], flat=f["surf_points_flat"], less_flat=f["surf_points_less_flat"],
         corner_ds=cs, surf_ds=sf, surf_valid=vs, surf_coeff=cfs, surf_nn=nns, corner_valid=vc, corner_nn=nnc, pose=pose,
         n_surf=int(st["n_surf"]), n_corner=int(st["n_corner"]), lm_iterations=int(st["lm_iterations"]), gf_sel=gf["sel"], gf_H=gf["H"])
-    for name in ("knn_nanoflann.npz", "oracle_small.npz"):
+    # ---- workload cache: voxel-filtered keyframe features of the §8d submap (synthetic.keyframe_map_features); ~30 s of ray casting
+    import synthetic as syn
+    surf_f, corner_f = syn.keyframe_map_features(syn.make_scene(), orc.extract_cloud, orc.voxel_grid, use_cache=False)
+    np.savez_compressed(os.path.join(HERE, "submap_keyframes_filtered.npz"), surf=surf_f, corner=corner_f, tag=f"{syn.SEED}_30_64x2048")
+    for name in ("knn_nanoflann.npz", "oracle_small.npz", "submap_keyframes_filtered.npz"):
         print(name, os.path.getsize(os.path.join(HERE, name)), "bytes")
 
 

@@ -43,7 +43,7 @@ def main():
     truth = syn.trajectory(3)[2]
     surf_map, corner_map = syn.make_submap(scene, 60000)
     init = syn.perturb_pose(truth, np.random.Generator(np.random.PCG64(77)))
-    exts = [lidar_extrinsic(syn, r, world) for r in range(world)]
+    exts = [lidar_extrinsic(syn, r, max(world, 2)) for r in range(world)]
     clouds = [syn.make_sweep(scene, truth, 16, 1024, seed=50, lidar_id=r, ext=exts[r]) for r in range(world)]
     ctx.set_extrinsic(exts[rank])
     cloud, ss, se = clouds[rank]

@@ -287,6 +287,26 @@ def frame_multi(cloud_, scan_start, scan_end, n_lidars, ext7, surf_map, corner_m
     return out, st
 
 
+def prepare_multi(cloud_, scan_start, scan_end, n_lidars, ext7, corner_leaf=0.2, surf_leaf=0.4):
+    """(corner_ds, surf_ds) of one LiDAR group as they enter scan2MapOptimization."""
+    pts = cloud(cloud_)
+    ss = np.ascontiguousarray(scan_start, np.int32)
+    se = np.ascontiguousarray(scan_end, np.int32)
+    ext = np.ascontiguousarray(ext7, np.float64).reshape(-1)
+    co, so = np.empty((pts.shape[0], 4), np.float32), np.empty((pts.shape[0], 4), np.float32)
+    nc, ns = C.c_int(0), C.c_int(0)
+    lib().orc_prepare_multi(_p(pts), pts.shape[0], _p(ss), _p(se), ss.shape[0], n_lidars, _p(ext), C.c_float(corner_leaf), C.c_float(surf_leaf),
+                            _p(co), C.byref(nc), _p(so), C.byref(ns))
+    return co[:nc.value].copy(), so[:ns.value].copy()
+
+
+def set_gf_groups(surf_sizes=None, corner_sizes=None):
+    """Per-group good-feature selection for the next scan2map calls (None: one selection over the whole scan)."""
+    s = np.ascontiguousarray(surf_sizes if surf_sizes is not None else [], np.int32)
+    c = np.ascontiguousarray(corner_sizes if corner_sizes is not None else [], np.int32)
+    lib().orc_set_gf_groups(int(s.shape[0]), _p(s), _p(c))
+
+
 def use_ref_tree(on: bool = True) -> bool:
     """Timed CPU arm only: build / search the kd-trees with the reference's nanoflann (oracle/_ref/libref_knn.so)."""
     path = os.path.join(ORC_DIR, "_ref", "libref_knn.so")

@@ -295,3 +295,59 @@ def make_multi_sweep(scene: Scene, pose: np.ndarray, n_lidars: int, n_rings: int
         clouds.append(c), starts.append(ss + base), ends.append(se + base)
         base += c.shape[0]
     return (np.ascontiguousarray(np.concatenate(clouds)), np.concatenate(starts).astype(np.int32), np.concatenate(ends).astype(np.int32), ext)
+
+
+# ----------------------------------------------------------------------------- keyframe-built submap
+import os
+
+_KF_CACHE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "submap_keyframes_filtered.npz")
+
+
+def keyframe_map_features(scene: Scene, extract_cloud, voxel_grid, n_keyframes: int = 30, n_rings: int = 64, horizon: int = 2048,
+                          use_cache: bool = True):
+    """Voxel-filtered edge / surf features of `n_keyframes` earlier keyframes in the world frame: ray-cast sweeps from poses
+    1 m apart along the corridor (DISTANCE_KEYFRAMES = 1.0), extractCloud, keyframe pose, pcl::VoxelGrid 0.2 / 0.4
+    (MAP_CORNER_RES / MAP_SURF_RES).  `extract_cloud` / `voxel_grid` are passed in (the oracle's: this module stays a pure
+    workload generator).  The result for the default arguments is cached in tests/golden/ (made by tests/golden/make_golden.py;
+    ~30 s of ray casting otherwise)."""
+    tag = f"{SEED}_{n_keyframes}_{n_rings}x{horizon}"
+    if use_cache and os.path.exists(_KF_CACHE):
+        z = np.load(_KF_CACHE)
+        if str(z["tag"]) == tag:
+            return z["surf"], z["corner"]
+    corner_all, surf_all = [], []
+    for k in range(n_keyframes):
+        x = -27.0 + 1.0 * k
+        kf = pose7([x, 0.3 * math.sin(0.4 * k), 1.8], quat_from_rpy(0.0, 0.0, 0.05 * math.sin(0.3 * k)))
+        cloud, ss, se = make_sweep(scene, kf, n_rings, horizon, seed=5000 + k)
+        f = extract_cloud(cloud, ss, se)
+        R = quat_to_mat(kf[3:])
+        for key, acc in (("corner_points_less_sharp", corner_all), ("surf_points_less_flat", surf_all)):
+            p = f[key][:, :3].astype(np.float64) @ R.T + kf[:3]
+            acc.append(p.astype(np.float32))
+
+    def filt(parts, leaf):
+        p = np.concatenate(parts)
+        p4 = np.ascontiguousarray(np.concatenate([p, np.zeros((p.shape[0], 1), np.float32)], axis=1), dtype=np.float32)
+        return voxel_grid(p4, leaf, True)[0][:, :3].copy()
+
+    return filt(surf_all, 0.4), filt(corner_all, 0.2)
+
+
+def make_submap_keyframes(scene: Scene, n_total: int, extract_cloud, voxel_grid, seed: int = SEED, jitter: float = 0.01, **kw):
+    """The submap as the mapper accumulates it: the voxel-filtered keyframe features re-sampled with N(0, 1 cm)
+    jitter to exactly n_total points (edge : surf = 1 : 9).  Returns (surf_map, corner_map, info)."""
+    surf_f, corner_f = keyframe_map_features(scene, extract_cloud, voxel_grid, **kw)
+    rng = np.random.Generator(np.random.PCG64(seed + 5))
+
+    def resample(ds, n_want):
+        m = ds.shape[0]
+        if m >= n_want:
+            out = ds[np.sort(rng.choice(m, size=n_want, replace=False))].astype(np.float64)
+        else:  # up-sample: every filtered point once, then jittered duplicates
+            extra = rng.choice(m, size=n_want - m, replace=True)
+            out = np.concatenate([ds.astype(np.float64), ds[extra].astype(np.float64) + rng.normal(0, jitter, (n_want - m, 3))])
+        return np.ascontiguousarray(np.concatenate([out, np.zeros((n_want, 1))], axis=1), dtype=np.float32)
+
+    n_edge = n_total // 10
+    return resample(surf_f, n_total - n_edge), resample(corner_f, n_edge), {"filtered_surf": int(surf_f.shape[0]), "filtered_corner": int(corner_f.shape[0])}

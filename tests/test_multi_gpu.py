@@ -65,13 +65,17 @@ def test_bench_workload_is_rank_invariant_where_it_must_be():
     assert bench.lidar_extrinsic(syn, 0, 4) is None
     e1, e2 = bench.lidar_extrinsic(syn, 1, 4), bench.lidar_extrinsic(syn, 2, 4)
     assert abs(np.linalg.norm(e1[3:]) - 1) < 1e-12 and not np.allclose(e1, e2)
-    bench.MAP_POINTS[2] = 20000  # small maps for the test
-    bench.RINGS, bench.HORIZON = 16, 256
-    sm0, cm0, fr0, x0 = bench.make_workload(syn, 2, 0, 2)
-    sm1, cm1, fr1, x1 = bench.make_workload(syn, 2, 1, 2)
-    assert np.array_equal(sm0, sm1) and np.array_equal(cm0, cm1)          # replicated submap
-    assert all(np.array_equal(a["init"], b["init"]) for a, b in zip(fr0, fr1))  # shared LM state starts identical
-    assert not np.array_equal(fr0[0]["cloud"], fr1[0]["cloud"]) and x0 is None and x1 is not None
+    cfg = dict(bench.CONFIGS["C4"], rings=16, horizon=256, map_points=20000)  # small for the test
+    w0 = bench.make_workload(syn, cfg, 2, 0, 2, "uniform")
+    w1 = bench.make_workload(syn, cfg, 2, 1, 2, "uniform")
+    assert np.array_equal(w0["surf_map"], w1["surf_map"]) and np.array_equal(w0["corner_map"], w1["corner_map"])  # replicated submap
+    assert all(np.array_equal(a["init"], b["init"]) for a, b in zip(w0["frames"], w1["frames"]))  # shared LM state starts identical
+    assert w0["groups"] == [[0, 1], [2, 3]]                                                    # LiDARs sharded in consecutive groups
+    g0, g1 = w0["frames"][0]["groups"][0], w1["frames"][0]["groups"][1]
+    assert not np.array_equal(g0["cloud"][:100], g1["cloud"][:100]) and g0["ext"].shape == (2, 7) and g0["ss"].shape[0] == 32
+    # rank 0 can rebuild every group's sweeps for the per-N parity check; they equal what the other rank generated
+    wa = bench.make_workload(syn, cfg, 2, 0, 2, "uniform", all_groups=True)
+    assert np.array_equal(wa["frames"][0]["groups"][1]["cloud"], g1["cloud"])
 
 
 @pytest.mark.gpu
