@@ -509,9 +509,16 @@ def main():
             return 0
         import oracle_lib as orc
         n_frames = max(1, min(args.steps, 3))
-        wl = make_workload(syn, cfg, 1, 0, n_frames, args.map)
         warm = max(0, min(args.warmup, 1))
-        fps_rig, threads, times, _, tree = cpu_reference_arm(orc, cfg, wl, max(1, args.steps), warm, time_cap_s=150.0)
+        if cfg["calib"]:
+            from bench_calib import cpu_calib_arm, make_calib_workload
+            cases, map_info = make_calib_workload(syn, cfg, n_frames, args.map)
+            wl = {"map_info": map_info}
+            fps_rig, times, _, tree = cpu_calib_arm(orc, cfg, cases, max(1, args.steps), time_cap_s=150.0)
+            threads = 1
+        else:
+            wl = make_workload(syn, cfg, 1, 0, n_frames, args.map)
+            fps_rig, threads, times, _, tree = cpu_reference_arm(orc, cfg, wl, max(1, args.steps), warm, time_cap_s=150.0)
         steps = len(times)
         value = L * fps_rig
         sample = (f"{steps} rig frame(s) of {cfg_name} ({L} LiDAR sweep(s) each, {sum(times):.1f} s of CPU work): CPU restatement of the reference path "
@@ -608,7 +615,12 @@ def main():
         config["pose_err_vs_oracle"] = R.get("parity")
     # ---- cpu_baseline (N = 1 only): bounded sample of the same workload
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and cfg["calib"]:
+        from bench_calib import cpu_calib_arm
+        fps_rig, times, _, tree = cpu_calib_arm(orc, cfg, wl["cases"], 6, time_cap_s=30.0)
+        cpu = {"value": L * fps_rig, "unit": "frames/s", "cores": 1, "kind": "port",
+               "sample": f"{len(times)} calibration step(s) of this workload ({sum(times):.1f} s of CPU work), CPU restatement (-O3), kd-tree = {tree}, single-threaded as the reference"}
+    elif not args.no_cpu_baseline and world == 1:
         est = 0.6 * L * cfg["map_points"] / 1e6 + 0.3  # ~s per rig frame on one core
         n_cpu = args.cpu_sample or max(2, min(12, int(round(15.0 / est))))
         fps_rig, threads, times, _, tree = cpu_reference_arm(orc, cfg, wl, n_cpu, 1, time_cap_s=40.0)

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
-    "mloam_frame_device", "mloam_set_extrinsic", "mloam_set_lidars", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init",
+    "mloam_frame_device", "mloam_set_extrinsic", "mloam_set_lidars", "mloam_calib_frame", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init",
 ]
 
 
@@ -334,6 +334,19 @@ class Context:
         st = SolveStats()
         self._ck(lib().mloam_scan2map_ua(self._h, _p(ss), ss.shape[0], _p(sc), _p(cs), cs.shape[0], _p(cc), _p(pi), _p(out), C.byref(st)))
         return out, st.as_dict()
+
+    def calib_frame(self, surf_ref, corner_ref, surf_cal, corner_cal, pivot7, pose_i7, ext_ref7, ext_cal7, max_outer: int = 2, max_inner: int = 4,
+                    huber_a: float = 1.0):
+        sr, cr, sc, cc = (None if x is None or len(x) == 0 else _cloud(x) for x in (surf_ref, corner_ref, surf_cal, corner_cal))
+        n = [0 if x is None else x.shape[0] for x in (sr, cr, sc, cc)]
+        pv = np.ascontiguousarray(pivot7, np.float64)
+        pi = np.array(pose_i7, np.float64)
+        er = np.ascontiguousarray(ext_ref7, np.float64)
+        ec = np.array(ext_cal7, np.float64)
+        st = SolveStats()
+        self._ck(lib().mloam_calib_frame(self._h, _p(sr), n[0], _p(cr), n[1], _p(sc), n[2], _p(cc), n[3], _p(pv), _p(pi), _p(er), _p(ec),
+                                         max_outer, max_inner, C.c_double(huber_a), C.byref(st)))
+        return pi, ec, st.as_dict()
 
     def odom_solve(self, types, points, coeffs, pivot7, pose_i7, ext7, free_mask: int, max_iterations: int = 4, huber_a: float = 1.0,
                    sqrt_info: float = 1.0):

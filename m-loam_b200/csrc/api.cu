@@ -137,7 +137,9 @@ void mloam_ctx_destroy(mloam_ctx_t *h) {
   for (auto &m : c->maps) {
     m.sorted.release(), m.orig.release(), m.cells.release(), m.rank_of.release(), m.tile_sums.release(), m.hdr.release();
   }
-  for (int i = 0; i < 2; i++) c->scan_pts[i].release(), c->feat_valid[i].release(), c->feat_coeff[i].release(), c->feat_nn[i].release(), c->knn_pos[i].release(), c->knn_changed[i].release(), c->knn_anchor[i].release(), c->knn_heavy[i].release(), c->gf_work[i].release();
+  for (int i = 0; i < 4; i++) c->scan_pts[i].release(), c->feat_valid[i].release(), c->feat_coeff[i].release(), c->feat_nn[i].release(), c->knn_pos[i].release(), c->knn_changed[i].release(), c->knn_anchor[i].release(), c->knn_heavy[i].release();
+  for (int i = 0; i < 2; i++) c->gf_work[i].release();
+  c->knn_heavy_list.release(), c->knn_trace.release();
   c->partials.release(), c->lm_state.release();
   for (auto &s : c->scratch) s.release();
   if (c->pinned) cudaFreeHost(c->pinned);

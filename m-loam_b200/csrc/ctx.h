@@ -113,15 +113,15 @@ struct Ctx {
   MapStorage maps[MLOAM_NUM_MAPS];
 
   // scan features (device copies when the caller passes host buffers)
-  DevBuf scan_pts[2];             // [0] corner, [1] surf
-  DevBuf feat_valid[2];           // unsigned char per query
-  DevBuf feat_coeff[2];           // float[6] per query
-  DevBuf feat_nn[2];              // int[n_neigh] per query (optional)
-  DevBuf knn_pos[2];              // int[n_neigh] per query: neighbour positions handed from k_match_knn to k_match_fit
-  DevBuf knn_changed[2];          // unsigned char per query: neighbour list differs from the previous iteration's
-  DevBuf knn_anchor[2];           // float4 per query: position of its last real search + tolerated displacement
+  DevBuf scan_pts[4];             // [0] corner, [1] surf
+  DevBuf feat_valid[4];           // unsigned char per query
+  DevBuf feat_coeff[4];           // float[6] per query
+  DevBuf feat_nn[4];              // int[n_neigh] per query (optional)
+  DevBuf knn_pos[4];              // int[n_neigh] per query: neighbour positions handed from k_match_knn to k_match_fit
+  DevBuf knn_changed[4];          // unsigned char per query: neighbour list differs from the previous iteration's
+  DevBuf knn_anchor[4];           // float4 per query: position of its last real search + tolerated displacement
   DevBuf gf_work[2];              // good-feature selection scratch per set (Jacobian rows, pool tree, mask, ...)
-  DevBuf knn_heavy[2];            // 2 x unsigned char per query: "needed a real search" verdicts of the last two launches
+  DevBuf knn_heavy[4];            // 2 x unsigned char per query: "needed a real search" verdicts of the last two launches
   DevBuf knn_heavy_list;          // 3 rotating counters + 2 lists of feature indices that needed a real search (match_kernels.cu HeavyQ)
   int knn_rot = 0;                // launch ordinal inside the current solve (rotation of the heavy lists / counters)
   int knn_parity = 0;             // which half of knn_heavy the next seeded launch reads
@@ -232,7 +232,8 @@ struct MatchJob {
   int seeded;               // 1: same features against the same map as the previous call with this job index — its neighbour
                             // lists (Ctx::knn_pos) seed the search and unchanged lists keep their fit
 };
-int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_pose7, const MatchCfg &cfg, int *d_work);
+// buf_base: which pair of the context's per-set buffers (knn_pos / knn_anchor / ...) the jobs use: 0 (sets 0, 1) or 2 (sets 2, 3)
+int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_pose7, const MatchCfg &cfg, int *d_work, int buf_base = 0);
 
 // track_kernels.cu
 int match_from_scan_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const double *d_pose7, unsigned char *d_valid,

@@ -415,6 +415,55 @@ static void prepare_multi(const float *cloud, int n, const int *scan_start, cons
   if (t_down) *t_down = t2 - t1;
 }
 
+// ---- online extrinsic calibration step (Estimator::optimizeMap with ESTIMATE_EXTRINSIC == 1, estimator.cpp:687-787, with the
+// association of buildCalibMap :1135-1149 redone at every outer iteration).  Blocks: pivot (constant, :631), pose_i, ext_ref
+// (constant, :642), ext_cal.  Reference LiDAR features of frame i: matched at pivot^-1 * pose_i * ext_ref with n_neigh 5,
+// CHECK_FOV true -> LidarPureOdom{PlaneNorm,Edge}Factor(point, coeffs, 1.0) on (pivot, pose_i, ext_ref) (:696-703, :746-754).
+// Calibrated LiDAR features at the pivot: matched at ext_cal with n_neigh 10, CHECK_FOV true -> LidarOnlineCalib{PlaneNorm,Edge}Factor
+// (point, coeffs, 1.0) on ext_cal (:733-737, :776-779).  HuberLoss(huber_a) (:602), ceres::Solve(max_inner) per outer iteration.
+// surf_map_cal / corner_map_cal: the calibrated LiDAR's own local map (leaf 0.2, :1103-1109); n == 0 -> the reference maps.
+// stats[4]: lm_iterations, final_cost, residual rows of the last problem, termination
+void orc_calib_frame(const float *surf_map, int n_sm, const float *corner_map, int n_cm, const float *surf_map_cal, int n_smc,
+                     const float *corner_map_cal, int n_cmc, const float *surf_ref, int n_sr, const float *corner_ref, int n_cr,
+                     const float *surf_cal, int n_sc, const float *corner_cal, int n_cc, const double *pivot7, double *pose_i7,
+                     const double *ext_ref7, double *ext_cal7, int max_outer, int max_inner, double huber_a, const double *opts, double *stats) {
+  Cloud sm = to_cloud(surf_map, n_sm), cm = to_cloud(corner_map, n_cm), smc = to_cloud(surf_map_cal, n_smc), cmc = to_cloud(corner_map_cal, n_cmc);
+  Cloud sr = to_cloud(surf_ref, n_sr), cr = to_cloud(corner_ref, n_cr), sc = to_cloud(surf_cal, n_sc), cc = to_cloud(corner_cal, n_cc);
+  KdTree kd_s, kd_c, kd_sc, kd_cc;
+  kd_s.setInputCloud(&sm), kd_c.setInputCloud(&cm);
+  const bool own = n_smc > 0 && n_cmc > 0;
+  if (own) kd_sc.setInputCloud(&smc), kd_cc.setInputCloud(&cmc);
+  const MatchParams mp = mp_from(opts);
+  double xp[7], xr[7];
+  std::memcpy(xp, pivot7, sizeof(xp)), std::memcpy(xr, ext_ref7, sizeof(xr));
+  int its = 0, rows = 0, term = 0;
+  double cost = 0;
+  for (int outer = 0; outer < max_outer; outer++) {
+    const Pose pose_a = pose_mul(pose_inv(to_pose(xp)), pose_mul(to_pose(pose_i7), to_pose(xr)));  // :1086-1090
+    const Pose pose_b = to_pose(ext_cal7);
+    std::vector<Feature> f_sr, f_cr, f_sc, f_cc;
+    match_from_map('s', kd_s, sm, sr, pose_a, f_sr, 5, true, mp);
+    match_from_map('c', kd_c, cm, cr, pose_a, f_cr, 5, true, mp);
+    match_from_map('s', own ? kd_sc : kd_s, own ? smc : sm, sc, pose_b, f_sc, 10, true, mp);
+    match_from_map('c', own ? kd_cc : kd_c, own ? cmc : cm, cc, pose_b, f_cc, 10, true, mp);
+    Problem pr;
+    pr.huber_a = huber_a;
+    const int ip = pr.add_param(xp, true), ii = pr.add_param(pose_i7), ir = pr.add_param(xr, true), ie = pr.add_param(ext_cal7);
+    for (const Feature &f : f_sr)
+      pr.blocks.push_back(ResidualBlock{F_ODOM_PLANE, f.point, {f.coeffs[0], f.coeffs[1], f.coeffs[2], f.coeffs[3], 0, 0}, 1.0, {ip, ii, ir}});
+    for (const Feature &f : f_sc)
+      pr.blocks.push_back(ResidualBlock{F_PLANE, f.point, {f.coeffs[0], f.coeffs[1], f.coeffs[2], f.coeffs[3], 0, 0}, 1.0, {ie, 0, 0}});
+    for (const Feature &f : f_cr)
+      pr.blocks.push_back(ResidualBlock{F_ODOM_EDGE, f.point, {f.coeffs[0], f.coeffs[1], f.coeffs[2], f.coeffs[3], f.coeffs[4], f.coeffs[5]}, 1.0, {ip, ii, ir}});
+    for (const Feature &f : f_cc)
+      pr.blocks.push_back(ResidualBlock{F_EDGE, f.point, {f.coeffs[0], f.coeffs[1], f.coeffs[2], f.coeffs[3], f.coeffs[4], f.coeffs[5]}, 1.0, {ie, 0, 0}});
+    rows = (int)pr.blocks.size();
+    SolveSummary s = solve(pr, max_inner);
+    its += s.iterations, cost = s.final_cost, term = s.termination;
+  }
+  if (stats) stats[0] = its, stats[1] = cost, stats[2] = rows, stats[3] = term;
+}
+
 // ---- Estimator::optimizeMap residual blocks for one frame / one LiDAR (estimator.cpp:687-848): LidarPureOdom factors on
 // (pose_pivot [constant], pose_i, ext_n); free_mask bit 0 frees pose_i, bit 1 frees ext.  ceres::Solve(max_it),
 // HuberLoss(huber_a).  stats[3]: lm_iterations, final_cost, termination

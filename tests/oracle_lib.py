@@ -307,6 +307,24 @@ def set_gf_groups(surf_sizes=None, corner_sizes=None):
     lib().orc_set_gf_groups(int(s.shape[0]), _p(s), _p(c))
 
 
+def calib_frame(surf_map, corner_map, surf_ref, corner_ref, surf_cal, corner_cal, pivot, pose_i, ext_ref, ext_cal, max_outer=2, max_inner=4,
+                huber_a=1.0, surf_map_cal=None, corner_map_cal=None, opts=None):
+    """Online extrinsic calibration step (orc_calib_frame).  Returns (pose_i, ext_cal, stats)."""
+    e4 = np.zeros((0, 4), np.float32)
+    arrs = [cloud(x) if x is not None and len(x) else e4 for x in (surf_map, corner_map, surf_map_cal, corner_map_cal, surf_ref, corner_ref, surf_cal, corner_cal)]
+    opts = default_opts() if opts is None else np.ascontiguousarray(opts, np.float64)
+    pv = np.ascontiguousarray(pivot, np.float64)
+    pi = np.array(pose_i, np.float64)
+    er = np.ascontiguousarray(ext_ref, np.float64)
+    ec = np.array(ext_cal, np.float64)
+    st = np.zeros(4)
+    args = []
+    for a in arrs:
+        args += [_p(a), a.shape[0]]
+    lib().orc_calib_frame(*args, _p(pv), _p(pi), _p(er), _p(ec), max_outer, max_inner, C.c_double(huber_a), _p(opts), _p(st))
+    return pi, ec, {"lm_iterations": int(st[0]), "final_cost": st[1], "rows": int(st[2]), "termination": int(st[3])}
+
+
 def use_ref_tree(on: bool = True) -> bool:
     """Timed CPU arm only: build / search the kd-trees with the reference's nanoflann (oracle/_ref/libref_knn.so)."""
     path = os.path.join(ORC_DIR, "_ref", "libref_knn.so")

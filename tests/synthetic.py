@@ -351,3 +351,37 @@ def make_submap_keyframes(scene: Scene, n_total: int, extract_cloud, voxel_grid,
 
     n_edge = n_total // 10
     return resample(surf_f, n_total - n_edge), resample(corner_f, n_edge), {"filtered_surf": int(surf_f.shape[0]), "filtered_corner": int(corner_f.shape[0])}
+
+
+# ----------------------------------------------------------------------------- online-calibration case (config C3)
+def transform_cloud(cloud: np.ndarray, T: np.ndarray) -> np.ndarray:
+    """T * p for a float32 [n,4] cloud (double math, float store; intensity kept)."""
+    out = cloud.copy()
+    out[:, :3] = (cloud[:, :3].astype(np.float64) @ quat_to_mat(T[3:]).T + T[:3]).astype(np.float32)
+    return out
+
+
+def make_calib_case(scene: Scene, extract_cloud, voxel_grid, n_rings: int, horizon: int, map_points: int, seed: int = 31, submap=None):
+    """Inputs of one online-calibration step (Estimator::optimizeMap, ESTIMATE_EXTRINSIC == 1): the local map in the PIVOT frame, the
+    reference LiDAR's features of a later frame i, the second LiDAR's features at the pivot frame (both sensor frame, window-level
+    down-sampling 0.2 / 0.4, estimator.cpp:485-496), truth and perturbed initial values (ext_cal off by 2 deg / 5 cm)."""
+    traj = trajectory(10)
+    pivot, pose_i = traj[3], traj[7]
+    ext = rig_extrinsics(2)
+    surf_w, corner_w = submap if submap is not None else make_submap(scene, map_points)
+    Pinv = pose_inv(pivot)
+    surf_map, corner_map = transform_cloud(surf_w, Pinv), transform_cloud(corner_w, Pinv)
+
+    def feats(pose, e, sd):
+        cloud, ss, se = make_sweep(scene, pose, n_rings, horizon, seed=sd, lidar_id=0 if e is ext[0] else 1, ext=e)
+        f = extract_cloud(cloud, ss, se)
+        return voxel_grid(f["surf_points_less_flat"], 0.4, False)[0], voxel_grid(f["corner_points_less_sharp"], 0.2, False)[0]
+
+    surf_ref, corner_ref = feats(pose_i, ext[0], seed)
+    surf_cal, corner_cal = feats(pivot, ext[1], seed + 1)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pose_i_init = perturb_pose(pose_i, rng)
+    d = math.radians(2.0) / math.sqrt(3.0)
+    ext_init = pose_mul(ext[1], pose7([0.03, -0.03, 0.027], quat_from_rpy(d, -d, d)))
+    return dict(surf_map=surf_map, corner_map=corner_map, surf_ref=surf_ref, corner_ref=corner_ref, surf_cal=surf_cal, corner_cal=corner_cal,
+                pivot=pivot, pose_i=pose_i, ext_ref=ext[0], ext_cal=ext[1], pose_i_init=pose_i_init, ext_cal_init=ext_init)

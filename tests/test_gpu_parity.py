@@ -397,6 +397,33 @@ def test_extract_128_rings(ctx):
         assert np.array_equal(got[k], ref[k]), k
 
 
+# ------------------------------------------------------------------------------------------------ online extrinsic calibration (C3)
+@pytest.mark.parametrize("rings,horizon,map_pts,outer,inner", [(16, 1024, 100_000, 10, 1), (16, 1024, 100_000, 2, 4), (64, 2048, 2_000_000, 10, 1)])
+def test_calib_frame_matches_oracle(ctx, rings, horizon, map_pts, outer, inner):
+    """12-DoF step [pose_i | ext_cal]: buildCalibMap's association (n_neigh 5 / 10, CHECK_FOV true) + LidarPureOdom rows of the
+    reference LiDAR + LidarOnlineCalib rows of the second LiDAR, both groups in one context (one GPU).  The last case is BASELINE
+    config C3's size (64-ring sweeps, 2M-point map, 10 iterations)."""
+    scene = syn.make_scene()
+    cs = syn.make_calib_case(scene, orc.extract_cloud, orc.voxel_grid, rings, horizon, map_pts)
+    ctx.map_build(0, cs["corner_map"], 0.25)
+    ctx.map_build(1, cs["surf_map"], 0.25)
+    pi, ec, st = ctx.calib_frame(cs["surf_ref"], cs["corner_ref"], cs["surf_cal"], cs["corner_cal"], cs["pivot"], cs["pose_i_init"], cs["ext_ref"],
+                                 cs["ext_cal_init"], outer, inner)
+    rpi, rec, rst = orc.calib_frame(cs["surf_map"], cs["corner_map"], cs["surf_ref"], cs["corner_ref"], cs["surf_cal"], cs["corner_cal"], cs["pivot"],
+                                    cs["pose_i_init"], cs["ext_ref"], cs["ext_cal_init"], outer, inner)
+    assert st["n_surf"] == rst["rows"] and st["lm_iterations"] == rst["lm_iterations"]
+    for got, ref in ((pi, rpi), (ec, rec)):
+        dt, dr = syn.pose_err(got, ref)
+        assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
+    # the step does calibrate: the 2 deg error of the initial extrinsic shrinks
+    assert syn.pose_err(ec, cs["ext_cal"])[1] < 0.5 * syn.pose_err(cs["ext_cal_init"], cs["ext_cal"])[1]
+    # one group at a time (what each rank of the 2-GPU run evaluates) is the 6-DoF sub-problem of that group
+    pi_only, ec_same, _ = ctx.calib_frame(cs["surf_ref"], cs["corner_ref"], None, None, cs["pivot"], cs["pose_i_init"], cs["ext_ref"], cs["ext_cal_init"], outer, inner)
+    rpi_only, _, _ = orc.calib_frame(cs["surf_map"], cs["corner_map"], cs["surf_ref"], cs["corner_ref"], None, None, cs["pivot"], cs["pose_i_init"],
+                                     cs["ext_ref"], cs["ext_cal_init"], outer, inner)
+    assert np.allclose(ec_same, cs["ext_cal_init"], atol=1e-12) and max(syn.pose_err(pi_only, rpi_only)) <= POSE_TOL_T
+
+
 # ------------------------------------------------------------------------------------------------ scan-to-scan (tracker)
 @pytest.fixture(scope="module")
 def two_sweeps():

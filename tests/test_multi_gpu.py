@@ -92,6 +92,19 @@ def test_two_gpu_frame_parity(exchange):
     assert out.returncode == 0 and "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+@pytest.mark.gpu
+def test_two_gpu_calibration_parity():
+    """12-DoF online calibration sharded over two GPUs (one LiDAR each) with the NCCL all-reduce of the 12x12 normal equations."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run tests/multi_gpu_calib_check.py under torchrun with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "multi_gpu_calib_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTI_GPU_CALIB_CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_peer_exchange_protocol_model():
     """Model of lm_tail's peer-memory exchange (solve_kernels.cu): per rank an exchange buffer with slots[2][N] and
     flags[2][N], double-buffered by epoch parity; a rank publishes its contribution into every rank's slot[parity][me],
