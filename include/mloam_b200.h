@@ -278,6 +278,12 @@ int mloam_comm_destroy(mloam_ctx_t *ctx);
  * init: handles = nranks x 64 bytes gathered by the caller (rank order).  Falls back to NCCL when not initialised. */
 int mloam_comm_p2p_export(mloam_ctx_t *ctx, void *handle64);
 int mloam_comm_p2p_init(mloam_ctx_t *ctx, int nranks, int rank, const void *handles);
+/* The exchange is collective: every rank must run the same sequence of mloam_frame* / mloam_scan2map* calls (the map-size gate
+ * depends on the replicated maps only).  Solves that belong to one rank alone (mloam_track_cloud, mloam_odom_solve,
+ * mloam_normal_equations) never exchange.  A rank that waits ~3 s for a peer, or finds a peer AHEAD of the exchange it expects
+ * (lost lock-step), ends the solve with termination 9 and the call returns MLOAM_E_NCCL on that rank; recover by calling
+ * mloam_comm_p2p_reset on every rank between two host-side barriers. */
+int mloam_comm_p2p_reset(mloam_ctx_t *ctx);
 
 #ifdef __cplusplus
 }

@@ -141,6 +141,19 @@ int mloam_comm_p2p_init(mloam_ctx_t *h, int nranks, int rank, const void *handle
   return MLOAM_OK;
 }
 
+// Re-synchronise after a failed exchange (termination 9): every rank calls this BETWEEN two host barriers (no rank may be inside
+// a collective solve); flags, slots and the epoch of the local buffer go back to zero, so all ranks restart at exchange 0.
+int mloam_comm_p2p_reset(mloam_ctx_t *h) {
+  if (!h) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  if (!c->p2p_local) return MLOAM_OK;
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+  MLOAM_CUDA_OK(c, cudaMemset(c->p2p_local, 0, MLOAM_P2P_BYTES));
+  MLOAM_CUDA_OK(c, cudaDeviceSynchronize());
+  return MLOAM_OK;
+}
+
 int mloam_comm_destroy(mloam_ctx_t *h) {
   if (!h) return MLOAM_E_INVALID;
   Ctx *c = &h->c;

@@ -188,6 +188,7 @@ struct Ctx {
   void *p2p_peer[MLOAM_P2P_MAX_RANKS] = {nullptr};
   void *p2p_view = nullptr;        // device copy of the P2PView the kernels read
   bool p2p_on = false;
+  bool p2p_collective = false;     // the solve being enqueued is the collective one (all ranks in lock-step): sum over the ranks
 };
 
 // RAII-less helper: bracket a kernel (or a few) with events when profiling is on.

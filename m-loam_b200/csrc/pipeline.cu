@@ -27,6 +27,14 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
   if (!MS.built || !MC.built) return fail(c, MLOAM_E_STATE, "scan2map: build MLOAM_MAP_SURF and MLOAM_MAP_CORNER first");
   if (!((MS.m > 50) && (MC.m > 10))) return MLOAM_OK;  // lidar_mapper_keyframe.cpp:429 ("Map surf num is not enough")
   c->s2m_ran = 1;
+  // Collective participation: the gate above depends on the replicated maps only, so every rank takes the same branch; from here
+  // on every rank enqueues the same number of LM evaluations (max_outer x (1 + max_inner) with max_inner == 1; with max_inner > 1
+  // the done flag all ranks poll is the identical, summed state).  Per-rank solves (tracker, odometry) never set the flag.
+  struct CollectiveScope {
+    Ctx *c;
+    explicit CollectiveScope(Ctx *cc) : c(cc) { c->p2p_collective = true; }
+    ~CollectiveScope() { c->p2p_collective = false; }
+  } collective_scope(c);
   int rc = reserve_feat(c, 0, S.n_corner);
   if (rc) return rc;
   rc = reserve_feat(c, 1, S.n_surf);
@@ -106,6 +114,12 @@ int scan2map_finish(Ctx *c, const ScanRef &S, const double *pose_init7, double *
   if (!S.d_n_surf) h_cnt[0] = S.n_surf;
   if (!S.d_n_corner) h_cnt[1] = S.n_corner;
   for (int k = 0; k < 7; k++) pose_out7[k] = hs->x[k];
+  if (hs->termination == 9) {  // the peer-memory exchange timed out or the ranks lost lock-step: the summed state is not trustworthy
+    for (int k = 0; k < 7; k++) pose_out7[k] = pose_init7[k];
+    if (stats) stats->ran = 1, stats->termination = 9;
+    return fail(c, MLOAM_E_NCCL, "scan2map: peer-memory exchange failed (a rank did not arrive or the ranks lost lock-step); "
+                                  "call mloam_comm_p2p_reset on every rank behind a barrier");
+  }
   if (c->prof_on) {  // device-side cycle counters of the fused LM tail, reported next to the event-timed stages
     int khz = 0;
     cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);

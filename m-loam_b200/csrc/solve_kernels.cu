@@ -539,7 +539,13 @@ __device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMSta
       *reinterpret_cast<volatile unsigned *>(p2p->flags[threadIdx.x] + par * MLOAM_P2P_MAX_RANKS + me) = target;  // notify rank threadIdx.x
       volatile unsigned *mine = reinterpret_cast<volatile unsigned *>(p2p->flags[me] + par * MLOAM_P2P_MAX_RANKS + threadIdx.x);
       const long long w0 = clock64();
-      while ((int)(*mine - target) < 0) {
+      while (true) {
+        const unsigned v = *mine;
+        if (v == target) break;
+        if ((int)(v - target) > 0) {  // the peer is AHEAD of this exchange: the ranks lost lock-step, its slot holds a later sum
+          p2p_timeout = 2;
+          break;
+        }
         if (clock64() - w0 > 6000000000ll) {  // ~3 s: a peer never showed up
           p2p_timeout = 1;
           break;
@@ -639,8 +645,11 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
     c->ticket_zeroed_for = c->partials.p;
   }
   const double eig_thre = c->lm_eig_thre >= 0.0 ? c->lm_eig_thre : c->params.eig_thre;
-  const bool fused = lm_mode != 0 && (!c->nccl_comm || c->p2p_on) && !d_out30;
-  a.p2p = (fused && c->p2p_on) ? static_cast<const P2PView *>(c->p2p_view) : nullptr;
+  const bool collective = c->nccl_comm && c->p2p_collective;  // sum over the ranks wanted for this solve
+  const bool fused = lm_mode != 0 && (!collective || c->p2p_on) && !d_out30;
+  // only the collective solves (scan2map on every rank in lock-step) exchange; per-rank solves on the same context — the tracker,
+  // mloam_normal_equations — stay local (c->p2p_collective is raised by scan2map_enqueue alone)
+  a.p2p = (fused && c->p2p_on && c->p2p_collective) ? static_cast<const P2PView *>(c->p2p_view) : nullptr;
   a.lm_mode = fused ? lm_mode : 0, a.want_eig = want_eig, a.eig_thre = eig_thre, a.ticket = ticket;
   a.state_rw = c->lm_state.as<LMState>();
   {
@@ -652,7 +661,7 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
     MLOAM_CUDA_OK(c, cudaGetLastError());
     return MLOAM_OK;
   }
-  if (c->nccl_comm && lm_mode != 0) {
+  if (collective && lm_mode != 0) {
     // multi-GPU: rank-local sum -> NCCL all-reduce of the 30 packed doubles -> identical LM step on every rank
     double *ne = c->partials.as<double>() + (size_t)NE_PACK * max_nb;
     {
