@@ -23,6 +23,7 @@ namespace mloam {
 
 constexpr int GF_THREADS = 1024;
 constexpr int kGfMaxRandomQueue = 20;  // MAX_RANDOM_QUEUE_TIME, lidar_mapper.h:83
+constexpr int kGfSmemInts = 50 * 1024;  // 200 KB of dynamic shared memory for the candidate pool (one CTA per launch)
 
 __global__ void k_gf_jaco(const float4 *__restrict__ pts, const unsigned char *__restrict__ valid, const float *__restrict__ coeff, int n,
                           const int *__restrict__ d_n, int is_plane, const float *__restrict__ cov6, const double *__restrict__ sinfo,
@@ -122,6 +123,7 @@ struct GfArgs {
   int *sel;      // out, selection order
   int *n_sel;    // out
   double *H;     // out 36
+  int smem_ints; // words of dynamic shared memory the launch provides for the pool
 };
 
 __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
@@ -132,13 +134,24 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
   __shared__ int cand[32];
   const int tid = threadIdx.x, lane = tid & 31;
   const int n = a.d_n ? min(a.n, *a.d_n) : a.n;
+  // The selection is a chain of dependent pool operations (16-step Fenwick descents, visited marks) issued by ONE thread: in
+  // global memory every step is an L2 round trip (~4 us per pick measured); the pool lives in shared memory whenever it fits
+  // (a.smem_ints words of dynamic shared memory: Fenwick tree first, then the visited marks).
+  extern __shared__ int gf_smem[];
+  int *const fen = (n + 1 <= a.smem_ints) ? gf_smem : a.fen;
+  int *const visited = (2 * n + 1 <= a.smem_ints) ? gf_smem + (n + 1) : a.visited;
+  const bool matched_in_smem = 2 * n + 1 + (n + 3) / 4 <= a.smem_ints;
+  unsigned char *const matched_s = reinterpret_cast<unsigned char *>(gf_smem + (2 * n + 1));
+  if (matched_in_smem)
+    for (int i = tid; i < n; i += GF_THREADS) matched_s[i] = a.matched[i];
+  const unsigned char *const matched = matched_in_smem ? matched_s : a.matched;
   if (a.mask)
     for (int i = tid; i < n; i += GF_THREADS) a.mask[i] = 0;
   const int num_use = (int)((size_t)((size_t)n * a.gf_ratio));  // static_cast<size_t>(num_all_features * gf_ratio), :248
   if (tid < 36) H[tid] = (tid % 7 == 0) ? 1e-6 : 0.0;              // sub_mat_H = I * 1e-6 (:504, :519)
   if (tid == 0) s_num_sel = 0, s_stop = 0, s_pick = -1;
-  for (int i = tid; i <= n; i += GF_THREADS) a.fen[i] = i & -i;    // Fenwick tree of an all-ones array
-  for (int i = tid; i < n; i += GF_THREADS) a.visited[i] = a.method == 2 ? 0 : -1, a.dist[i] = 1e5f;
+  for (int i = tid; i <= n; i += GF_THREADS) fen[i] = i & -i;    // Fenwick tree of an all-ones array
+  for (int i = tid; i < n; i += GF_THREADS) visited[i] = a.method == 2 ? 0 : -1, a.dist[i] = 1e5f;
   __syncthreads();
   int top = 1;
   while (top * 2 <= n) top *= 2;
@@ -148,7 +161,7 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
     if (tid == 0) {
       int k = 0;
       for (int q = 0; q < n; q++)
-        if (a.matched[q]) gf_add_outer(H, a.jaco + (size_t)q * 6), a.sel[k++] = q;
+        if (matched[q]) gf_add_outer(H, a.jaco + (size_t)q * 6), a.sel[k++] = q;
       s_num_sel = k;
     }
   } else if (a.method == 1) {  // rnd (:300-346)
@@ -156,9 +169,9 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
       int k = 0, size = n;
       while (k < num_use && size > 0) {
         const int j = gf_uniform(rng, 0, size - 1);
-        const int q = fen_find_kth(a.fen, n, top, j);
-        if (a.matched[q]) gf_add_outer(H, a.jaco + (size_t)q * 6), a.sel[k++] = q;
-        fen_remove(a.fen, n, q);
+        const int q = fen_find_kth(fen, n, top, j);
+        if (matched[q]) gf_add_outer(H, a.jaco + (size_t)q * 6), a.sel[k++] = q;
+        fen_remove(fen, n, q);
         size--;
       }
       s_num_sel = k;
@@ -168,8 +181,8 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
       int old = 0;
       if (tid == 0) {
         const int k0 = gf_uniform(rng, 0, n - 1);
-        a.visited[k0] = 1;
-        if (a.matched[k0]) a.sel[0] = k0, s_num_sel = 1;  // selected, but never added to sub_mat_H (:375-379)
+        visited[k0] = 1;
+        if (matched[k0]) a.sel[0] = k0, s_num_sel = 1;  // selected, but never added to sub_mat_H (:375-379)
         s_pick = k0;
       }
       __syncthreads();
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
         float best_d = -1.0f;
         int best_j = 0x7fffffff;
         for (int j = tid; j < n; j += GF_THREADS) {
-          if (a.visited[j]) continue;
+          if (visited[j]) continue;
           const float4 pn = a.pts[j];
           const float dx = po.x - pn.x, dy = po.y - pn.y, dz = po.z - pn.z;
           const float d = sqrtf(dx * dx + dy * dy + dz * dz);
@@ -204,8 +217,8 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
           for (int w = 1; w < GF_THREADS / 32; w++)
             if (red_d[w] > bd || (red_d[w] == bd && red_j[w] < bj)) bd = red_d[w], bj = red_j[w];
           const int q = bj;
-          a.visited[q] = 1;
-          if (a.matched[q]) gf_add_outer(H, a.jaco + (size_t)q * 6), a.sel[s_num_sel] = q, s_num_sel = s_num_sel + 1;
+          visited[q] = 1;
+          if (matched[q]) gf_add_outer(H, a.jaco + (size_t)q * 6), a.sel[s_num_sel] = q, s_num_sel = s_num_sel + 1;
           s_pick = q;
         }
         __syncthreads();
@@ -232,16 +245,16 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
             int j = 0, q = -1;
             while (num_rnd_que < kGfMaxRandomQueue) {
               j = gf_uniform(rng, 0, size - 1);
-              q = fen_find_kth(a.fen, n, top, j);
-              if (a.visited[q] < num_sel) {
-                a.visited[q] = num_sel;
+              q = fen_find_kth(fen, n, top, j);
+              if (visited[q] < num_sel) {
+                visited[q] = num_sel;
                 break;
               }
               num_rnd_que++;
             }
             if (num_rnd_que >= kGfMaxRandomQueue) break;
-            if (!a.matched[q]) {  // "not found constraints or outlier constraints" (:518-523): leaves the pool
-              fen_remove(a.fen, n, q);
+            if (!matched[q]) {  // "not found constraints or outlier constraints" (:518-523): leaves the pool
+              fen_remove(fen, n, q);
               size--;
               continue;
             }
@@ -257,7 +270,8 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
         int order = 0x7fffffff, cidx = -1;
         if (lane < n_cand) {
           cidx = cand[lane];
-          sc = gf_logdet_with(H, a.jaco + (size_t)cidx * 6);
+          // a round of ONE candidate (gf_ratio > 0.5: size_rnd_subset == 1) picks it whatever its score: skip the 6x6 Cholesky
+          sc = size_rnd_subset > 1 ? gf_logdet_with(H, a.jaco + (size_t)cidx * 6) : 0.0;
           order = heap_n + lane;
         }
 #pragma unroll
@@ -271,9 +285,12 @@ __global__ void __launch_bounds__(GF_THREADS) k_gf_select(GfArgs a) {
         heap_n += n_cand;
         __syncwarp();
         if (heap_n >= size_rnd_subset && heap_n > 0) {  // pop the heap's top: the round's pick
+          {  // sub_mat_H += J^T J: one element per lane (the same single addition per element as the sequential loop)
+            const double *jb = a.jaco + (size_t)best_idx * 6;
+            for (int e = lane; e < 36; e += 32) H[e] += jb[e / 6] * jb[e % 6];
+          }
           if (lane == 0) {
-            gf_add_outer(H, a.jaco + (size_t)best_idx * 6);
-            fen_remove(a.fen, n, best_idx);
+            fen_remove(fen, n, best_idx);
             a.sel[num_sel] = best_idx;
           }
           size--;
@@ -324,7 +341,12 @@ int gf_select_set_device(Ctx *c, int t, const FeatSet &fs, const double *d_pose7
   a.mask = reinterpret_cast<unsigned char *>(p + o_mask);
   {
     ProfScope ps(c, "gf_select");
-    k_gf_select<<<1, GF_THREADS, 0, c->stream>>>(a);
+    a.smem_ints = kGfSmemInts;
+    if (!c->smem_opt_in_gf) {
+      MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_gf_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kGfSmemInts * (int)sizeof(int)));
+      c->smem_opt_in_gf = true;
+    }
+    k_gf_select<<<1, GF_THREADS, kGfSmemInts * sizeof(int), c->stream>>>(a);
   }
   c->launches += 2;
   MLOAM_CUDA_OK(c, cudaGetLastError());
@@ -382,7 +404,12 @@ extern "C" int mloam_good_features(mloam_ctx_t *h, int slot, int type, const mlo
   a.sel = reinterpret_cast<int *>(p + o_sel), a.n_sel = reinterpret_cast<int *>(p + o_ns), a.H = reinterpret_cast<double *>(p + o_H);
   {
     ProfScope ps(c, "gf_select");
-    k_gf_select<<<1, GF_THREADS, 0, c->stream>>>(a);
+    a.smem_ints = kGfSmemInts;
+    if (!c->smem_opt_in_gf) {
+      MLOAM_CUDA_OK(c, cudaFuncSetAttribute(k_gf_select, cudaFuncAttributeMaxDynamicSharedMemorySize, kGfSmemInts * (int)sizeof(int)));
+      c->smem_opt_in_gf = true;
+    }
+    k_gf_select<<<1, GF_THREADS, kGfSmemInts * sizeof(int), c->stream>>>(a);
   }
   c->launches += 2;
   MLOAM_CUDA_OK(c, cudaGetLastError());

@@ -68,14 +68,25 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
     // the solve below only sees the selected ones.  Corner first, then surf, as in the reference.
     sets[0].mask = sets[1].mask = nullptr;
     if (P.gf_method != 0) {
+      // the two selections are independent single-CTA chains: corner on the side stream next to surf (also inside a captured graph)
+      const bool fork_gf = !c->prof_on && sets[0].n > 0 && sets[1].n > 0;
+      if (fork_gf) {
+        MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_fork3, c->stream));
+        MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream3, c->ev_fork3, 0));
+      }
       for (int t = 0; t < 2; t++) {
         if (sets[t].n <= 0) continue;
         unsigned char *mask = nullptr;
+        cudaStream_t main_stream = c->stream;
+        if (fork_gf && t == 0) c->stream = c->stream3;
         rc = gf_select_set_device(c, t, sets[t], d_pose, sinfo, P.gf_method, (double)P.gf_ratio,
                                   (unsigned long long)P.gf_seed + 2ull * (unsigned long long)outer + (unsigned long long)t, &mask);
+        c->stream = main_stream;
         if (rc) return rc;
+        if (fork_gf && t == 0) MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_join3, c->stream3));
         sets[t].mask = mask;
       }
+      if (fork_gf) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join3, 0));
     }
     // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve.  The device
     // only needs the degeneracy decision; scan2map_finish fills in the eigenvalue report of the last iteration.
