@@ -561,6 +561,27 @@ def main():
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
+    # ---- N > 1: the BASELINE configurations differ from N to N (calibration at 2, 128 rings + feature selection at 8), so their
+    # values do not form a scaling curve.  A compact second measurement keeps one: the same number of 64-ring LiDARs as GPUs,
+    # plain scan2MapOptimization, the configuration's submap size ("C2-like x N", what round 1 reported).
+    probe = None
+    if world > 1 and (cfg["calib"] or cfg["gf_method"] or cfg["rings"] != 64):
+        pc = dict(CONFIGS["C2"], lidars=world, map_points=cfg["map_points"])
+        saved = None
+        if rank == 0:
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+        try:
+            P = gpu_measure(m, syn, torch, dist, "C2-like", pc, args, rank, local_rank, world, min(args.steps, 20), args.warmup, 4, full=False)
+        finally:
+            if saved is not None:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+        probe = {"workload": f"C2-like x {world}: one 64-ring x 2048 LiDAR per GPU, {pc['map_points']}-pt submap, 10 GN iterations, no calibration / feature selection",
+                 "value": P["value"], "unit": "frames/s", "ms_per_step": 1e3 * P["t_max"] / min(args.steps, 20), "e2e": P["e2e"], "exchange": P["exchange"],
+                 "exchange_timeouts": P["exchange_timeouts"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -641,6 +662,8 @@ def main():
         line["knn_queries_per_step_by_path"] = R["knn_paths"]
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if probe is not None:
+        line["weak_scaling_probe"] = probe
     # ---- the north star's target configuration next to the default one: C4 (4 x 64-ring LiDARs, 5M-point submap) on ONE GPU
     if world == 1 and cfg_name == "C2" and not args.no_c4:
         c4 = dict(CONFIGS["C4"])

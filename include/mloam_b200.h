@@ -243,7 +243,7 @@ int mloam_odom_solve(mloam_ctx_t *ctx, int n, const unsigned char *h_types, cons
  *     MLOAM_MAP_CORNER / MLOAM_MAP_SURF with n_neigh = 5, CHECK_FOV = true (:1135-1149) and enter as LidarPureOdom{PlaneNorm,Edge}Factor
  *     on (pivot, pose_i, ext_ref) — 1x6 rows on pose_i;
  *   calibrated LiDAR, pivot frame : features are matched at ext_cal (n_neigh = 10, CHECK_FOV = true) against slots
- *     MLOAM_MAP_SCAN_CORNER / MLOAM_MAP_SCAN_SURF when those are built (its own local map, leaf 0.2, :1103-1109), else the same maps,
+ *     MLOAM_MAP_SCAN_CORNER / MLOAM_MAP_SCAN_SURF when own_cal_maps != 0 (its own local map, leaf 0.2, :1103-1109), else the same maps,
  *     and enter as LidarOnlineCalib{PlaneNorm,Edge}Factor on ext_cal (lidar_online_calib_factor.hpp:24-227) — 1x6 rows on ext_cal.
  * Either group may be empty: with a communicator (mloam_comm_init) rank 0 passes the reference LiDAR's features, rank 1 the
  * calibrated LiDAR's, and the packed 12x12 normal equations (92 doubles) are summed with one ncclAllReduce per LM evaluation
@@ -252,7 +252,7 @@ int mloam_odom_solve(mloam_ctx_t *ctx, int n, const unsigned char *h_types, cons
 int mloam_calib_frame(mloam_ctx_t *ctx, const mloam_point_t *h_surf_ref, int n_surf_ref, const mloam_point_t *h_corner_ref,
                       int n_corner_ref, const mloam_point_t *h_surf_cal, int n_surf_cal, const mloam_point_t *h_corner_cal,
                       int n_corner_cal, const double *pose_pivot7, double *pose_i7, const double *ext_ref7, double *ext_cal7,
-                      int max_outer, int max_inner, double huber_a, mloam_solve_stats_t *stats);
+                      int max_outer, int max_inner, double huber_a, int own_cal_maps, mloam_solve_stats_t *stats);
 
 /* ---- ActiveFeatureSelection::goodFeatureMatching for one feature set (lidar_mapper.h:229-573; Estimator::goodFeatureMatching,
  * estimator.cpp:1347-1517): match every feature of `h_pts` against map `slot` at pose7, evaluate its 1x6 Jacobian row

@@ -336,7 +336,7 @@ class Context:
         return out, st.as_dict()
 
     def calib_frame(self, surf_ref, corner_ref, surf_cal, corner_cal, pivot7, pose_i7, ext_ref7, ext_cal7, max_outer: int = 2, max_inner: int = 4,
-                    huber_a: float = 1.0):
+                    huber_a: float = 1.0, own_cal_maps: bool = False):
         sr, cr, sc, cc = (None if x is None or len(x) == 0 else _cloud(x) for x in (surf_ref, corner_ref, surf_cal, corner_cal))
         n = [0 if x is None else x.shape[0] for x in (sr, cr, sc, cc)]
         pv = np.ascontiguousarray(pivot7, np.float64)
@@ -345,7 +345,7 @@ class Context:
         ec = np.array(ext_cal7, np.float64)
         st = SolveStats()
         self._ck(lib().mloam_calib_frame(self._h, _p(sr), n[0], _p(cr), n[1], _p(sc), n[2], _p(cc), n[3], _p(pv), _p(pi), _p(er), _p(ec),
-                                         max_outer, max_inner, C.c_double(huber_a), C.byref(st)))
+                                         max_outer, max_inner, C.c_double(huber_a), int(own_cal_maps), C.byref(st)))
         return pi, ec, st.as_dict()
 
     def odom_solve(self, types, points, coeffs, pivot7, pose_i7, ext7, free_mask: int, max_iterations: int = 4, huber_a: float = 1.0,

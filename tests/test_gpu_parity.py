@@ -422,6 +422,17 @@ def test_calib_frame_matches_oracle(ctx, rings, horizon, map_pts, outer, inner):
     rpi_only, _, _ = orc.calib_frame(cs["surf_map"], cs["corner_map"], cs["surf_ref"], cs["corner_ref"], None, None, cs["pivot"], cs["pose_i_init"],
                                      cs["ext_ref"], cs["ext_cal_init"], outer, inner)
     assert np.allclose(ec_same, cs["ext_cal_init"], atol=1e-12) and max(syn.pose_err(pi_only, rpi_only)) <= POSE_TOL_T
+    if rings == 16 and inner == 1:
+        # the calibrated LiDAR's OWN local map (buildCalibMap filters it with leaf 0.2, estimator.cpp:1103-1109) in the scan slots
+        surf_c, _ = orc.voxel_grid(cs["surf_map"], 0.2, False)
+        corner_c, _ = orc.voxel_grid(cs["corner_map"], 0.2, False)
+        ctx.map_build(2, corner_c, 0.25)
+        ctx.map_build(3, surf_c, 0.25)
+        pi2, ec2, st2 = ctx.calib_frame(cs["surf_ref"], cs["corner_ref"], cs["surf_cal"], cs["corner_cal"], cs["pivot"], cs["pose_i_init"], cs["ext_ref"],
+                                        cs["ext_cal_init"], outer, inner, own_cal_maps=True)
+        rpi2, rec2, rst2 = orc.calib_frame(cs["surf_map"], cs["corner_map"], cs["surf_ref"], cs["corner_ref"], cs["surf_cal"], cs["corner_cal"], cs["pivot"],
+                                           cs["pose_i_init"], cs["ext_ref"], cs["ext_cal_init"], outer, inner, surf_map_cal=surf_c, corner_map_cal=corner_c)
+        assert st2["n_surf"] == rst2["rows"] and max(syn.pose_err(ec2, rec2) + syn.pose_err(pi2, rpi2)) <= POSE_TOL_T
 
 
 # ------------------------------------------------------------------------------------------------ scan-to-scan (tracker)
