@@ -189,6 +189,11 @@ int mloam_profile_get(mloam_ctx_t *h, const char *name, double *ms_total, long l
   Ctx *c = &h->c;
   cudaStreamSynchronize(c->stream);
   prof_collect(c);
+  if (!strcmp(name, "graph_capture_failures")) {  // frames that ran on the stream path because their graph capture failed
+    if (ms_total) *ms_total = 0.0;
+    if (launches) *launches = c->graph_capture_failures;
+    return MLOAM_OK;
+  }
   // query counts / SM cycles of the matcher's search paths (k_match_knn), reported through `launches`
   if (!strncmp(name, "knn_slow_rec", 12) && name[12] >= '0' && name[12] <= '9') {
     long long v = 0;

@@ -354,9 +354,9 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
       }
       if (graph) cudaGraphDestroy(graph);
       cudaGetLastError();
-      e->exec = nullptr, e->seen = 0;  // capture failed: fall through to the stream path
-      c->launches = l0;
-      if (rc) return rc;
+      e->exec = nullptr, e->seen = 0;  // capture failed (e.g. a buffer had to grow, which is illegal while capturing): run this frame on
+      c->launches = l0;                // the plain stream path below — it performs the allocation — and capture at a later sighting
+      c->graph_capture_failures++;
     } else if (!e) {
       if (c->graphs.size() >= 32) {
         if (c->graphs.front().exec) cudaGraphExecDestroy(c->graphs.front().exec);

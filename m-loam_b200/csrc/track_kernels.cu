@@ -152,8 +152,8 @@ int track_cloud_device(Ctx *c, const float4 *d_prev_less_sharp, int n_pls, const
                        const float4 *d_cur_sharp, int n_cs, const float4 *d_cur_flat, int n_cf, const double *pose_ini7,
                        double *pose_out7, mloam_solve_stats_t *stats) {
   if (stats) memset(stats, 0, sizeof(*stats));
-  // :27-34 kd-trees over the previous sweep's less-sharp / less-flat features.  Cell 1.3 m: a 4-cell block (5.2 m)
-  // covers the DISTANCE_SQ_THRESHOLD = 25 search ball.
+  // :27-34 kd-trees over the previous sweep's less-sharp / less-flat features.  Cell 1.3 m: the nearest neighbour of a tracked
+  // feature is almost always inside the 27-cell neighbourhood; the shells of knn.cuh cover the rest of the 5 m ball.
   const float cell = fmaxf(0.26f, sqrtf(c->params.distance_sq_threshold) * 0.26f);
   int rc = map_build_device(c, MLOAM_MAP_SCAN_CORNER, d_prev_less_sharp, n_pls, cell);
   if (rc) return rc;
@@ -165,14 +165,18 @@ int track_cloud_device(Ctx *c, const float4 *d_prev_less_sharp, int n_pls, const
   if (rc) return rc;
   const int max_outer = 2, max_inner = 4;  // :44, :114
   const double huber_a = 0.1;              // :47
-  c->lm_min_corr = 10;                     // :64-68
-  c->lm_eig_thre = 0.0;                    // evalDegenracy is commented out in trackCloud (:101-108)
+  // per-solve settings travel through context fields that lm_init_state / linearize_device read: restored on every exit path
+  struct SolveSettings {
+    Ctx *c;
+    explicit SolveSettings(Ctx *cc) : c(cc) {
+      c->lm_min_corr = 10;  // :64-68
+      c->lm_eig_thre = 0.0; // evalDegenracy is commented out in trackCloud (:101-108)
+    }
+    ~SolveSettings() { c->lm_min_corr = 0, c->lm_eig_thre = -1.0, c->want_eig = 1; }
+  } settings(c);
   rc = lm_init_state(c, pose_ini7, max_inner, 0.0);
   c->lm_min_corr = 0;
-  if (rc) {
-    c->lm_eig_thre = -1.0;
-    return rc;
-  }
+  if (rc) return rc;
   LMState *st = c->lm_state.as<LMState>();
   int *h_done = reinterpret_cast<int *>(reinterpret_cast<char *>(c->pinned) + 2048);
   FeatSet sets[2] = {FeatSet{d_cur_sharp, c->feat_valid[0].as<unsigned char>(), c->feat_coeff[0].as<float>(), n_cs, 2, nullptr},

@@ -74,3 +74,13 @@ def test_cpp_host_shim_compiles_links_and_refuses_to_run_without_gpu(mloam):
         pytest.skip("a GPU is present (the gpu-marked test runs the binary)")
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 2 and "no CPU path" in out.stdout
+
+
+def test_wire_format_helpers_selftest():
+    """m-loam_b200/host/mloam_io.hpp (PointCloud2 <-> float4, mloam_msgs PODs, TUM dump): host-only, checked by its own self-test."""
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(ROOT, "m-loam_b200", "host", "io_selftest")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "m-loam_b200"), "host/io_selftest"], stdout=subprocess.DEVNULL)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "io_selftest OK" in out.stdout, out.stdout + out.stderr
