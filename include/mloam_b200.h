@@ -186,6 +186,31 @@ int mloam_scan2map_ua(mloam_ctx_t *ctx, const mloam_point_t *h_surf_scan, int n_
                       const mloam_point_t *h_corner_scan, int n_corner, const float *h_corner_cov6, const double *pose_init7,
                       double *pose_out7, mloam_solve_stats_t *stats);
 
+/* ---- submap assembly with uncertainty: the data path of extractSurroundingKeyFrames (lidar_mapper_keyframe.cpp:254-354).
+ * Pose covariances are row-major 6x6 in the reference's order [translation | rotation].
+ * mloam_compound_pose_cov: compoundPoseWithCov (associate_uct.hpp:9-88, method 2), host-side: pose_out = pose1 * pose2 with its covariance.
+ * mloam_cloud_uct_associate: cloudUCTAssociateToMap (:1116-1158) for one keyframe cloud (intensity = laser id): per point
+ *   pose_ext[id]^-1 -> evalPointUncertainty under pose_compound[id] / cov_compound[id] (= compoundPoseWithCov(pose_global, pose_ext[id]))
+ *   -> dropped when trace > trace_threshold (TRACE_THRESHOLD_MAPPING) -> pointAssociateToMap with pose_global -> updateCov.  with_ua = 0:
+ *   no gate, zero covariance.  Outputs (capacity n): points, cov_vec (xx xy xz yy yz zz), cov_trace, in input order.
+ * mloam_voxel_downsample_cov: VoxelGridCovarianceMLOAM<PointIWithCov>::filter — the covariance-weighted merge per voxel
+ *   (voxel_grid_covariance_mloam_impl.hpp:293-333): w = trace_threshold - trace, points with |trace| >= trace_threshold skipped.
+ * mloam_submap_assemble: n_keyframes clouds (concatenated, counts[k] points each) -> cloudUCTAssociateToMap with poses7[k] and the
+ *   per-(keyframe, LiDAR) compounds (pose_compound7 / cov_compound36: n_keyframes x n_lasers) -> merged -> VoxelGridCovarianceMLOAM(leaf,
+ *   trace_threshold_filter) -> installed in map slot `slot` (setInputCloud) without leaving the device.  h_out / h_cov6_out (nullable,
+ *   capacity = sum of counts) receive the submap; *n_out its size. */
+int mloam_compound_pose_cov(const double *pose1_7, const double *cov1_36, const double *pose2_7, const double *cov2_36, double *pose_out7,
+                            double *cov_out36);
+int mloam_cloud_uct_associate(mloam_ctx_t *ctx, const mloam_point_t *h_pts, int n, const double *pose_global7, int n_lasers, const double *ext7,
+                              const double *pose_compound7, const double *cov_compound36, const double *cov_meas9, int with_ua,
+                              double trace_threshold, mloam_point_t *h_out, float *h_cov6_out, float *h_trace_out, int *n_out);
+int mloam_voxel_downsample_cov(mloam_ctx_t *ctx, const mloam_point_t *h_pts, const float *h_cov6, const float *h_trace, int n, float leaf,
+                               float trace_threshold, mloam_point_t *h_out, float *h_cov6_out, float *h_trace_out, int *n_out);
+int mloam_submap_assemble(mloam_ctx_t *ctx, int slot, int n_keyframes, const mloam_point_t *h_pts, const int *counts, const double *poses7,
+                          int n_lasers, const double *ext7, const double *pose_compound7, const double *cov_compound36, const double *cov_meas9,
+                          int with_ua, double trace_threshold_assoc, float leaf, float trace_threshold_filter, float map_cell,
+                          mloam_point_t *h_out, float *h_cov6_out, int *n_out);
+
 /* ---- the whole per-scan hot path for one LiDAR sweep (extractCloud -> scan down-sampling ->
  * scan2MapOptimization), inputs in host memory (mloam_frame) or already resident in HBM
  * (mloam_frame_device).  rebuild_maps != 0 re-runs setInputCloud on the two maps first, as the reference

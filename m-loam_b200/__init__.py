@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
-    "mloam_frame_device", "mloam_set_extrinsic", "mloam_set_lidars", "mloam_calib_frame", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init", "mloam_comm_p2p_reset",
+    "mloam_frame_device", "mloam_set_extrinsic", "mloam_set_lidars", "mloam_calib_frame", "mloam_compound_pose_cov", "mloam_cloud_uct_associate", "mloam_voxel_downsample_cov", "mloam_submap_assemble", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init", "mloam_comm_p2p_reset",
 ]
 
 
@@ -172,6 +172,9 @@ class Context:
 
     def map_build_device(self, slot: int, d_ptr: int, m: int, cell: float = 0.0):
         self._ck(lib().mloam_map_build_device(self._h, slot, C.c_void_p(d_ptr), m, C.c_float(cell)))
+
+    def map_size(self, slot: int) -> int:
+        return int(lib().mloam_map_size(self._h, slot))
 
     def knn(self, slot: int, q, k: int, max_sqdist: float, pose7=None):
         q = _cloud(q)
@@ -347,6 +350,64 @@ class Context:
         self._ck(lib().mloam_calib_frame(self._h, _p(sr), n[0], _p(cr), n[1], _p(sc), n[2], _p(cc), n[3], _p(pv), _p(pi), _p(er), _p(ec),
                                          max_outer, max_inner, C.c_double(huber_a), int(own_cal_maps), C.byref(st)))
         return pi, ec, st.as_dict()
+
+    # ---- submap assembly with uncertainty
+    @staticmethod
+    def compound_pose_cov(p1, cov1, p2, cov2):
+        a, b = np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p2, np.float64)
+        c1, c2 = np.ascontiguousarray(cov1, np.float64).reshape(36), np.ascontiguousarray(cov2, np.float64).reshape(36)
+        po, co = np.zeros(7), np.zeros(36)
+        rc = lib().mloam_compound_pose_cov(_p(a), _p(c1), _p(b), _p(c2), _p(po), _p(co))
+        if rc != 0:
+            raise MloamError(f"mloam_compound_pose_cov: {rc}")
+        return po, co.reshape(6, 6)
+
+    def cloud_uct_associate(self, pts, pose_global, ext, pose_compound, cov_compound, cov_meas, with_ua: bool = True, trace_threshold: float = 200.0):
+        pts = _cloud(pts)
+        n = pts.shape[0]
+        ext = np.ascontiguousarray(ext, np.float64).reshape(-1, 7)
+        pc = np.ascontiguousarray(pose_compound, np.float64).reshape(-1, 7)
+        cc = np.ascontiguousarray(cov_compound, np.float64).reshape(-1, 36)
+        cm = np.ascontiguousarray(cov_meas, np.float64).reshape(9)
+        pg = np.ascontiguousarray(pose_global, np.float64)
+        op, oc, ot = np.zeros((max(n, 1), 4), np.float32), np.zeros((max(n, 1), 6), np.float32), np.zeros(max(n, 1), np.float32)
+        no = C.c_int(0)
+        self._ck(lib().mloam_cloud_uct_associate(self._h, _p(pts), n, _p(pg), ext.shape[0], _p(ext), _p(pc), _p(cc), _p(cm), int(with_ua),
+                                                 C.c_double(trace_threshold), _p(op), _p(oc), _p(ot), C.byref(no)))
+        return op[:no.value].copy(), oc[:no.value].copy(), ot[:no.value].copy()
+
+    def voxel_downsample_cov(self, pts, cov6, trace, leaf: float, trace_threshold: float):
+        pts = _cloud(pts)
+        n = pts.shape[0]
+        c6 = np.ascontiguousarray(cov6, np.float32).reshape(-1, 6)
+        tr = np.ascontiguousarray(trace, np.float32)
+        op, oc, ot = np.zeros((max(n, 1), 4), np.float32), np.zeros((max(n, 1), 6), np.float32), np.zeros(max(n, 1), np.float32)
+        no = C.c_int(0)
+        self._ck(lib().mloam_voxel_downsample_cov(self._h, _p(pts), _p(c6), _p(tr), n, C.c_float(leaf), C.c_float(trace_threshold), _p(op), _p(oc),
+                                                  _p(ot), C.byref(no)))
+        return op[:no.value].copy(), oc[:no.value].copy(), ot[:no.value].copy()
+
+    def submap_assemble(self, slot: int, clouds, poses7, ext, pose_compound, cov_compound, cov_meas, leaf: float, with_ua: bool = True,
+                        trace_threshold_assoc: float = 200.0, trace_threshold_filter: float = 200.0, map_cell: float = 0.0, want_output: bool = True):
+        """clouds: list of [n_k,4] keyframe clouds; poses7 [K,7]; pose_compound [K,L,7]; cov_compound [K,L,36]."""
+        clouds = [_cloud(x) for x in clouds]
+        counts = np.ascontiguousarray([x.shape[0] for x in clouds], np.int32)
+        allp = _cloud(np.concatenate(clouds)) if clouds else np.zeros((0, 4), np.float32)
+        n = allp.shape[0]
+        poses = np.ascontiguousarray(poses7, np.float64).reshape(-1, 7)
+        ext = np.ascontiguousarray(ext, np.float64).reshape(-1, 7)
+        pc = np.ascontiguousarray(pose_compound, np.float64).reshape(-1, 7)
+        cc = np.ascontiguousarray(cov_compound, np.float64).reshape(-1, 36)
+        cm = np.ascontiguousarray(cov_meas, np.float64).reshape(9)
+        op = np.zeros((max(n, 1), 4), np.float32) if want_output else None
+        oc = np.zeros((max(n, 1), 6), np.float32) if want_output else None
+        no = C.c_int(0)
+        self._ck(lib().mloam_submap_assemble(self._h, slot, len(clouds), _p(allp), _p(counts), _p(poses), ext.shape[0], _p(ext), _p(pc), _p(cc), _p(cm),
+                                             int(with_ua), C.c_double(trace_threshold_assoc), C.c_float(leaf), C.c_float(trace_threshold_filter),
+                                             C.c_float(map_cell), _p(op), _p(oc), C.byref(no)))
+        if not want_output:
+            return no.value
+        return op[:no.value].copy(), oc[:no.value].copy()
 
     def odom_solve(self, types, points, coeffs, pivot7, pose_i7, ext7, free_mask: int, max_iterations: int = 4, huber_a: float = 1.0,
                    sqrt_info: float = 1.0):

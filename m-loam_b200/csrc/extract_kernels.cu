@@ -61,7 +61,7 @@ __global__ void k_prim_scan_apply(const int *__restrict__ in, int n, const int *
 }
 
 // exclusive scan d_in[0..n) -> d_out (may alias), optional device total.  tmp must hold ceil(n/PRIM_TILE) ints.
-static void scan_exclusive(Ctx *c, const int *d_in, int *d_out, int n, int *d_tmp, int *d_total) {
+void scan_exclusive(Ctx *c, const int *d_in, int *d_out, int n, int *d_tmp, int *d_total) {
   if (n <= 0) {
     if (d_total) cudaMemsetAsync(d_total, 0, sizeof(int), c->stream);
     return;
@@ -312,6 +312,69 @@ __global__ void k_centroids(const float4 *__restrict__ pts, const unsigned long 
   out[slot[i]] = make_float4(sx / cnt, sy / cnt, sz / cnt, intensity_last ? last : si / cnt);
 }
 
+// VoxelGridCovarianceMLOAM<PointIWithCov>: the covariance-weighted merge of a voxel (voxel_grid_covariance_mloam_impl.hpp:293-333),
+// one thread per run head, float arithmetic in the reference's order: w = thr - trace (points with |trace| >= thr are skipped),
+// mu += w * xyz, intensity of the heaviest point, cov(7) += (w * w) * [cov_vec | cov_trace], then / W and / (W * W);
+// the output trace is recomputed from the merged diagonal (:332).
+struct CovIO {
+  const float *cov6_in;    // n * 6
+  const float *trace_in;   // n
+  float *cov6_out, *trace_out;
+  float trace_threshold;
+  const SegBox *box;       // the cloud's bounding box: the int32-overflow case copies the input through (:92-101)
+  float inv;
+};
+__global__ void k_centroids_cov(const float4 *__restrict__ pts, const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals,
+                                const int *__restrict__ head, const int *__restrict__ slot, int n, const int *__restrict__ d_n_valid, CovIO io,
+                                float4 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d_n_valid) n = min(n, *d_n_valid);
+  if (i >= n || !head[i]) return;
+  const unsigned long long k = keys[i];
+  {
+    const SegBox b = io.box[0];
+    const float mn0 = ord2f(b.mn[0]), mn1 = ord2f(b.mn[1]), mn2 = ord2f(b.mn[2]);
+    const float mx0 = ord2f(b.mx[0]), mx1 = ord2f(b.mx[1]), mx2 = ord2f(b.mx[2]);
+    const long long dx = (long long)((mx0 - mn0) * io.inv) + 1, dy = (long long)((mx1 - mn1) * io.inv) + 1, dz = (long long)((mx2 - mn2) * io.inv) + 1;
+    if (dx * dy * dz > 2147483647ll) {  // "leaf size is too small": output = input (every point is its own run here)
+      const unsigned q = vals[i];
+      const int o = slot[i];
+      out[o] = pts[q];
+#pragma unroll
+      for (int a = 0; a < 6; a++) io.cov6_out[(size_t)o * 6 + a] = io.cov6_in[(size_t)q * 6 + a];
+      io.trace_out[o] = io.trace_in[q];
+      return;
+    }
+  }
+  float mu0 = 0.f, mu1 = 0.f, mu2 = 0.f, ity = 0.f, wt = 0.f, w_max = 0.f;
+  float cov[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = i; j < n && keys[j] == k; j++) {
+    const unsigned q = vals[j];
+    const float4 p = pts[q];
+    const float *c6 = io.cov6_in + (size_t)q * 6;
+    const float tr = c6[0] + c6[3] + c6[5];
+    if (fabsf(tr) >= io.trace_threshold) continue;
+    const float w = io.trace_threshold - tr;
+    mu0 = mu0 + w * p.x, mu1 = mu1 + w * p.y, mu2 = mu2 + w * p.z;
+    ity = w > w_max ? p.w : ity;
+    w_max = w > w_max ? w : w_max;
+    const float ww = w * w;
+#pragma unroll
+    for (int a = 0; a < 6; a++) cov[a] = cov[a] + ww * c6[a];
+    cov[6] = cov[6] + ww * io.trace_in[q];
+    wt = wt + w;
+  }
+  if (wt == 0.f) wt = 1.0f;
+  const float w2 = wt * wt;
+  const int o = slot[i];
+  out[o] = make_float4(mu0 / wt, mu1 / wt, mu2 / wt, ity);
+#pragma unroll
+  for (int a = 0; a < 6; a++) cov[a] = cov[a] / w2;
+#pragma unroll
+  for (int a = 0; a < 6; a++) io.cov6_out[(size_t)o * 6 + a] = cov[a];
+  io.trace_out[o] = cov[0] + cov[3] + cov[5];
+}
+
 // Shared voxel pipeline.  scratch layout is owned by the caller (VoxelWork).
 struct VoxelWork {
   SegBox *box;
@@ -321,7 +384,7 @@ struct VoxelWork {
   unsigned *ticket;
 };
 static int voxel_pipeline(Ctx *c, const float4 *d_pts, const int *d_seg, const int *d_seg_begin, int n, const int *d_n_valid,
-                          int n_seg, float leaf, int intensity_last, VoxelWork w, float4 *d_out, int *d_n_out) {
+                          int n_seg, float leaf, int intensity_last, VoxelWork w, float4 *d_out, int *d_n_out, const CovIO *cov = nullptr) {
   cudaStream_t st = c->stream;
   if (n <= 0) {
     cudaMemsetAsync(d_n_out, 0, sizeof(int), st);
@@ -344,7 +407,12 @@ static int voxel_pipeline(Ctx *c, const float4 *d_pts, const int *d_seg, const i
   k_run_heads<<<nb, 256, 0, st>>>(ks, n, d_n_valid, w.head);
   c->launches++;
   scan_exclusive(c, w.head, w.slot, n, w.tmp, d_n_out);
-  k_centroids<<<nb, 256, 0, st>>>(d_pts, ks, vs, w.head, w.slot, n, d_n_valid, intensity_last, d_out);
+  if (cov) {
+    CovIO io = *cov;
+    io.box = w.box, io.inv = inv;
+    k_centroids_cov<<<nb, 256, 0, st>>>(d_pts, ks, vs, w.head, w.slot, n, d_n_valid, io, d_out);
+  }
+  else k_centroids<<<nb, 256, 0, st>>>(d_pts, ks, vs, w.head, w.slot, n, d_n_valid, intensity_last, d_out);
   c->launches++;
   return MLOAM_OK;
 }
@@ -406,6 +474,24 @@ int voxel_downsample_device(Ctx *c, const float4 *d_in, int n, const int *d_n_in
   int rc = voxel_work_reserve(c, c->scratch[work_slot], n, 1, &w);
   if (rc) return rc;
   rc = voxel_pipeline(c, d_in, nullptr, nullptr, n, d_n_in, 1, leaf, intensity_last, w, d_out, d_n_out);
+  if (rc) return rc;
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  return MLOAM_OK;
+}
+
+// VoxelGridCovarianceMLOAM<PointIWithCov>::filter (lidar_mapper_keyframe.cpp:344-347): always the radix pipeline.
+int voxel_downsample_cov_device(Ctx *c, const float4 *d_in, const float *d_cov6, const float *d_trace, int n, const int *d_n_in, float leaf,
+                                float trace_threshold, float4 *d_out, float *d_cov6_out, float *d_trace_out, int *d_n_out, int work_slot) {
+  if (!(leaf > 0.f) || n < 0) {
+    c->err = "voxel_downsample_cov: bad leaf / size";
+    return MLOAM_E_INVALID;
+  }
+  ProfScope ps(c, "voxel_cov");
+  VoxelWork w;
+  int rc = voxel_work_reserve(c, c->scratch[work_slot], n, 1, &w);
+  if (rc) return rc;
+  CovIO io{d_cov6, d_trace, d_cov6_out, d_trace_out, trace_threshold, nullptr, 0.f};
+  rc = voxel_pipeline(c, d_in, nullptr, nullptr, n, d_n_in, 1, leaf, 0, w, d_out, d_n_out, &io);
   if (rc) return rc;
   MLOAM_CUDA_OK(c, cudaGetLastError());
   return MLOAM_OK;

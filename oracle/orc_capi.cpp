@@ -4,6 +4,7 @@
 // [tx ty tz qx qy qz qw].  Never linked into the product library.
 #include "orc_pipeline.hpp"
 #include "orc_gf.hpp"
+#include "orc_uct.hpp"
 #include <cstdio>
 #ifdef _OPENMP
 #include <omp.h>
@@ -462,6 +463,52 @@ void orc_calib_frame(const float *surf_map, int n_sm, const float *corner_map, i
     its += s.iterations, cost = s.final_cost, term = s.termination;
   }
   if (stats) stats[0] = its, stats[1] = cost, stats[2] = rows, stats[3] = term;
+}
+
+// ---- submap assembly with uncertainty (orc_uct.hpp)
+void orc_compound_pose_cov(const double *p1, const double *cov1, const double *p2, const double *cov2, double *pose_out7, double *cov_out36) {
+  M6 c1, c2, cc;
+  std::memcpy(c1.m, cov1, sizeof(c1.m)), std::memcpy(c2.m, cov2, sizeof(c2.m));
+  // the reference's Pose objects are normalised on construction; the product is not re-normalised (associate_uct.hpp:37-38)
+  const Pose a = to_pose(p1), b = to_pose(p2);
+  Pose pc;
+  compound_pose_with_cov(a, c1, b, c2, pc, cc);
+  pose_to_param(pc, pose_out7);
+  std::memcpy(cov_out36, cc.m, sizeof(cc.m));
+}
+// cloud: [n,4] (intensity = laser id); ext7 / pose_compound7: n_lasers x 7; cov_compound: n_lasers x 36.  out_*: capacity n.
+void orc_cloud_uct_associate(const float *cloud, int n, const double *pose_global7, int n_lasers, const double *ext7, const double *pose_compound7,
+                             const double *cov_compound36, const double *cov_meas9, int with_ua, double trace_threshold, float *out_pts,
+                             float *out_cov6, float *out_trace, int *n_out) {
+  Cloud c = to_cloud(cloud, n);
+  std::vector<Pose> pe, pc;
+  std::vector<M6> cc(n_lasers);
+  for (int l = 0; l < n_lasers; l++) {
+    pe.push_back(to_pose(ext7 + 7 * l)), pc.push_back(to_pose(pose_compound7 + 7 * l));
+    std::memcpy(cc[l].m, cov_compound36 + 36 * l, sizeof(cc[l].m));
+  }
+  CovCloud o;
+  cloud_uct_associate(c, to_pose(pose_global7), pe, pc, cc, cov_meas9, with_ua != 0, trace_threshold, o);
+  *n_out = (int)o.pts.size();
+  if (*n_out) {
+    std::memcpy(out_pts, o.pts.data(), sizeof(PointI) * o.pts.size());
+    std::memcpy(out_cov6, o.cov6.data(), sizeof(float) * o.cov6.size());
+    std::memcpy(out_trace, o.trace.data(), sizeof(float) * o.trace.size());
+  }
+}
+int orc_voxel_grid_cov(const float *pts, const float *cov6, const float *trace, int n, float leaf, float trace_threshold, float *out_pts, float *out_cov6,
+                       float *out_trace, int *n_out) {
+  CovCloud in, o;
+  in.pts = to_cloud(pts, n);
+  in.cov6.assign(cov6, cov6 + 6 * (size_t)n), in.trace.assign(trace, trace + n);
+  const bool ok = voxel_grid_cov(in, leaf, trace_threshold, o);
+  *n_out = (int)o.pts.size();
+  if (*n_out) {
+    std::memcpy(out_pts, o.pts.data(), sizeof(PointI) * o.pts.size());
+    std::memcpy(out_cov6, o.cov6.data(), sizeof(float) * o.cov6.size());
+    std::memcpy(out_trace, o.trace.data(), sizeof(float) * o.trace.size());
+  }
+  return ok ? 1 : 0;
 }
 
 // ---- Estimator::optimizeMap residual blocks for one frame / one LiDAR (estimator.cpp:687-848): LidarPureOdom factors on

@@ -325,6 +325,43 @@ def calib_frame(surf_map, corner_map, surf_ref, corner_ref, surf_cal, corner_cal
     return pi, ec, {"lm_iterations": int(st[0]), "final_cost": st[1], "rows": int(st[2]), "termination": int(st[3])}
 
 
+def compound_pose_cov(p1, cov1, p2, cov2):
+    """compoundPoseWithCov (method 2): returns (pose7, cov 6x6) of p1 * p2."""
+    a, b = np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p2, np.float64)
+    c1, c2 = np.ascontiguousarray(cov1, np.float64).reshape(36), np.ascontiguousarray(cov2, np.float64).reshape(36)
+    po, co = np.zeros(7), np.zeros(36)
+    lib().orc_compound_pose_cov(_p(a), _p(c1), _p(b), _p(c2), _p(po), _p(co))
+    return po, co.reshape(6, 6)
+
+
+def cloud_uct_associate(cloud_, pose_global, ext, pose_compound, cov_compound, cov_meas, with_ua=True, trace_threshold=200.0):
+    """cloudUCTAssociateToMap: returns (points [m,4], cov6 [m,6], trace [m])."""
+    pts = cloud(cloud_)
+    n = pts.shape[0]
+    ext = np.ascontiguousarray(ext, np.float64).reshape(-1, 7)
+    pc = np.ascontiguousarray(pose_compound, np.float64).reshape(-1, 7)
+    cc = np.ascontiguousarray(cov_compound, np.float64).reshape(-1, 36)
+    cm = np.ascontiguousarray(cov_meas, np.float64).reshape(9)
+    pg = np.ascontiguousarray(pose_global, np.float64)
+    op, oc, ot = np.zeros((n, 4), np.float32), np.zeros((n, 6), np.float32), np.zeros(n, np.float32)
+    no = C.c_int(0)
+    lib().orc_cloud_uct_associate(_p(pts), n, _p(pg), ext.shape[0], _p(ext), _p(pc), _p(cc), _p(cm), int(with_ua), C.c_double(trace_threshold),
+                                  _p(op), _p(oc), _p(ot), C.byref(no))
+    return op[:no.value].copy(), oc[:no.value].copy(), ot[:no.value].copy()
+
+
+def voxel_grid_cov(pts, cov6, trace, leaf, trace_threshold):
+    """VoxelGridCovarianceMLOAM<PointIWithCov>::filter: returns (points, cov6, trace, ok)."""
+    p = cloud(pts)
+    n = p.shape[0]
+    c6 = np.ascontiguousarray(cov6, np.float32).reshape(-1, 6)
+    tr = np.ascontiguousarray(trace, np.float32)
+    op, oc, ot = np.zeros((max(n, 1), 4), np.float32), np.zeros((max(n, 1), 6), np.float32), np.zeros(max(n, 1), np.float32)
+    no = C.c_int(0)
+    ok = lib().orc_voxel_grid_cov(_p(p), _p(c6), _p(tr), n, C.c_float(leaf), C.c_float(trace_threshold), _p(op), _p(oc), _p(ot), C.byref(no))
+    return op[:no.value].copy(), oc[:no.value].copy(), ot[:no.value].copy(), bool(ok)
+
+
 def use_ref_tree(on: bool = True) -> bool:
     """Timed CPU arm only: build / search the kd-trees with the reference's nanoflann (oracle/_ref/libref_knn.so)."""
     path = os.path.join(ORC_DIR, "_ref", "libref_knn.so")

@@ -435,6 +435,100 @@ def test_calib_frame_matches_oracle(ctx, rings, horizon, map_pts, outer, inner):
         assert st2["n_surf"] == rst2["rows"] and max(syn.pose_err(ec2, rec2) + syn.pose_err(pi2, rpi2)) <= POSE_TOL_T
 
 
+# ------------------------------------------------------------------------------------------------ submap assembly with uncertainty (f2)
+def _uct_case(n_kf=4, n_lasers=2):
+    scene = syn.make_scene()
+    traj = syn.trajectory(n_kf + 2)
+    ext = syn.rig_extrinsics(n_lasers)
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(6, 6)) * 0.01
+    cov_pose = A @ A.T + np.eye(6) * 1e-5                      # keyframe pose covariance [translation | rotation]
+    cov_ext = [np.zeros((6, 6))] + [np.eye(6) * (1e-4 * (l + 1)) for l in range(1, n_lasers)]
+    cov_meas = np.eye(3) * 0.0025
+    clouds, poses, pcs, ccs = [], [], [], []
+    for k in range(n_kf):
+        parts = []
+        for l in range(n_lasers):
+            c, ss, se = syn.make_sweep(scene, traj[k + 1], 16, 512, seed=300 + k, lidar_id=l, ext=ext[l])
+            f = orc.extract_cloud(c, ss, se)
+            surf_l = orc.associate(f["surf_points_less_flat"], ext[l])   # keyframe features are stored in the base frame, laser id in the intensity
+            surf_l[:, 3] = l
+            parts.append(surf_l)
+        clouds.append(np.ascontiguousarray(np.concatenate(parts)))
+        poses.append(traj[k + 1])
+        pk, ck = [], []
+        for l in range(n_lasers):
+            p, cv = orc.compound_pose_cov(traj[k + 1], cov_pose * (1 + 0.3 * k), ext[l], cov_ext[l])
+            pk.append(p), ck.append(cv)
+        pcs.append(pk), ccs.append(ck)
+    return dict(clouds=clouds, poses=np.array(poses), ext=ext, pose_compound=np.array(pcs), cov_compound=np.array(ccs), cov_meas=cov_meas,
+                cov_pose=cov_pose, cov_ext=cov_ext)
+
+
+def test_compound_pose_cov_and_uct_associate(ctx, mloam):
+    u = _uct_case()
+    # compoundPoseWithCov: host-side algebra of the library vs the oracle restatement
+    for l in range(2):
+        p, cv = mloam.Context.compound_pose_cov(u["poses"][1], u["cov_pose"], u["ext"][l], u["cov_ext"][l])
+        rp, rcv = orc.compound_pose_cov(u["poses"][1], u["cov_pose"], u["ext"][l], u["cov_ext"][l])
+        assert np.allclose(p, rp, rtol=0, atol=1e-15) and np.allclose(cv, rcv, rtol=1e-13, atol=1e-18)
+    # cloudUCTAssociateToMap: a threshold that drops part of the cloud; points bit-exact, covariances to float rounding
+    k = 2
+    args = (u["clouds"][k], u["poses"][k], u["ext"], u["pose_compound"][k], u["cov_compound"][k], u["cov_meas"])
+    _, _, tr_all = orc.cloud_uct_associate(*args, with_ua=True, trace_threshold=1e9)
+    thr = float(np.percentile(tr_all, 70))
+    gp, gc, gt = ctx.cloud_uct_associate(*args, with_ua=True, trace_threshold=thr)
+    rp, rc, rt = orc.cloud_uct_associate(*args, with_ua=True, trace_threshold=thr)
+    assert 0 < rp.shape[0] < u["clouds"][k].shape[0] and gp.shape == rp.shape
+    assert np.array_equal(gp, rp)
+    assert np.allclose(gc, rc, rtol=2e-6, atol=1e-12) and np.allclose(gt, rt, rtol=2e-6)
+    gp0, gc0, _ = ctx.cloud_uct_associate(*args, with_ua=False)
+    rp0, rc0, _ = orc.cloud_uct_associate(*args, with_ua=False)
+    assert np.array_equal(gp0, rp0) and not gc0.any() and not rc0.any()
+
+
+def test_voxel_downsample_cov_bit_exact(ctx):
+    # the reference's own 4-point example (mloam_test/src/test_pointiwithcov.cpp:23-40): leaf 3, trace threshold 2
+    pts = np.array([[0, 0, 0, 0], [1, 0, 0, 0], [0, 1, 0, 0], [1, 1, 0, 0]], np.float32)
+    cov6 = np.zeros((4, 6), np.float32)
+    cov6[3, 0] = 1
+    trace = cov6[:, 0] + cov6[:, 3] + cov6[:, 5]
+    gp, gc, gt = ctx.voxel_downsample_cov(pts, cov6, trace, 3.0, 2.0)
+    assert gp.shape[0] == 1 and np.allclose(gp[0, :3], [3 / 7, 3 / 7, 0]) and np.isclose(gc[0, 0], 1 / 49)
+    # a real merged cloud: bit-exact against the oracle, including voxels whose points are all above the threshold
+    u = _uct_case()
+    k = 1
+    p, c6, tr = orc.cloud_uct_associate(u["clouds"][k], u["poses"][k], u["ext"], u["pose_compound"][k], u["cov_compound"][k], u["cov_meas"], True, 1e9)
+    thr = float(np.percentile(tr, 90))
+    for leaf in (0.4, 1.0):
+        gp, gc, gt = ctx.voxel_downsample_cov(p, c6, tr, leaf, thr)
+        rp, rc, rt, ok = orc.voxel_grid_cov(p, c6, tr, leaf, thr)
+        assert ok and gp.shape == rp.shape and rp.shape[0] < p.shape[0]
+        assert np.array_equal(gp, rp) and np.array_equal(gc, rc) and np.array_equal(gt, rt)
+
+
+def test_submap_assemble_on_device(ctx):
+    """extractSurroundingKeyFrames' data path for one map: 4 keyframes x 2 LiDARs -> cloudUCTAssociateToMap -> merged ->
+    VoxelGridCovarianceMLOAM -> map slot; the installed map answers kNN queries like a map built from the oracle's submap."""
+    u = _uct_case()
+    thr_a, leaf, thr_f = 50.0, 0.4, 50.0
+    gp, gc = ctx.submap_assemble(1, u["clouds"], u["poses"], u["ext"], u["pose_compound"], u["cov_compound"], u["cov_meas"], leaf, True, thr_a, thr_f, 0.5)
+    mp, mc, mt = [], [], []
+    for k in range(len(u["clouds"])):
+        p, c6, tr = orc.cloud_uct_associate(u["clouds"][k], u["poses"][k], u["ext"], u["pose_compound"][k], u["cov_compound"][k], u["cov_meas"], True, thr_a)
+        mp.append(p), mc.append(c6), mt.append(tr)
+    rp, rc, rt, ok = orc.voxel_grid_cov(np.concatenate(mp), np.concatenate(mc), np.concatenate(mt), leaf, thr_f)
+    assert ok and gp.shape == rp.shape and np.array_equal(gp, rp)
+    assert np.allclose(gc, rc, rtol=1e-5, atol=1e-12)   # covariances enter the merge with float rounding of the device's double sums
+    assert ctx.map_size(1) == rp.shape[0]
+    q = rp[::7].copy()
+    q[:, :3] += 0.05
+    idx, sqd = ctx.knn(1, q, 5, 4.0)
+    ridx, rsqd = orc.knn(rp, q, 5)
+    inside = rsqd < 4.0
+    assert np.array_equal(idx[inside], ridx[inside]) and np.array_equal(sqd[inside], rsqd[inside])
+
+
 # ------------------------------------------------------------------------------------------------ scan-to-scan (tracker)
 @pytest.fixture(scope="module")
 def two_sweeps():
