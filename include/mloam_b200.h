@@ -291,6 +291,25 @@ int mloam_good_features(mloam_ctx_t *ctx, int slot, int type, const mloam_point_
                         const double *pose7, int method, double gf_ratio, unsigned long long seed, int *h_sel, int *n_sel,
                         double *H36, unsigned char *h_matched, double *h_jaco);
 
+/* ---- Estimator::goodFeatureMatching, the odometry-side twin (estimator.cpp:1347-1517): features of frame i (sensor frame) against the local map
+ * in `slot`, matched at pose_local = pivot^-1 * pose_i * ext (n_neigh 5, CHECK_FOV false); rows from evaluateFeatJacobian (:1273-1345):
+ * surf -> the pose_i block of LidarPureOdomPlaneNormFactor(point, coeffs, 1.0), corner -> the constant row [1 0 0 0 0 0] (:1342).
+ * gf_ratio == 1.0: every matched feature in order (:1380-1414); else the stochastic greedy selection (seed instead of random_device, no
+ * wall-clock cap).  Outputs as mloam_good_features. */
+int mloam_good_features_odom(mloam_ctx_t *ctx, int slot, int type, const mloam_point_t *h_pts, int n, const double *pose_pivot7,
+                             const double *pose_i7, const double *ext7, double gf_ratio, unsigned long long seed, int *h_sel, int *n_sel,
+                             double *H36, unsigned char *h_matched, double *h_jaco);
+
+/* ---- Estimator::buildLocalMap / buildCalibMap, the map half (estimator.cpp:1175-1204 / :1084-1110) for one LiDAR and one feature kind:
+ * the window's stacked clouds (n_frames clouds concatenated, counts[i] points each, sensor frame) are moved into the pivot frame with
+ * pose_local7[i] = pivot^-1 * pose_i * ext (pcl::transformPointCloud with the float matrix, intensity kept), concatenated,
+ * filtered with pcl::VoxelGrid(leaf) (leaf = 0.4 * clamp(N_SCANS * NUM_OF_LASER * WINDOW_SIZE / 192, 0.75, 2) in buildLocalMap :1194;
+ * 0.4 / 0.2 in buildCalibMap :1103) and installed in map slot `slot` (setInputCloud, :1231-1233).  h_out (nullable, capacity = sum of
+ * counts) receives the filtered local map, *n_out its size.  The frames of the window are then matched with mloam_match_from_map /
+ * mloam_good_features_odom and solved with mloam_odom_solve / mloam_calib_frame. */
+int mloam_local_map_build(mloam_ctx_t *ctx, int slot, int n_frames, const mloam_point_t *h_pts, const int *counts, const double *pose_local7,
+                          float leaf, float map_cell, mloam_point_t *h_out, int *n_out);
+
 /* ---- multi-GPU: one LiDAR per GPU, one all-reduce of the packed normal equations per LM evaluation
  * (SURVEY.md §8e).  id128 is an ncclUniqueId (128 bytes) created on rank 0 and shared by the caller. */
 int mloam_comm_unique_id(void *id128);

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
-    "mloam_frame_device", "mloam_set_extrinsic", "mloam_set_lidars", "mloam_calib_frame", "mloam_compound_pose_cov", "mloam_cloud_uct_associate", "mloam_voxel_downsample_cov", "mloam_submap_assemble", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init", "mloam_comm_p2p_reset",
+    "mloam_frame_device", "mloam_set_extrinsic", "mloam_set_lidars", "mloam_calib_frame", "mloam_compound_pose_cov", "mloam_cloud_uct_associate", "mloam_voxel_downsample_cov", "mloam_submap_assemble", "mloam_good_features_odom", "mloam_local_map_build", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init", "mloam_comm_p2p_reset",
 ]
 
 
@@ -350,6 +350,30 @@ class Context:
         self._ck(lib().mloam_calib_frame(self._h, _p(sr), n[0], _p(cr), n[1], _p(sc), n[2], _p(cc), n[3], _p(pv), _p(pi), _p(er), _p(ec),
                                          max_outer, max_inner, C.c_double(huber_a), int(own_cal_maps), C.byref(st)))
         return pi, ec, st.as_dict()
+
+    def local_map_build(self, slot: int, clouds, pose_local7, leaf: float, map_cell: float = 0.0):
+        clouds = [_cloud(x) for x in clouds]
+        counts = np.ascontiguousarray([x.shape[0] for x in clouds], np.int32)
+        allp = _cloud(np.concatenate(clouds)) if clouds else np.zeros((0, 4), np.float32)
+        pl = np.ascontiguousarray(pose_local7, np.float64).reshape(-1, 7)
+        out = np.zeros((max(allp.shape[0], 1), 4), np.float32)
+        no = C.c_int(0)
+        self._ck(lib().mloam_local_map_build(self._h, slot, len(clouds), _p(allp), _p(counts), _p(pl), C.c_float(leaf), C.c_float(map_cell), _p(out),
+                                             C.byref(no)))
+        return out[:no.value].copy()
+
+    def good_features_odom(self, slot: int, kind: str, pts, pivot7, pose_i7, ext7, gf_ratio: float, seed: int):
+        pts = _cloud(pts)
+        n = pts.shape[0]
+        a, b, e = (np.ascontiguousarray(x, np.float64) for x in (pivot7, pose_i7, ext7))
+        sel = np.zeros(max(n, 1), np.int32)
+        n_sel = C.c_int(0)
+        H = np.zeros(36)
+        matched = np.zeros(max(n, 1), np.uint8)
+        jaco = np.zeros((max(n, 1), 6))
+        self._ck(lib().mloam_good_features_odom(self._h, slot, ord(kind), _p(pts), n, _p(a), _p(b), _p(e), C.c_double(gf_ratio), C.c_ulonglong(seed),
+                                                _p(sel), C.byref(n_sel), _p(H), _p(matched), _p(jaco)))
+        return {"sel": sel[:n_sel.value].copy(), "H": H.reshape(6, 6), "matched": matched[:n].astype(bool), "jaco": jaco[:n]}
 
     # ---- submap assembly with uncertainty
     @staticmethod

@@ -956,7 +956,7 @@ __global__ void k_lidar_offsets(const RingStage *__restrict__ stage, const int *
   off[l] = a, off[n_lidars + 1 + l] = b;
 }
 
-__global__ void k_merge_transform(float4 *__restrict__ pts, const int *__restrict__ off, int n_lidars, const float *__restrict__ ext12) {
+__global__ void k_merge_transform(float4 *__restrict__ pts, const int *__restrict__ off, int n_lidars, const float *__restrict__ ext12, int set_id = 1) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= off[n_lidars]) return;
   int l = 0;
@@ -968,7 +968,7 @@ __global__ void k_merge_transform(float4 *__restrict__ pts, const int *__restric
   o.x = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
   o.y = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
   o.z = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
-  o.w = (float)l;  // p.intensity = n
+  o.w = set_id ? (float)l : p.w;  // p.intensity = n (rig merge) / kept (local map, estimator.cpp:1185-1186)
   pts[i] = o;
 }
 
@@ -982,6 +982,16 @@ int merge_lidars_device(Ctx *c, ExtractOut out, int n_cap_less, int n_cap_lflat,
   if (n_cap_less > 0) k_merge_transform<<<(n_cap_less + 255) / 256, 256, 0, st>>>(out.less_sharp, d_off, n_lidars, d_ext12);
   if (n_cap_lflat > 0) k_merge_transform<<<(n_cap_lflat + 255) / 256, 256, 0, st>>>(out.less_flat, d_off + n_lidars + 1, n_lidars, d_ext12);
   c->launches += 3;
+  MLOAM_CUDA_OK(c, cudaGetLastError());
+  return MLOAM_OK;
+}
+
+// In place: segment l of `pts` (points [off[l], off[l+1])) <- float 3x4 matrix l times the point, intensity kept
+// (pcl::transformPointCloud with pose_local_[n][i].T_.cast<float>(), estimator.cpp:1185-1190).
+int transform_segments_device(Ctx *c, float4 *d_pts, int n, const int *d_off, int n_seg, const float *d_mat12) {
+  if (n <= 0) return MLOAM_OK;
+  k_merge_transform<<<(n + 255) / 256, 256, 0, c->stream>>>(d_pts, d_off, n_seg, d_mat12, 0);
+  c->launches++;
   MLOAM_CUDA_OK(c, cudaGetLastError());
   return MLOAM_OK;
 }

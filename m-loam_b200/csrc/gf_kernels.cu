@@ -50,6 +50,29 @@ __global__ void k_gf_jaco(const float4 *__restrict__ pts, const unsigned char *_
   for (int k = 0; k < 6; k++) jaco[(size_t)i * 6 + k] = J[k];
 }
 
+// Odometry-side rows (Estimator::evaluateFeatJacobian, estimator.cpp:1273-1345): surf features carry the pose_i block of
+// LidarPureOdomPlaneNormFactor(point, coeffs, 1.0) on (pivot, pose_i, ext); corner features the constant row
+// Matrix<double,1,6>::Identity() = [1 0 0 0 0 0] (:1342).
+__global__ void k_gf_jaco_odom(const float4 *__restrict__ pts, const unsigned char *__restrict__ valid, const float *__restrict__ coeff, int n,
+                               int is_plane, const double *__restrict__ x21 /* pivot | pose_i | ext */, double *__restrict__ jaco) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double J[6] = {0, 0, 0, 0, 0, 0};
+  if (valid[i]) {
+    if (is_plane) {
+      const Chain ch = make_chain(x21, x21 + 7, x21 + 14);
+      const float4 pf = pts[i];
+      const float *cf = coeff + (size_t)i * 6;
+      double Je[6];
+      odom_plane_factor(ch, D3{(double)pf.x, (double)pf.y, (double)pf.z}, D3{(double)cf[0], (double)cf[1], (double)cf[2]}, (double)cf[3], 1.0, nullptr, J, Je);
+    } else {
+      J[0] = 1.0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) jaco[(size_t)i * 6 + k] = J[k];
+}
+
 // ---- PCG32, identical to oracle/orc_gf.hpp
 __device__ __forceinline__ unsigned gf_next(unsigned long long &s) {
   const unsigned long long old = s;
@@ -358,9 +381,38 @@ int gf_select_set_device(Ctx *c, int t, const FeatSet &fs, const double *d_pose7
 
 using namespace mloam;
 
+static int good_features_impl(mloam_ctx_t *h, int slot, int type, const mloam_point_t *h_pts, int n, const float *h_cov6, const double *pose7,
+                              const double *odom_x21, int method, double gf_ratio, unsigned long long seed, int *h_sel, int *n_sel, double *H36,
+                              unsigned char *h_matched, double *h_jaco);
+
 extern "C" int mloam_good_features(mloam_ctx_t *h, int slot, int type, const mloam_point_t *h_pts, int n, const float *h_cov6,
                                    const double *pose7, int method, double gf_ratio, unsigned long long seed, int *h_sel, int *n_sel,
                                    double *H36, unsigned char *h_matched, double *h_jaco) {
+  return good_features_impl(h, slot, type, h_pts, n, h_cov6, pose7, nullptr, method, gf_ratio, seed, h_sel, n_sel, H36, h_matched, h_jaco);
+}
+
+// Estimator::goodFeatureMatching (estimator.cpp:1347-1517): features of frame i matched at pose_local = pivot^-1 * pose_i * ext
+// (n_neigh 5, CHECK_FOV false), rows from evaluateFeatJacobian, every matched feature when gf_ratio == 1.0 (:1380-1414), else the
+// stochastic greedy selection.
+extern "C" int mloam_good_features_odom(mloam_ctx_t *h, int slot, int type, const mloam_point_t *h_pts, int n, const double *pose_pivot7,
+                                        const double *pose_i7, const double *ext7, double gf_ratio, unsigned long long seed, int *h_sel, int *n_sel,
+                                        double *H36, unsigned char *h_matched, double *h_jaco) {
+  if (!pose_pivot7 || !pose_i7 || !ext7) return MLOAM_E_INVALID;
+  double x21[21], local[7];
+  for (int k = 0; k < 7; k++) x21[k] = pose_pivot7[k], x21[7 + k] = pose_i7[k], x21[14 + k] = ext7[k];
+  {  // Pose(pose_pivot.T_.inverse() * pose_i.T_ * pose_ext.T_) (:1358)
+    const PoseD P = pose_from_param(pose_pivot7), I = pose_from_param(pose_i7), E = pose_from_param(ext7);
+    const Q4 qpi = qconj(qnormalized(P.q));
+    const Q4 q = qnormalized(qmul(qpi, qmul(I.q, E.q)));
+    const D3 t = qrot(qpi, (qrot(I.q, E.t) + I.t) - P.t);
+    local[0] = t.x, local[1] = t.y, local[2] = t.z, local[3] = q.x, local[4] = q.y, local[5] = q.z, local[6] = q.w;
+  }
+  return good_features_impl(h, slot, type, h_pts, n, nullptr, local, x21, gf_ratio == 1.0 ? 0 : 3, gf_ratio, seed, h_sel, n_sel, H36, h_matched, h_jaco);
+}
+
+static int good_features_impl(mloam_ctx_t *h, int slot, int type, const mloam_point_t *h_pts, int n, const float *h_cov6, const double *pose7,
+                              const double *odom_x21, int method, double gf_ratio, unsigned long long seed, int *h_sel, int *n_sel, double *H36,
+                              unsigned char *h_matched, double *h_jaco) {
   if (!h || n < 0 || !pose7 || !n_sel || !H36 || method < 0 || method > 3 || !(gf_ratio >= 0.0) || gf_ratio > 1.0 ||
       (n > 0 && (!h_pts || !h_sel)) || (type != 's' && type != 'c'))
     return MLOAM_E_INVALID;
@@ -377,7 +429,9 @@ extern "C" int mloam_good_features(mloam_ctx_t *h, int slot, int type, const mlo
   double *d_pose;
   rc = upload_pose(c, pose7, &d_pose);
   if (rc) return rc;
-  rc = match_from_map_device(c, slot, type, c->scan_pts[t].as<float4>(), n, nullptr, d_pose, match_cfg(c),
+  MatchCfg mcfg = match_cfg(c);
+  if (odom_x21) mcfg.n_neigh = 5, mcfg.check_fov = 0;  // estimator.cpp:1377, :1393 / :1403
+  rc = match_from_map_device(c, slot, type, c->scan_pts[t].as<float4>(), n, nullptr, d_pose, mcfg,
                              c->feat_valid[t].as<unsigned char>(), c->feat_coeff[t].as<float>(), nullptr);
   if (rc) return rc;
   // scratch[3]: jaco | cov6 | fen | visited | dist | sel | n_sel | H
@@ -395,8 +449,17 @@ extern "C" int mloam_good_features(mloam_ctx_t *h, int slot, int type, const mlo
   double *d_jaco = reinterpret_cast<double *>(p + o_j);
   float *d_cov = h_cov6 ? reinterpret_cast<float *>(p + o_cov) : nullptr;
   if (h_cov6) MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_cov, h_cov6, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-  k_gf_jaco<<<(n + 127) / 128, 128, 0, c->stream>>>(c->scan_pts[t].as<float4>(), c->feat_valid[t].as<unsigned char>(), c->feat_coeff[t].as<float>(), n,
-                                                   nullptr, type == 's' ? 1 : 0, d_cov, nullptr, map_sqrt_info(c->params.cov_trace), d_pose, d_jaco);
+  if (odom_x21) {
+    double *stage = reinterpret_cast<double *>(c->pinned) + 200;
+    for (int k = 0; k < 21; k++) stage[k] = odom_x21[k];
+    double *d_x21 = c->scratch[7].as<double>() + 64;
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_x21, stage, 21 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_gf_jaco_odom<<<(n + 127) / 128, 128, 0, c->stream>>>(c->scan_pts[t].as<float4>(), c->feat_valid[t].as<unsigned char>(), c->feat_coeff[t].as<float>(),
+                                                          n, type == 's' ? 1 : 0, d_x21, d_jaco);
+  } else {
+    k_gf_jaco<<<(n + 127) / 128, 128, 0, c->stream>>>(c->scan_pts[t].as<float4>(), c->feat_valid[t].as<unsigned char>(), c->feat_coeff[t].as<float>(), n,
+                                                     nullptr, type == 's' ? 1 : 0, d_cov, nullptr, map_sqrt_info(c->params.cov_trace), d_pose, d_jaco);
+  }
   GfArgs a;
   a.method = method, a.gf_ratio = gf_ratio, a.seed = seed, a.n = n, a.d_n = nullptr, a.mask = nullptr;
   a.matched = c->feat_valid[t].as<unsigned char>(), a.jaco = d_jaco, a.pts = c->scan_pts[t].as<float4>();

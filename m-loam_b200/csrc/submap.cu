@@ -393,4 +393,57 @@ int mloam_submap_assemble(mloam_ctx_t *h, int slot, int n_keyframes, const mloam
   return MLOAM_OK;
 }
 
+// Estimator::buildLocalMap / buildCalibMap, the map half (estimator.cpp:1175-1204 / :1084-1110) for one LiDAR and one feature kind: the
+// window's stacked clouds (sensor frame) -> pivot frame with pose_local[i] -> `+=` -> pcl::VoxelGrid(leaf) -> map slot.
+int mloam_local_map_build(mloam_ctx_t *h, int slot, int n_frames, const mloam_point_t *h_pts, const int *counts, const double *pose_local7, float leaf,
+                          float map_cell, mloam_point_t *h_out, int *n_out) {
+  if (!h || slot < 0 || slot >= MLOAM_NUM_MAPS || n_frames < 0 || n_frames > 64 || !counts || !pose_local7 || !(leaf > 0.f)) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  if (n_out) *n_out = 0;
+  std::vector<int> off(n_frames + 1, 0);
+  for (int k = 0; k < n_frames; k++) {
+    if (counts[k] < 0) return MLOAM_E_INVALID;
+    off[k + 1] = off[k] + counts[k];
+  }
+  const int n = off[n_frames];
+  if (n > 0 && !h_pts) return MLOAM_E_INVALID;
+  cudaStream_t st = c->stream;
+  std::vector<float> mats(12 * (size_t)(n_frames + 1), 0.f);
+  for (int k = 0; k < n_frames; k++) {  // Pose(Matrix4d) normalises the quaternion; T_.cast<float>()
+    const double *e = pose_local7 + 7 * (size_t)k;
+    const M33 R = qmat(qnormalized(Q4{e[3], e[4], e[5], e[6]}));
+    for (int r = 0; r < 3; r++) {
+      for (int q = 0; q < 3; q++) mats[12 * k + 4 * r + q] = (float)R.m[3 * r + q];
+      mats[12 * k + 4 * r + 3] = (float)e[r];
+    }
+  }
+  DevBuf &in = c->scratch[0], &outb = c->scratch[1];
+  const size_t N1 = (size_t)n + 16;
+  MLOAM_CUDA_OK(c, in.reserve(16 * N1 + 4 * off.size() + 4 * mats.size() + 1024));
+  MLOAM_CUDA_OK(c, outb.reserve(16 * N1 + 256));
+  float4 *d_in = in.as<float4>();
+  int *d_off = reinterpret_cast<int *>(in.as<char>() + ((16 * N1 + 255) & ~(size_t)255));
+  float *d_mat = reinterpret_cast<float *>(d_off + ((off.size() + 63) & ~(size_t)63));
+  float4 *d_out = outb.as<float4>();
+  int *d_cnt = reinterpret_cast<int *>(outb.as<char>() + 16 * N1);
+  if (n > 0) MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_in, h_pts, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, st));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_mat, mats.data(), sizeof(float) * mats.size(), cudaMemcpyHostToDevice, st));
+  int rc = transform_segments_device(c, d_in, n, d_off, n_frames, d_mat);
+  if (rc) return rc;
+  rc = voxel_downsample_device(c, d_in, n, nullptr, leaf, 0, d_out, d_cnt, 5);  // pcl::VoxelGrid<PointI>: every field averaged
+  if (rc) return rc;
+  int *hc = reinterpret_cast<int *>(reinterpret_cast<char *>(c->pinned) + 3072);
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(hc, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(st));  // also: the host vectors above have been consumed
+  const int m = hc[0];
+  if (n_out) *n_out = m;
+  rc = map_build_device(c, slot, d_out, m, pick_cell(c, map_cell));
+  if (rc) return rc;
+  if (m > 0 && h_out) MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_out, d_out, sizeof(float4) * (size_t)m, cudaMemcpyDeviceToHost, st));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(st));
+  return MLOAM_OK;
+}
+
 }  // extern "C"

@@ -465,6 +465,54 @@ void orc_calib_frame(const float *surf_map, int n_sm, const float *corner_map, i
   if (stats) stats[0] = its, stats[1] = cost, stats[2] = rows, stats[3] = term;
 }
 
+// ---- odometry-side good features (orc_gf.hpp good_feature_matching_odom)
+void orc_good_features_odom(int type, const float *map, int m, const float *scan, int n, const double *pivot7, const double *pose_i7, const double *ext7,
+                            double gf_ratio, unsigned long long seed, const double *opts, unsigned char *matched, double *jaco, int *sel, int *n_sel,
+                            double *H36) {
+  Cloud mc = to_cloud(map, m), sc = to_cloud(scan, n);
+  KdTree tree;
+  tree.setInputCloud(&mc);
+  std::vector<Feature> all;
+  std::vector<unsigned char> mt;
+  std::vector<double> jc;
+  std::vector<int> s;
+  good_feature_matching_odom((char)type, tree, mc, sc, to_pose(pivot7), to_pose(pose_i7), to_pose(ext7), gf_ratio, seed, mp_from(opts), all, mt, jc, s, H36);
+  if (n > 0) std::memcpy(matched, mt.data(), n), std::memcpy(jaco, jc.data(), sizeof(double) * 6 * (size_t)n);
+  *n_sel = (int)s.size();
+  if (!s.empty()) std::memcpy(sel, s.data(), sizeof(int) * s.size());
+}
+
+// ---- Estimator::buildLocalMap / buildCalibMap, the map half (estimator.cpp:1175-1204 / :1084-1110): window clouds -> pivot frame with the
+// float matrix of pose_local[i] (pcl::transformPointCloud, PCL 1.8 evaluation order, intensity kept) -> `+=` -> pcl::VoxelGrid(leaf)
+void orc_local_map_build(int n_frames, const float *pts, const int *counts, const double *pose_local7, float leaf, float *out, int *n_out) {
+  Cloud merged;
+  size_t off = 0;
+  for (int k = 0; k < n_frames; k++) {
+    const double *e = pose_local7 + 7 * (size_t)k;
+    const Pose T = make_pose(Q4{e[3], e[4], e[5], e[6]}, V3{e[0], e[1], e[2]});
+    const M3 Rm = qmat(T.q);
+    float m[12];
+    for (int r = 0; r < 3; r++) {
+      for (int q = 0; q < 3; q++) m[4 * r + q] = (float)Rm(r, q);
+      m[4 * r + 3] = (float)(r == 0 ? T.t.x : (r == 1 ? T.t.y : T.t.z));
+    }
+    for (int i = 0; i < counts[k]; i++) {
+      const float *p = pts + 4 * (off + i);
+      PointI o;
+      o.x = m[0] * p[0] + m[1] * p[1] + m[2] * p[2] + m[3];
+      o.y = m[4] * p[0] + m[5] * p[1] + m[6] * p[2] + m[7];
+      o.z = m[8] * p[0] + m[9] * p[1] + m[10] * p[2] + m[11];
+      o.intensity = p[3];
+      merged.push_back(o);
+    }
+    off += (size_t)counts[k];
+  }
+  Cloud ds;
+  voxel_grid(merged, leaf, ds, false);
+  *n_out = (int)ds.size();
+  if (!ds.empty()) std::memcpy(out, ds.data(), sizeof(PointI) * ds.size());
+}
+
 // ---- submap assembly with uncertainty (orc_uct.hpp)
 void orc_compound_pose_cov(const double *p1, const double *cov1, const double *p2, const double *cov2, double *pose_out7, double *cov_out36) {
   M6 c1, c2, cc;

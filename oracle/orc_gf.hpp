@@ -183,4 +183,34 @@ inline void good_feature_matching(char type, const KdTree &tree, const Cloud &ma
   good_feature_select(method, gf_ratio, seed, (int)n, matched.data(), jaco.data(), xyz.data(), sel, H);
 }
 
+// Estimator::goodFeatureMatching (estimator.cpp:1347-1517) with evaluateFeatJacobian (:1273-1345): pose_local = pivot^-1 * pose_i * ext,
+// n_neigh 5, CHECK_FOV false; surf rows = the pose_i block of LidarPureOdomPlaneNormFactor(point, coeffs, 1.0), corner rows = [1 0 0 0 0 0];
+// gf_ratio == 1.0 takes every matched feature in order (:1380-1414), otherwise the stochastic greedy selection.
+inline void good_feature_matching_odom(char type, const KdTree &tree, const Cloud &map, const Cloud &scan, const Pose &pivot, const Pose &pose_i,
+                                       const Pose &ext, double gf_ratio, uint64_t seed, const MatchParams &mp, std::vector<Feature> &all,
+                                       std::vector<unsigned char> &matched, std::vector<double> &jaco, std::vector<int> &sel, double H[36]) {
+  const size_t n = scan.size();
+  all.assign(n, Feature());
+  matched.assign(n, 0);
+  jaco.assign(n * 6, 0.0);
+  const Pose pose_local = pose_mul(pose_inv(pivot), pose_mul(pose_i, ext));  // :1358
+  double xp[7], xi[7], xe[7];
+  pose_to_param(pivot, xp), pose_to_param(pose_i, xi), pose_to_param(ext, xe);
+  for (size_t i = 0; i < n; i++) {
+    const bool ok = type == 's' ? match_surf_point_from_map(tree, map, scan[i], pose_local, all[i], i, 5, false, mp)
+                                : match_corner_point_from_map(tree, map, scan[i], pose_local, all[i], i, 5, false, mp);
+    if (!ok) continue;
+    matched[i] = 1;
+    if (type == 's') {
+      double r, Jp[7], Ji[7], Je[7];
+      odom_plane_factor(all[i].point, all[i].coeffs, 1.0, xp, xi, xe, &r, Jp, Ji, Je);
+      for (int k = 0; k < 6; k++) jaco[i * 6 + k] = Ji[k];
+    } else {
+      jaco[i * 6] = 1.0;  // Matrix<double, 1, 6>::Identity() (:1342)
+    }
+  }
+  std::vector<float> xyz(n * 4, 0.f);
+  good_feature_select(gf_ratio == 1.0 ? 0 : 3, gf_ratio, seed, (int)n, matched.data(), jaco.data(), xyz.data(), sel, H);
+}
+
 }  // namespace orc

@@ -325,6 +325,29 @@ def calib_frame(surf_map, corner_map, surf_ref, corner_ref, surf_cal, corner_cal
     return pi, ec, {"lm_iterations": int(st[0]), "final_cost": st[1], "rows": int(st[2]), "termination": int(st[3])}
 
 
+def good_features_odom(kind, map_pts, scan, pivot, pose_i, ext, gf_ratio, seed, opts=None):
+    mp, sc = cloud(map_pts), cloud(scan)
+    n = sc.shape[0]
+    a, b, e = (np.ascontiguousarray(x, np.float64) for x in (pivot, pose_i, ext))
+    opts = default_opts() if opts is None else np.ascontiguousarray(opts, np.float64)
+    matched, jaco, sel, H = np.zeros(max(n, 1), np.uint8), np.zeros((max(n, 1), 6)), np.zeros(max(n, 1), np.int32), np.zeros(36)
+    ns = C.c_int(0)
+    lib().orc_good_features_odom(ord(kind), _p(mp), mp.shape[0], _p(sc), n, _p(a), _p(b), _p(e), C.c_double(gf_ratio), C.c_ulonglong(seed), _p(opts),
+                                 _p(matched), _p(jaco), _p(sel), C.byref(ns), _p(H))
+    return {"sel": sel[:ns.value].copy(), "H": H.reshape(6, 6), "matched": matched[:n].astype(bool), "jaco": jaco[:n]}
+
+
+def local_map_build(clouds, pose_local7, leaf):
+    clouds = [cloud(x) for x in clouds]
+    counts = np.ascontiguousarray([x.shape[0] for x in clouds], np.int32)
+    allp = cloud(np.concatenate(clouds))
+    pl = np.ascontiguousarray(pose_local7, np.float64).reshape(-1, 7)
+    out = np.zeros((allp.shape[0], 4), np.float32)
+    no = C.c_int(0)
+    lib().orc_local_map_build(len(clouds), _p(allp), _p(counts), _p(pl), C.c_float(leaf), _p(out), C.byref(no))
+    return out[:no.value].copy()
+
+
 def compound_pose_cov(p1, cov1, p2, cov2):
     """compoundPoseWithCov (method 2): returns (pose7, cov 6x6) of p1 * p2."""
     a, b = np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p2, np.float64)

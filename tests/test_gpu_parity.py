@@ -435,6 +435,44 @@ def test_calib_frame_matches_oracle(ctx, rings, horizon, map_pts, outer, inner):
         assert st2["n_surf"] == rst2["rows"] and max(syn.pose_err(ec2, rec2) + syn.pose_err(pi2, rpi2)) <= POSE_TOL_T
 
 
+# ------------------------------------------------------------------------------------------------ odometry node: local map + good features
+def test_local_map_build_and_odometry_good_features(ctx):
+    """Estimator::buildLocalMap for one LiDAR: window clouds -> pivot frame -> VoxelGrid(leaf formula) -> map slot, then
+    Estimator::goodFeatureMatching of a later frame against it (PureOdom pose_i rows for surf, the identity row for corners)."""
+    scene = syn.make_scene()
+    traj = syn.trajectory(8)
+    ext = syn.rig_extrinsics(2)[1]
+    pivot = traj[2]
+    window = [2, 3, 4, 5]                                        # frames of the window that enter the local map
+    leaf = float(0.4 * min(2.0, max(0.75, 1.0 / 192 * float(16 * 2 * 4))))   # estimator.cpp:1194 with N_SCANS 16, 2 LiDARs, WINDOW_SIZE 4
+    surf_stack, corner_stack, pose_local = [], [], []
+    for i in window:
+        c, ss, se = syn.make_sweep(scene, traj[i], 16, 1024, seed=400 + i, lidar_id=1, ext=ext)
+        f = orc.extract_cloud(c, ss, se)
+        surf_stack.append(orc.voxel_grid(f["surf_points_less_flat"], 0.4, False)[0])     # window-level down-sampling, estimator.cpp:485-496
+        corner_stack.append(orc.voxel_grid(f["corner_points_less_sharp"], 0.2, False)[0])
+        pose_local.append(syn.pose_mul(syn.pose_inv(pivot), syn.pose_mul(traj[i], ext)))
+    for slot, stack in ((1, surf_stack), (0, corner_stack)):
+        got = ctx.local_map_build(slot, stack, pose_local, leaf, 0.5)
+        ref = orc.local_map_build(stack, pose_local, leaf)
+        assert got.shape == ref.shape and np.array_equal(got, ref) and ctx.map_size(slot) == ref.shape[0]
+    surf_map, corner_map = orc.local_map_build(surf_stack, pose_local, leaf), orc.local_map_build(corner_stack, pose_local, leaf)
+    # frame 6 against the window's local map
+    c, ss, se = syn.make_sweep(scene, traj[6], 16, 1024, seed=406, lidar_id=1, ext=ext)
+    f = orc.extract_cloud(c, ss, se)
+    pose_i = syn.perturb_pose(traj[6], np.random.Generator(np.random.PCG64(9)))
+    for kind, slot, scan, mp in (("s", 1, orc.voxel_grid(f["surf_points_less_flat"], 0.4, False)[0], surf_map),
+                                 ("c", 0, orc.voxel_grid(f["corner_points_less_sharp"], 0.2, False)[0], corner_map)):
+        for ratio in (1.0, 0.4):
+            g = ctx.good_features_odom(slot, kind, scan, pivot, pose_i, ext, ratio, 77)
+            r = orc.good_features_odom(kind, mp, scan, pivot, pose_i, ext, ratio, 77)
+            assert np.array_equal(g["matched"], r["matched"]) and g["matched"].sum() > 50
+            assert np.allclose(g["jaco"], r["jaco"], rtol=1e-9, atol=1e-12)
+            assert np.array_equal(g["sel"], r["sel"]) and np.allclose(g["H"], r["H"], rtol=1e-9, atol=1e-12)
+            if kind == "c":
+                assert np.array_equal(g["jaco"][g["matched"]], np.tile([1.0, 0, 0, 0, 0, 0], (int(g["matched"].sum()), 1)))
+
+
 # ------------------------------------------------------------------------------------------------ submap assembly with uncertainty (f2)
 def _uct_case(n_kf=4, n_lasers=2):
     scene = syn.make_scene()
