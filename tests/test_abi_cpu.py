@@ -84,3 +84,22 @@ def test_wire_format_helpers_selftest():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "m-loam_b200"), "host/io_selftest"], stdout=subprocess.DEVNULL)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and "io_selftest OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_adapter_compiles_against_stub_headers(mloam):
+    """m-loam_b200/host/mloam_adapter.hpp — the hot-path classes with the reference's own PCL / Eigen / Ceres types — is compiled
+    against the minimal stand-in headers of tests/stubs/ with the reference's call shapes, and every C-ABI symbol it needs is exported."""
+    import subprocess
+    import tempfile
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        obj = os.path.join(td, "adapter_compile_test.o")
+        out = subprocess.run(["g++", "-std=c++14", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "stubs"), "-c",
+                              os.path.join(ROOT, "tests", "stubs", "adapter_compile_test.cpp"), "-o", obj], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-3000:]
+        syms = subprocess.run(["nm", "-C", obj], capture_output=True, text=True).stdout
+    needed = sorted(set(re.findall(r"U (mloam_[a-z0-9_]+)", syms)))
+    assert len(needed) >= 10
+    lib = mloam.lib()
+    for s in needed:
+        assert hasattr(lib, s), s
