@@ -117,6 +117,14 @@ int mloam_profile_enable(mloam_ctx_t *ctx, int on);
 int mloam_profile_get(mloam_ctx_t *ctx, const char *name, double *ms_total, long long *launches);
 int mloam_profile_reset(mloam_ctx_t *ctx);
 
+/* ---- ImageSegmenter::segmentCloud with ScanInfo::segment_flag_ == false (`segment_cloud: 0`): the range-image projection
+ *      (image_segmenter.hpp:88-136) and the ring-ordered output + ScanInfo (:381-389) that feed extractCloud (estimator.cpp:122,228,258).
+ *      vertical_scans 16 / 32 / 64 and horizon_scans as ImageSegmenter::setParameter takes them (image_segmenter.cpp:18-63); roi_range = ROI_RANGE
+ *      (parameters.cpp:211).  h_out holds up to n points (intensity += ring id), h_scan_start / h_scan_end hold vertical_scans entries each.
+ *      The BFS labelling of segment_cloud: 1 (image_segmenter.hpp:160-360) is not provided. */
+int mloam_project_cloud(mloam_ctx_t *ctx, const mloam_point_t *h_cloud, int n, int vertical_scans, int horizon_scans, double roi_range,
+                        mloam_point_t *h_out, int *n_out, int *h_scan_start, int *h_scan_end);
+
 /* ---- FeatureExtract::extractCloud (feature_extract.cpp:118-297) -------------------------------- */
 int mloam_extract_features(mloam_ctx_t *ctx, const mloam_point_t *h_cloud, int n, const int *h_scan_start,
                            const int *h_scan_end, int n_scans, mloam_features_t *out);

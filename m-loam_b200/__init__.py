@@ -26,7 +26,7 @@ E_NO_DEVICE = -2
 ABI_SYMBOLS = [
     "mloam_default_params", "mloam_ctx_create", "mloam_ctx_destroy", "mloam_set_params", "mloam_set_stream", "mloam_sync",
     "mloam_last_error", "mloam_version", "mloam_launch_count", "mloam_profile_enable", "mloam_profile_get",
-    "mloam_profile_reset", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
+    "mloam_profile_reset", "mloam_project_cloud", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
     "mloam_frame_device", "mloam_set_extrinsic", "mloam_set_lidars", "mloam_calib_frame", "mloam_compound_pose_cov", "mloam_cloud_uct_associate", "mloam_voxel_downsample_cov", "mloam_submap_assemble", "mloam_good_features_odom", "mloam_local_map_build", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init", "mloam_comm_p2p_reset",
@@ -258,6 +258,16 @@ class Context:
         n = C.c_int(0)
         self._ck(lib().mloam_voxel_downsample(self._h, _p(pts), pts.shape[0], C.c_float(leaf), int(intensity_last), _p(out), C.byref(n)))
         return out[: n.value].copy()
+
+    def project_cloud(self, cloud, vertical_scans: int, horizon_scans: int, roi_range: float = 0.5):
+        """ImageSegmenter::segmentCloud with segment_cloud: 0 -> (ring-ordered cloud, scan_start, scan_end)."""
+        pts = _cloud(cloud)
+        out = np.empty((max(pts.shape[0], 1), 4), np.float32)
+        ss, se = np.zeros(max(vertical_scans, 1), np.int32), np.zeros(max(vertical_scans, 1), np.int32)
+        n = C.c_int(0)
+        self._ck(lib().mloam_project_cloud(self._h, _p(pts), pts.shape[0], int(vertical_scans), int(horizon_scans), C.c_double(roi_range), _p(out),
+                                           C.byref(n), _p(ss), _p(se)))
+        return out[: n.value].copy(), ss, se
 
     # ---- orchestrators
     def scan2map(self, surf_scan, corner_scan, pose_init7):

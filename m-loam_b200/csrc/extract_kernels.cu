@@ -12,6 +12,7 @@
 //
 // Float arithmetic follows the reference's evaluation order; integer/index results are exact.
 #include "ctx.h"
+#include "project.cuh"
 #include "primitives.cuh"
 
 namespace mloam {
@@ -441,6 +442,88 @@ static int voxel_work_reserve(Ctx *c, DevBuf &buf, int n, int n_seg, VoxelWork *
   w->hist = reinterpret_cast<int *>(p + o_hist), w->tmp = reinterpret_cast<int *>(p + o_tmp);
   w->head = reinterpret_cast<int *>(p + o_head), w->slot = reinterpret_cast<int *>(p + o_slot);
   w->ticket = reinterpret_cast<unsigned *>(p + o_ticket);
+  return MLOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------ range-image projection
+// ImageSegmenter::segmentCloud with segment_flag_ == false (image_segmenter.hpp:88-136, 381-389; parameters image_segmenter.cpp:18-63):
+// every point gets a (row, column) pixel of the vertical_scans x horizon_scans range image, the first point (input order) of a pixel wins,
+// intensity += row, and the output is the rows concatenated, each in input order; ScanInfo = [row begin + 5, row end - 6].
+// The float arithmetic follows the reference expression by expression (explicitly rounded operations, fdlibm atanf / atan2f — fd_atan.cuh).
+__global__ void k_project_pixels(const float4 *__restrict__ P, int n, ProjectParam sp, int *__restrict__ pix, int *__restrict__ winner) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int row = 0;
+  const int px = project_pixel(sp, P[i], &row);
+  pix[i] = px;
+  if (px >= 0) atomicMin(&winner[px], i);
+}
+__global__ void k_project_keys(const int *__restrict__ pix, const int *__restrict__ winner, int n, int horizon_scans,
+                               unsigned long long *__restrict__ keys, unsigned *__restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int px = pix[i];
+  keys[i] = (px >= 0 && winner[px] == i) ? (unsigned long long)(px / horizon_scans) : 255ull;
+  vals[i] = (unsigned)i;
+}
+__global__ void k_project_emit(const float4 *__restrict__ P, const unsigned long long *__restrict__ keys, const unsigned *__restrict__ vals,
+                               int n, float4 *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const unsigned long long k = keys[j];
+  if (k >= 255ull) return;
+  float4 p = P[vals[j]];
+  p.w = __fadd_rn(p.w, (float)(int)k);
+  out[j] = p;
+}
+// thread r <= vertical_scans: first sorted position whose row is >= r
+__global__ void k_project_rows(const unsigned long long *__restrict__ keys, int n, int vertical_scans, int *__restrict__ scan_start,
+                               int *__restrict__ scan_end, int *__restrict__ n_out) {
+  __shared__ int begin[257];
+  const int r = threadIdx.x;
+  if (r <= vertical_scans) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (keys[mid] < (unsigned long long)r) lo = mid + 1;
+      else hi = mid;
+    }
+    begin[r] = lo;
+  }
+  __syncthreads();
+  if (r < vertical_scans) scan_start[r] = begin[r] + 5, scan_end[r] = begin[r + 1] - 6;
+  if (r == vertical_scans) *n_out = begin[r];
+}
+
+int project_cloud_device(Ctx *c, const float4 *d_in, int n, int vertical_scans, int horizon_scans, double roi_range, float4 *d_out,
+                         int *d_scan_start, int *d_scan_end, int *d_n_out) {
+  if (n <= 0 || horizon_scans <= 0 || (vertical_scans != 16 && vertical_scans != 32 && vertical_scans != 64)) {
+    c->err = "project_cloud: vertical_scans must be 16, 32 or 64 (ImageSegmenter::setParameter)";
+    return MLOAM_E_INVALID;
+  }
+  ProfScope ps(c, "project");
+  const ProjectParam sp = project_param(vertical_scans, horizon_scans, roi_range);
+  VoxelWork w;
+  int rc = voxel_work_reserve(c, c->scratch[5], n, 1, &w);
+  if (rc) return rc;
+  const size_t n_pix = (size_t)vertical_scans * horizon_scans;
+  MLOAM_CUDA_OK(c, c->scratch[2].reserve(sizeof(int) * n_pix));
+  int *winner = c->scratch[2].as<int>();
+  cudaStream_t st = c->stream;
+  MLOAM_CUDA_OK(c, cudaMemsetAsync(winner, 0x7f, sizeof(int) * n_pix, st));
+  MLOAM_CUDA_OK(c, cudaMemsetAsync(w.ticket, 0, 16, st));
+  const int nb = (n + 255) / 256;
+  k_project_pixels<<<nb, 256, 0, st>>>(d_in, n, sp, w.head, winner);
+  k_project_keys<<<nb, 256, 0, st>>>(w.head, winner, n, horizon_scans, w.k0, w.v0);
+  c->launches += 2;
+  SortBufs sb{w.k0, w.k1, w.v0, w.v1, w.hist, w.tmp, w.ticket};
+  const int cur = radix_sort(c, sb, n, nullptr, 8);
+  const unsigned long long *ks = cur ? w.k1 : w.k0;
+  const unsigned *vs = cur ? w.v1 : w.v0;
+  k_project_emit<<<nb, 256, 0, st>>>(d_in, ks, vs, n, d_out);
+  k_project_rows<<<1, 96, 0, st>>>(ks, n, vertical_scans, d_scan_start, d_scan_end, d_n_out);
+  c->launches += 2;
+  MLOAM_CUDA_OK(c, cudaGetLastError());
   return MLOAM_OK;
 }
 

@@ -491,6 +491,39 @@ int mloam_extract_debug(mloam_ctx_t *h, float *h_curvature, int *h_label, int n)
   return MLOAM_OK;
 }
 
+// ------------------------------------------------------------------------------------------ range image
+int mloam_project_cloud(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, int vertical_scans, int horizon_scans, double roi_range,
+                        mloam_point_t *h_out, int *n_out, int *h_scan_start, int *h_scan_end) {
+  if (!h || n < 0 || !n_out || !h_scan_start || !h_scan_end || (n > 0 && (!h_cloud || !h_out))) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  cudaSetDevice(c->device);
+  *n_out = 0;
+  if (vertical_scans != 16 && vertical_scans != 32 && vertical_scans != 64)
+    return fail(c, MLOAM_E_INVALID, "project_cloud: vertical_scans must be 16, 32 or 64 (ImageSegmenter::setParameter)");
+  if (horizon_scans <= 0) return MLOAM_E_INVALID;
+  if (n == 0) {  // image_segmenter.hpp:381-387 on an empty cloud
+    for (int i = 0; i < vertical_scans; i++) h_scan_start[i] = 5, h_scan_end[i] = -6;
+    return MLOAM_OK;
+  }
+  DevBuf &in = c->scratch[0], &outb = c->scratch[1];
+  MLOAM_CUDA_OK(c, in.reserve(sizeof(float4) * (size_t)n));
+  MLOAM_CUDA_OK(c, outb.reserve(sizeof(float4) * (size_t)n + 1024));
+  cudaStream_t st = c->stream;
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(in.p, h_cloud, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  int *d_meta = reinterpret_cast<int *>(outb.as<char>() + sizeof(float4) * (size_t)n);  // [0] count, [64..] start, [128..] end
+  int rc = project_cloud_device(c, in.as<float4>(), n, vertical_scans, horizon_scans, roi_range, outb.as<float4>(), d_meta + 64, d_meta + 128,
+                                d_meta);
+  if (rc) return rc;
+  int *hc = reinterpret_cast<int *>(reinterpret_cast<char *>(c->pinned) + 3072);
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(hc, d_meta, sizeof(int) * 192, cudaMemcpyDeviceToHost, st));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(st));
+  *n_out = hc[0];
+  std::memcpy(h_scan_start, hc + 64, sizeof(int) * vertical_scans), std::memcpy(h_scan_end, hc + 128, sizeof(int) * vertical_scans);
+  if (hc[0] > 0) MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_out, outb.p, sizeof(float4) * (size_t)hc[0], cudaMemcpyDeviceToHost, st));
+  MLOAM_CUDA_OK(c, cudaStreamSynchronize(st));
+  return MLOAM_OK;
+}
+
 // ------------------------------------------------------------------------------------------ voxel grid
 int mloam_voxel_downsample(mloam_ctx_t *h, const mloam_point_t *h_in, int n, float leaf, int intensity_last, mloam_point_t *h_out,
                            int *n_out) {

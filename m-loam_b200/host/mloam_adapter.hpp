@@ -1,5 +1,5 @@
 // mloam_adapter.hpp — the hot-path classes with the REFERENCE'S OWN types (PCL clouds, Eigen vectors, Ceres bases), for a tree that
-// has PCL / Eigen / Ceres: include it INSTEAD of estimator/src/featureExtract/feature_extract.hpp, lidarTracker/lidar_tracker.h,
+// has PCL / Eigen / Ceres: include it INSTEAD of estimator/src/imageSegmenter/image_segmenter.hpp, featureExtract/feature_extract.hpp, lidarTracker/lidar_tracker.h,
 // factor/pose_local_parameterization.h and factor/lidar_{map,scan,pure_odom,online_calib}_factor.hpp, AFTER the reference's
 // parameters.h (ScanInfo, cloudFeature, PointPlaneFeature), pose.h (Pose) and <pcl/point_cloud.h>, <Eigen/Dense>, <ceres/ceres.h>.
 //
@@ -19,6 +19,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -78,6 +79,43 @@ class KdTreeFLANN {
 };
 
 }  // namespace mloam
+
+// ----------------------------------------------------------------------------------------------- ImageSegmenter
+// imageSegmenter/image_segmenter.hpp:47-84.  segmentCloud with scan_info.segment_flag_ == false (`segment_cloud: 0`: projection onto the
+// range image, first point of a pixel wins, intensity += ring, ring-ordered output, ScanInfo) runs on the GPU; the BFS labelling of
+// `segment_cloud: 1` (image_segmenter.hpp:160-360) is not provided and throws.
+extern double ROI_RANGE;  // parameters.h:86
+class ImageSegmenter {
+ public:
+  ImageSegmenter() {}
+  void setParameter(const int &vertical_scans, const int &horizon_scans, const int &min_cluster_size, const int &segment_valid_point_num,
+                    const int &segment_valid_line_num) {
+    vertical_scans_ = vertical_scans, horizon_scans_ = horizon_scans;
+    (void)min_cluster_size, (void)segment_valid_point_num, (void)segment_valid_line_num;  // BFS labelling only
+  }
+  template <typename PointType>
+  void segmentCloud(const typename pcl::PointCloud<PointType> &laser_cloud_in, typename pcl::PointCloud<PointType> &laser_cloud_out,
+                    typename pcl::PointCloud<PointType> &laser_cloud_outlier, ScanInfo &scan_info) {
+    if (scan_info.segment_flag_) throw std::runtime_error("mloam::ImageSegmenter: segment_cloud: 1 (BFS labelling) is not provided");
+    mloam_ctx_t *ctx = mloam::ThreadContext::get();
+    std::vector<mloam_point_t> in = mloam::packCloud(laser_cloud_in);
+    std::vector<mloam_point_t> out(in.size() + 1);
+    int n_out = 0;
+    scan_info.scan_start_ind_.resize(vertical_scans_), scan_info.scan_end_ind_.resize(vertical_scans_);
+    mloam::check(ctx, mloam_project_cloud(ctx, in.data(), (int)in.size(), vertical_scans_, horizon_scans_, ROI_RANGE, out.data(), &n_out,
+                                          scan_info.scan_start_ind_.data(), scan_info.scan_end_ind_.data()), "mloam_project_cloud");
+    laser_cloud_out.clear();
+    laser_cloud_out.resize((size_t)n_out);
+    for (int i = 0; i < n_out; i++) {
+      PointType &q = laser_cloud_out.points[i];
+      q.x = out[i].x, q.y = out[i].y, q.z = out[i].z, q.intensity = out[i].intensity;
+    }
+    if (n_out > 0) laser_cloud_outlier.push_back(laser_cloud_out.points[0]);  // image_segmenter.hpp:388
+  }
+
+ private:
+  int vertical_scans_ = 64, horizon_scans_ = 2048;
+};
 
 // ----------------------------------------------------------------------------------------------- FeatureExtract
 class FeatureExtract {

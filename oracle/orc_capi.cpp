@@ -5,6 +5,7 @@
 #include "orc_pipeline.hpp"
 #include "orc_gf.hpp"
 #include "orc_uct.hpp"
+#include "orc_segment.hpp"
 #include <cstdio>
 #ifdef _OPENMP
 #include <omp.h>
@@ -511,6 +512,29 @@ void orc_local_map_build(int n_frames, const float *pts, const int *counts, cons
   voxel_grid(merged, leaf, ds, false);
   *n_out = (int)ds.size();
   if (!ds.empty()) std::memcpy(out, ds.data(), sizeof(PointI) * ds.size());
+}
+
+// ---- ImageSegmenter::segmentCloud with segment_flag false: range-image projection + ring re-ordering (orc_segment.hpp)
+void orc_project_cloud(const float *cloud, int n, int vertical_scans, int horizon_scans, double roi_range, float *out, int *n_out, int *scan_start,
+                       int *scan_end) {
+  Cloud c = to_cloud(cloud, n), o;
+  std::vector<int> ss, se;
+  project_cloud(c, vertical_scans, horizon_scans, roi_range, o, ss, se);
+  *n_out = (int)o.size();
+  if (!o.empty()) std::memcpy(out, o.data(), sizeof(PointI) * o.size());
+  std::memcpy(scan_start, ss.data(), sizeof(int) * vertical_scans), std::memcpy(scan_end, se.data(), sizeof(int) * vertical_scans);
+}
+
+// pixel (row * horizon_scans + column) of every point, -1 where projectCloud skips it before the first-point-wins test
+void orc_project_pixels(const float *cloud, int n, int vertical_scans, int horizon_scans, double roi_range, int *pix) {
+  const SegmenterParam sp = segmenter_param(vertical_scans, horizon_scans);
+  for (int i = 0; i < n; i++) {
+    PointI p;
+    p.x = cloud[4 * i], p.y = cloud[4 * i + 1], p.z = cloud[4 * i + 2], p.intensity = cloud[4 * i + 3];
+    int row, col;
+    float range;
+    pix[i] = project_point(sp, p, roi_range, &row, &col, &range) ? row * horizon_scans + col : -1;
+  }
 }
 
 // ---- submap assembly with uncertainty (orc_uct.hpp)

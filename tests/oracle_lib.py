@@ -348,6 +348,24 @@ def local_map_build(clouds, pose_local7, leaf):
     return out[:no.value].copy()
 
 
+def project_cloud(cloud_, vertical_scans, horizon_scans, roi_range=0.5):
+    """ImageSegmenter::segmentCloud with segment_flag false: (ring-ordered cloud, scan_start, scan_end)."""
+    pts = cloud(cloud_)
+    n = pts.shape[0]
+    out = np.zeros((max(n, 1), 4), np.float32)
+    ss, se = np.zeros(vertical_scans, np.int32), np.zeros(vertical_scans, np.int32)
+    no = C.c_int(0)
+    lib().orc_project_cloud(_p(pts), n, vertical_scans, horizon_scans, C.c_double(roi_range), _p(out), C.byref(no), _p(ss), _p(se))
+    return out[:no.value].copy(), ss, se
+
+
+def project_pixels(cloud_, vertical_scans, horizon_scans, roi_range=0.5):
+    pts = cloud(cloud_)
+    pix = np.zeros(max(pts.shape[0], 1), np.int32)
+    lib().orc_project_pixels(_p(pts), pts.shape[0], vertical_scans, horizon_scans, C.c_double(roi_range), _p(pix))
+    return pix[:pts.shape[0]]
+
+
 def compound_pose_cov(p1, cov1, p2, cov2):
     """compoundPoseWithCov (method 2): returns (pose7, cov 6x6) of p1 * p2."""
     a, b = np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p2, np.float64)

@@ -14,6 +14,12 @@ int adapter_use_everything() {
   FeatureExtract f_extract;
   PointICloud cloud, map;
   ScanInfo scan_info(64, false);
+  {  // estimator.cpp:117-122
+    ImageSegmenter img_segment;
+    img_segment.setParameter(64, 2048, 5, 5, 3);
+    PointICloud laser_cloud_segment, laser_cloud_outlier;
+    img_segment.segmentCloud<PointI>(cloud, laser_cloud_segment, laser_cloud_outlier, scan_info);
+  }
   cloudFeature feat;
   f_extract.extractCloud(cloud, scan_info, feat);
 

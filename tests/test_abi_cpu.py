@@ -103,3 +103,55 @@ def test_adapter_compiles_against_stub_headers(mloam):
     lib = mloam.lib()
     for s in needed:
         assert hasattr(lib, s), s
+
+
+def _host_projection_lib(td):
+    import ctypes
+    import subprocess
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(td, "libproject_host.so")
+    out = subprocess.run(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "m-loam_b200", "csrc"),
+                          os.path.join(ROOT, "tests", "stubs", "project_host.cpp"), "-o", so], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return ctypes.CDLL(so)
+
+
+def test_projection_arithmetic_matches_oracle_on_the_host():
+    """csrc/project.cuh + csrc/fd_atan.cuh (what k_project_pixels evaluates) built for the host: (a) fd::atanf / fd::atan2f return the C
+    library's bits (the reference's pixel assignment depends on them: image_segmenter.hpp:103,119), (b) every point lands in the oracle's
+    pixel — random clouds, points on pixel borders, degenerate points — for the 16-, 32- and 64-ring parameter sets."""
+    import ctypes as C
+    import tempfile
+    import numpy as np
+    import oracle_lib as orc
+    with tempfile.TemporaryDirectory() as td:
+        h = _host_projection_lib(td)
+        h.host_fd_atan_mismatches.restype = C.c_long
+        rng = np.random.default_rng(5)
+        n = 2_000_000
+        x = (rng.uniform(-80, 80, n) * np.exp2(rng.integers(-40, 40, n) * (rng.random(n) < 0.3))).astype(np.float32)
+        y = (rng.uniform(-80, 80, n) * np.exp2(rng.integers(-40, 40, n) * (rng.random(n) < 0.3))).astype(np.float32)
+        sp = np.array([0, -0.0, 1, -1, np.inf, -np.inf, np.nan, 1e-38, -1e-38, 1e38, 1e-45, 0.4375, 0.6875, 1.1875, 2.4375, 2.0 ** 25, 2.0 ** 26], np.float32)
+        x = np.concatenate([x, np.repeat(sp, sp.size)]).astype(np.float32)
+        y = np.concatenate([y, np.tile(sp, sp.size)]).astype(np.float32)
+        ok = ~(np.isnan(x) | np.isnan(y))  # NaN payloads are not compared
+        xs, ys = np.ascontiguousarray(x[ok]), np.ascontiguousarray(y[ok])
+        bad = h.host_fd_atan_mismatches(xs.ctypes.data_as(C.c_void_p), ys.ctypes.data_as(C.c_void_p), C.c_long(xs.size))
+        assert bad == 0, bad
+        for rings, hs in ((16, 1800), (32, 2169), (64, 2048)):
+            n = 400_000
+            az, el = rng.uniform(-np.pi, np.pi, n), np.deg2rad(rng.uniform(-35, 20, n))
+            # a third of the azimuths / elevations sit (almost) on pixel borders
+            k = n // 3
+            az[:k] = np.deg2rad((rng.integers(0, hs, k) + 0.5) * 360.0 / hs - 180.0) + rng.normal(0, 1e-7, k)
+            if rings == 16:
+                el[k:2 * k] = np.deg2rad(rng.integers(-1, 17, k) * 2.0 - 15.1) + rng.normal(0, 1e-7, k)
+            r = rng.uniform(0.1, 90, n)
+            pts = np.stack([r * np.cos(el) * np.sin(az), r * np.cos(el) * np.cos(az), r * np.sin(el), rng.random(n)], 1).astype(np.float32)
+            pts[:8] = [[0, 0, 0, 0], [0, 0, 1, 0], [0, 0, -1, 0], [1, 0, 0, 0], [0, 1, 0, 0], [-1, 0, 0, 0], [0, -1, 0, 0], [np.nan, 1, 1, 0]]
+            for roi in (0.5, 0.0):
+                want = orc.project_pixels(pts, rings, hs, roi)
+                got = np.zeros(n, np.int32)
+                h.host_project_pixels(pts.ctypes.data_as(C.c_void_p), n, rings, hs, C.c_double(roi), got.ctypes.data_as(C.c_void_p))
+                assert np.array_equal(got, want), (rings, roi, int((got != want).sum()))
+                assert (want >= 0).sum() > n // 4

@@ -322,15 +322,21 @@ def test_frame_pose_parity_c1(ctx, c1, mloam, outer, inner):
     assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
 
 
-def test_frame_c2_full_size(ctx):
+@pytest.mark.parametrize("map_kind", ["uniform", "keyframes"])
+def test_frame_c2_full_size(ctx, map_kind):
     """Config C2 at full size: 64 x 2048 sweep, 1M-point submap, 10 GN iterations; pose parity against the oracle
-    plus size-independent properties."""
+    plus size-independent properties.  Two submaps: area-uniform samples of the scene, and the keyframe-built one of SURVEY 8d
+    (30 ray-cast keyframes -> extractCloud -> VoxelGrid 0.2 / 0.4 -> re-sampled with 1 cm jitter: clusters of near-duplicates at
+    voxel spacing, which exercises the shell / ball search paths and the keep shortcut's zero-slack case)."""
     scene = syn.make_scene()
     traj = syn.trajectory(8)
-    surf_map, corner_map = syn.make_submap(scene, 1_000_000)
+    if map_kind == "uniform":
+        surf_map, corner_map = syn.make_submap(scene, 1_000_000)
+    else:
+        surf_map, corner_map, _ = syn.make_submap_keyframes(scene, 1_000_000, orc.extract_cloud, orc.voxel_grid)
     cloud, ss, se = syn.make_sweep(scene, traj[7], 64, 2048, seed=7)
     init = syn.perturb_pose(traj[7], np.random.Generator(np.random.PCG64(17)))
-    ctx.set_params(max_outer=10, max_inner=1, n_scans=64, map_cell=0.26)
+    ctx.set_params(max_outer=10, max_inner=1, n_scans=64, map_cell=0.26 if map_kind == "uniform" else 0.0)  # 0: auto cell per map
     try:
         pose, st = ctx.frame(cloud, ss, se, surf_map, corner_map, init)
         pose_b, st_b = ctx.frame(cloud, ss, se, surf_map, corner_map, init)
@@ -348,7 +354,7 @@ def test_frame_c2_full_size(ctx):
     dt, dr = syn.pose_err(pose, ref)
     assert dt <= POSE_TOL_T and dr <= POSE_TOL_R, (dt, dr)
     et, er = syn.pose_err(pose, traj[7])
-    assert et < 0.05 and er < 2e-3
+    assert et < 0.05 and er < 3e-3
 
 
 # ------------------------------------------------------------------------------------------------ several LiDARs on one GPU
@@ -395,6 +401,49 @@ def test_extract_128_rings(ctx):
     ref = orc.extract_cloud(cloud, ss, se)
     for k in ("corner_points_sharp", "corner_points_less_sharp", "surf_points_flat", "surf_points_less_flat"):
         assert np.array_equal(got[k], ref[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ range-image projection (f1a)
+@pytest.mark.parametrize("rings,horizon,sweep_h", [(16, 1800, 2048), (32, 2169, 2048), (64, 2048, 2048), (64, 1024, 4096)])
+def test_project_cloud_matches_oracle(ctx, rings, horizon, sweep_h):
+    """ImageSegmenter::segmentCloud with segment_cloud: 0 (image_segmenter.hpp:88-136, 381-389): pixel of every point, first point of a
+    pixel wins, intensity += ring, rows concatenated in input order, ScanInfo — bit-exact on a raw (unordered, noisy, duplicate-carrying)
+    cloud; then the reference's chain segmentCloud -> extractCloud (estimator.cpp:258-259) end to end."""
+    scene = syn.make_scene()
+    cloud, _, _ = syn.make_sweep(scene, syn.trajectory(3)[1], rings if rings != 32 else 64, sweep_h, seed=21)
+    rng = np.random.default_rng(rings + horizon)
+    raw = cloud.copy()
+    raw[:, 3] -= np.floor(raw[:, 3])  # the driver's cloud: intensity carries no ring id yet
+    raw[:, :3] += rng.normal(0, 0.01, raw[:, :3].shape).astype(np.float32)
+    raw = np.concatenate([raw, raw[rng.integers(0, raw.shape[0], 5000)], np.zeros((3, 4), np.float32), [[0, 0, 2, 0], [np.nan, 1, 1, 0]]]).astype(np.float32)
+    raw = np.ascontiguousarray(raw[rng.permutation(raw.shape[0])])
+    for roi in (0.5, 0.0):
+        got, gs, ge = ctx.project_cloud(raw, rings, horizon, roi)
+        ref, rs, re_ = orc.project_cloud(raw, rings, horizon, roi)
+        assert got.shape == ref.shape and ref.shape[0] > raw.shape[0] // 8
+        assert np.array_equal(gs, rs) and np.array_equal(ge, re_)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    if rings == 16:
+        # sensor-ordered input (azimuth sweep per ring): the projected cloud feeds extractCloud
+        sweep, _, _ = syn.make_sweep(scene, syn.trajectory(3)[1], 16, 1800, seed=4)
+        sweep[:, 3] -= np.floor(sweep[:, 3])
+        got, gs, ge = ctx.project_cloud(sweep, 16, 1800, 0.5)
+        ref, rs, re_ = orc.project_cloud(sweep, 16, 1800, 0.5)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)) and np.array_equal(gs, rs) and np.array_equal(ge, re_)
+        ctx.set_params(n_scans=16)
+        try:
+            f = ctx.extract_features(got, gs, ge)
+        finally:
+            ctx.set_params(n_scans=64)
+        rf = orc.extract_cloud(ref, rs, re_)
+        for k in ("corner_points_sharp", "corner_points_less_sharp", "surf_points_flat", "surf_points_less_flat"):
+            assert np.array_equal(f[k], rf[k]), k
+        assert rf["surf_points_less_flat"].shape[0] > 500
+    # empty cloud and an unsupported ring count
+    e, es, ee = ctx.project_cloud(np.zeros((0, 4), np.float32), rings, horizon, 0.5)
+    assert e.shape[0] == 0 and np.all(es == 5) and np.all(ee == -6)
+    with pytest.raises(Exception):
+        ctx.project_cloud(raw, 40, horizon, 0.5)
 
 
 # ------------------------------------------------------------------------------------------------ online extrinsic calibration (C3)
