@@ -118,6 +118,7 @@ int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out
     if (v >= 2 && v <= 4) c->knn_min_blocks = v;
   }
   if (const char *e = getenv("MLOAM_KNN_TMA_MIN")) c->knn_tma_min = (unsigned)strtoul(e, nullptr, 10);
+  if (const char *e = getenv("MLOAM_FUSE_ITER")) c->fuse_iter = (e[0] == '0') ? 0 : 1;
   if (const char *e = getenv("MLOAM_DISABLE_SEEDS")) c->use_seeds = (e[0] == '0' || e[0] == '\0') ? 1 : 0;
   *out = h;
   return MLOAM_OK;

@@ -17,6 +17,27 @@ inline unsigned long long &alloc_epoch() {
   return e;
 }
 
+// Input / output of the per-feature line / plane fit (match_fit.cuh)
+struct FitSet {
+  const float4 *sorted;  // MapView::sorted of the set's map
+  const float4 *pts;
+  int n;
+  const int *d_n;
+  const int *pos;        // n * K from k_match_knn
+  unsigned char *valid;  // out
+  float *coeff;          // out: n * 6
+  int *nn;               // out (nullable): n * K original map indices
+  int is_plane;
+  const unsigned char *changed;  // nullable: 0 -> same neighbours as the previous iteration, valid/coeff already hold the fit
+};
+// A fit whose launch the matcher left to the first evaluation of the solve (k_linearize pass 0)
+struct PendingFit {
+  FitSet set[2];
+  int K = 0;  // 0: nothing pending
+  float min_plane_dis = 0.f;
+  int check_fov = 0;
+};
+
 // Grow-only device buffer (cudaMalloc only when capacity is exceeded; steady-state frames allocate nothing).
 struct DevBuf {
   void *p = nullptr;
@@ -175,6 +196,10 @@ struct Ctx {
   int s2m_ran = 0;
   int lm_min_corr = 0;              // lm_init_state: minimum matched features for a Solve (tracker: 10)
   double lm_eig_thre = -1.0;        // < 0: use params.eig_thre; the tracker disables evalDegenracy with 0
+  int fuse_iter = 1;               // scan2map: fit inside the first evaluation + both evaluations of an LM iteration in ONE launch
+                                   // (grid barrier between them); MLOAM_FUSE_ITER=0 restores the three launches
+  PendingFit pending_fit;          // set by match_pair_device(defer_fit), consumed by the next linearize_device(lm_mode 1)
+  bool lin_two_pass = false;       // request (scan2map_enqueue) -> linearize_device clears it when it could not honour it
   int want_eig = 1;                // k_lm mode 1: always run the 6x6 eigen-solver (1) or only when degenerate (0)
   bool lidar_merge = false;        // mloam_set_lidars was given extrinsics: features go through the rig merge (also for one LiDAR)
   int n_lidars = 1;                // LiDARs batched into one frame of this context (mloam_set_lidars)
@@ -236,7 +261,9 @@ struct MatchJob {
                             // lists (Ctx::knn_pos) seed the search and unchanged lists keep their fit
 };
 // buf_base: which pair of the context's per-set buffers (knn_pos / knn_anchor / ...) the jobs use: 0 (sets 0, 1) or 2 (sets 2, 3)
-int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_pose7, const MatchCfg &cfg, int *d_work, int buf_base = 0);
+// defer_fit: skip the fit launch and leave the fit to the next linearize_device(lm_mode 1) on this context (Ctx::pending_fit)
+int match_pair_device(Ctx *c, const MatchJob *jobs, int n_jobs, const double *d_pose7, const MatchCfg &cfg, int *d_work, int buf_base = 0,
+                      bool defer_fit = false);
 
 // track_kernels.cu
 int match_from_scan_device(Ctx *c, int slot, int type, const float4 *d_pts, int n, const double *d_pose7, unsigned char *d_valid,

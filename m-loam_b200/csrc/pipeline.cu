@@ -61,7 +61,9 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
                    c->feat_coeff[0].as<float>(), nullptr, seeded},
           MatchJob{MLOAM_MAP_SURF, 's', S.surf, ns_use, S.d_n_surf, c->feat_valid[1].as<unsigned char>(),
                    c->feat_coeff[1].as<float>(), nullptr, seeded}};
-      rc = match_pair_device(c, jobs, 2, d_pose, cfg, &st->work[0]);
+      // without good-feature selection nothing reads the fit before the solve: its launch folds into the first evaluation
+      const bool defer_fit = c->fuse_iter && P.gf_method == 0;
+      rc = match_pair_device(c, jobs, 2, d_pose, cfg, &st->work[0], 0, defer_fit);
       if (rc) return rc;
     }
     // goodFeatureMatching (:503-532 with FLAGS_gf_method != wo_gf): select gf_ratio of the features per set, on the device;
@@ -91,11 +93,14 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
     // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve.  The device
     // only needs the degeneracy decision; scan2map_finish fills in the eigenvalue report of the last iteration.
     c->want_eig = 0;
+    c->lin_two_pass = c->fuse_iter && P.max_inner == 1;  // the one LM iteration's second evaluation rides in the same launch
     rc = linearize_device(c, sets, 2, sinfo, P.huber_a, nullptr, 1, 1, nullptr);
     c->want_eig = 1;
+    const bool second_done = c->lin_two_pass;
+    c->lin_two_pass = false;
     if (rc) return rc;
     // :586-596 ceres::Solve, at most max_inner LM iterations; the device raises `done`
-    for (int it = 0; it < P.max_inner; it++) {
+    for (int it = 0; it < P.max_inner && !second_done; it++) {
       rc = linearize_device(c, sets, 2, sinfo, P.huber_a, nullptr, 2, 2, nullptr);
       if (rc) return rc;
       if (P.max_inner > 1) {
@@ -130,6 +135,12 @@ int scan2map_finish(Ctx *c, const ScanRef &S, const double *pose_init7, double *
     if (stats) stats->ran = 1, stats->termination = 9;
     return fail(c, MLOAM_E_NCCL, "scan2map: peer-memory exchange failed (a rank did not arrive or the ranks lost lock-step); "
                                   "call mloam_comm_p2p_reset on every rank behind a barrier");
+  }
+  if (hs->termination == 8) {  // k_linearize's grid barrier gave up: a block of the grid never became resident within ~2 s
+    for (int k = 0; k < 7; k++) pose_out7[k] = pose_init7[k];
+    if (stats) stats->ran = 1, stats->termination = 8;
+    return fail(c, MLOAM_E_STATE, "scan2map: the two-evaluation launch timed out at its grid barrier (GPU shared with a kernel that never "
+                                   "yields?); set MLOAM_FUSE_ITER=0 to use one launch per evaluation");
   }
   if (c->prof_on) {  // device-side cycle counters of the fused LM tail, reported next to the event-timed stages
     int khz = 0;

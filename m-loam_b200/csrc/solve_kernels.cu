@@ -12,6 +12,7 @@
 //   k_lm        : the same tail as a stand-alone kernel (NCCL path, mloam_normal_equations).
 #include "ctx.h"
 #include "factors.cuh"
+#include "match_fit.cuh"
 
 namespace mloam {
 
@@ -45,20 +46,60 @@ struct LinArgs {
   unsigned *ticket;        // zero between launches
   LMState *state_rw;
   const P2PView *p2p;      // device copy of the peer-memory view, or null: sum the packed normal equations over the ranks
+  // two_pass (needs the fused tail): the evaluation at x, the LM step, and the evaluation at the candidate xc in ONE launch.  The
+  // blocks wait at a grid barrier (generation word next to the ticket) for the block that ran the tail; every block of the grid
+  // is resident (<= 64 blocks of 256 threads, one per SM).
+  int two_pass;
+  // deferred fit (KFIT > 0): the thread that evaluates a feature first fits its line / plane from the matcher's neighbour list
+  FitSet fit[2];
+  float fit_min_plane_dis;
+  int fit_check_fov;
 };
 
 __device__ __noinline__ void lm_tail(const double *partials, int n_blocks, LMState *gst, int mode, double eig_thre, int want_eig, double *out_ne,
                                      const P2PView *p2p);
 
+template <int KFIT>
 __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__restrict__ partials) {
   __shared__ double sm[LIN_THREADS / 32][NE_PACK];
   __shared__ bool is_last;
-  const double *px = a.use_state == 1 ? a.state->x : (a.use_state == 2 ? a.state->xc : a.pose);
+  __shared__ int barrier_failed;
   if (a.respect_done && a.state && a.state->done) {  // Solve already terminated: nothing to evaluate
     if (a.lm_mode != 0 && blockIdx.x == 0 && threadIdx.x == 0) a.state_rw->work[0] = 0, a.state_rw->work[1] = 0;
     return;
   }
-  const PoseR P = make_poser(px);
+  volatile unsigned *const gen = a.ticket + 1;
+  const unsigned gen0 = a.two_pass ? *gen : 0u;  // read before this block's ticket: the release cannot have happened yet
+#pragma unroll 1
+  for (int pass = 0; pass < (a.two_pass ? 2 : 1); pass++) {
+  double xs[7];
+  if (pass == 0) {
+    const double *px = a.use_state == 1 ? a.state->x : (a.use_state == 2 ? a.state->xc : a.pose);
+#pragma unroll
+    for (int k = 0; k < 7; k++) xs[k] = px[k];
+  } else {
+    // grid barrier: the block that ran the tail of pass 0 publishes the state and bumps the generation word
+    if (threadIdx.x == 0) {
+      barrier_failed = 0;
+      const long long w0 = clock64();
+      while (*gen == gen0) {
+        if (clock64() - w0 > 4000000000ll) {  // ~2 s: a block of this grid never became resident
+          barrier_failed = 1;
+          break;
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    if (barrier_failed) {
+      if (threadIdx.x == 0) a.state_rw->termination = 8, a.state_rw->done = 1;
+      return;
+    }
+    if (__ldcg(&a.state_rw->done)) return;  // the step of pass 0 ended the Solve (tolerance, too few rows, invalid steps)
+#pragma unroll
+    for (int k = 0; k < 7; k++) xs[k] = __ldcg(&a.state_rw->xc[k]);  // L2: this SM's L1 may hold the line from pass 0
+  }
+  const PoseR P = make_poser(xs);
   double acc[NE_PACK];
 #pragma unroll
   for (int k = 0; k < NE_PACK; k++) acc[k] = 0.0;
@@ -69,6 +110,10 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
     // the last thread downwards, so that a thread evaluates one feature of either set instead of one of each.
     const int G = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
     for (int i = (s & 1) ? G - 1 - gid : gid; i < fn; i += G) {
+      if (KFIT > 0 && pass == 0 && a.fit[s].pos) {  // deferred fit: this thread is the only one that touches feature i
+        const PoseD T = pose_from_param(xs);
+        fit_one<(KFIT > 0 ? KFIT : 5)>(a.fit[s], i, T, a.fit_min_plane_dis, a.fit_check_fov);
+      }
       if (!fs.valid[i] || (fs.mask && !fs.mask[i])) continue;
       const float4 pf = __ldg(fs.pts + i);
       const D3 p{(double)pf.x, (double)pf.y, (double)pf.z};
@@ -162,10 +207,22 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linearize(LinArgs a, double *__
   __syncthreads();
   if (threadIdx.x == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) {
+    if (a.two_pass && pass == 0) continue;  // on to the barrier of pass 1
+    return;
+  }
   __threadfence();
-  lm_tail(partials, (int)gridDim.x, a.state_rw, a.lm_mode, a.eig_thre, a.want_eig, nullptr, a.p2p);
-  if (threadIdx.x == 0) *a.ticket = 0u;
+  lm_tail(partials, (int)gridDim.x, a.state_rw, pass == 0 ? a.lm_mode : 2, a.eig_thre, pass == 0 ? a.want_eig : 1, nullptr, a.p2p);
+  __threadfence();  // the state (written by all threads of this block) before the ticket reset and the release
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *a.ticket = 0u;
+    if (a.two_pass && pass == 0) {
+      __threadfence();
+      atomicAdd(a.ticket + 1, 1u);  // release the grid into pass 1
+    }
+  }
+  }
 }
 
 // ---------------------------------------------------------------------------------------- small dense (device)
@@ -652,9 +709,29 @@ int linearize_device(Ctx *c, const FeatSet *sets, int n_sets, double sqrt_info, 
   a.p2p = (fused && c->p2p_on && c->p2p_collective) ? static_cast<const P2PView *>(c->p2p_view) : nullptr;
   a.lm_mode = fused ? lm_mode : 0, a.want_eig = want_eig, a.eig_thre = eig_thre, a.ticket = ticket;
   a.state_rw = c->lm_state.as<LMState>();
+  // both evaluations of an LM iteration in one launch: only with the fused tail (the barrier is released by the block that ran it)
+  a.two_pass = (c->lin_two_pass && fused && lm_mode == 1) ? 1 : 0;
+  c->lin_two_pass = a.two_pass != 0;
+  // a fit the matcher deferred to this evaluation
+  int kfit = 0;
+  memset(a.fit, 0, sizeof(a.fit));
+  a.fit_min_plane_dis = 0.f, a.fit_check_fov = 0;
+  if (c->pending_fit.K) {
+    if (lm_mode != 1 || n_sets != 2 || (c->pending_fit.K != 5 && c->pending_fit.K != 10)) {
+      c->err = "linearize: a deferred fit is pending but this is not the first evaluation of a solve";
+      c->pending_fit.K = 0;
+      return MLOAM_E_STATE;
+    }
+    kfit = c->pending_fit.K;
+    a.fit[0] = c->pending_fit.set[0], a.fit[1] = c->pending_fit.set[1];
+    a.fit_min_plane_dis = c->pending_fit.min_plane_dis, a.fit_check_fov = c->pending_fit.check_fov;
+    c->pending_fit.K = 0;
+  }
   {
     ProfScope ps(c, "linearize");
-    k_linearize<<<nb, LIN_THREADS, 0, c->stream>>>(a, c->partials.as<double>());
+    if (kfit == 5) k_linearize<5><<<nb, LIN_THREADS, 0, c->stream>>>(a, c->partials.as<double>());
+    else if (kfit == 10) k_linearize<10><<<nb, LIN_THREADS, 0, c->stream>>>(a, c->partials.as<double>());
+    else k_linearize<0><<<nb, LIN_THREADS, 0, c->stream>>>(a, c->partials.as<double>());
     c->launches++;
   }
   if (fused) {
