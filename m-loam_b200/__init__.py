@@ -259,6 +259,14 @@ class Context:
         self._ck(lib().mloam_voxel_downsample(self._h, _p(pts), pts.shape[0], C.c_float(leaf), int(intensity_last), _p(out), C.byref(n)))
         return out[: n.value].copy()
 
+    def debug_stamps(self):
+        """MLOAM_STAMP=1: [(label, ns since the frame's first stamp)] of the last frame (graph replay included)."""
+        buf = (C.c_ulonglong * 256)()
+        n = C.c_int(0)
+        self._ck(lib().mloam_debug_stamps(self._h, buf, 256, C.byref(n)))
+        lib().mloam_debug_stamp_label.restype = C.c_char_p
+        return [(lib().mloam_debug_stamp_label(self._h, i).decode(), int(buf[i]) - int(buf[0])) for i in range(n.value)]
+
     def project_cloud(self, cloud, vertical_scans: int, horizon_scans: int, roi_range: float = 0.5):
         """ImageSegmenter::segmentCloud with segment_cloud: 0 -> (ring-ordered cloud, scan_start, scan_end)."""
         pts = _cloud(cloud)

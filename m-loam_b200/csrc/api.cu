@@ -118,6 +118,7 @@ int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out
     if (v >= 2 && v <= 4) c->knn_min_blocks = v;
   }
   if (const char *e = getenv("MLOAM_KNN_TMA_MIN")) c->knn_tma_min = (unsigned)strtoul(e, nullptr, 10);
+  if (const char *e = getenv("MLOAM_STAMP")) c->stamp_on = e[0] == '1';
   if (const char *e = getenv("MLOAM_FUSE_ITER")) c->fuse_iter = (e[0] == '0') ? 0 : 1;
   if (const char *e = getenv("MLOAM_DISABLE_SEEDS")) c->use_seeds = (e[0] == '0' || e[0] == '\0') ? 1 : 0;
   *out = h;
@@ -255,6 +256,37 @@ int mloam_map_build(mloam_ctx_t *h, int slot, const mloam_point_t *h_pts, int m,
   MLOAM_CUDA_OK(c, stage.reserve(sizeof(float4) * (size_t)(m + 1)));
   MLOAM_CUDA_OK(c, cudaMemcpyAsync(stage.p, h_pts, sizeof(float4) * (size_t)m, cudaMemcpyHostToDevice, c->stream));
   return map_build_device(c, slot, stage.as<float4>(), m, pick_cell(c, cell));
+}
+
+__global__ void k_stamp(unsigned long long *slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+}  // extern "C" (reopened below)
+namespace mloam {
+void stamp(Ctx *c, const char *label) {
+  if (!c->stamp_on || c->stamp_n >= 256) return;
+  if (c->stamps.reserve(256 * sizeof(unsigned long long)) != cudaSuccess) return;
+  if ((int)c->stamp_labels.size() <= c->stamp_n) c->stamp_labels.resize(c->stamp_n + 1);
+  c->stamp_labels[c->stamp_n] = label;
+  k_stamp<<<1, 1, 0, c->stream>>>(c->stamps.as<unsigned long long>() + c->stamp_n);
+  c->stamp_n++;
+}
+}  // namespace mloam
+extern "C" {
+// Diagnosis only: the globaltimer stamps [ns] of the last frame (MLOAM_STAMP=1) and their labels.
+int mloam_debug_stamps(mloam_ctx_t *h, unsigned long long *out_ns, int cap, int *n) {
+  if (!h || !out_ns || !n) return MLOAM_E_INVALID;
+  cudaSetDevice(h->c.device);
+  *n = h->c.stamp_n < cap ? h->c.stamp_n : cap;
+  if (*n <= 0) return MLOAM_OK;
+  if (cudaStreamSynchronize(h->c.stream) != cudaSuccess) return MLOAM_E_CUDA;
+  return cudaMemcpy(out_ns, h->c.stamps.p, sizeof(unsigned long long) * (size_t)*n, cudaMemcpyDeviceToHost) == cudaSuccess ? MLOAM_OK : MLOAM_E_CUDA;
+}
+const char *mloam_debug_stamp_label(mloam_ctx_t *h, int i) {
+  if (!h || i < 0 || i >= (int)h->c.stamp_labels.size()) return "";
+  return h->c.stamp_labels[i].c_str();
 }
 
 // Diagnosis only (not part of include/mloam_b200.h): per-query words of the last traced k_match_knn launch.

@@ -191,6 +191,12 @@ struct Ctx {
   unsigned knn_tma_min = 8;        // kNN staging: runs of >= this many points use TMA bulk copies, shorter ones 16 B loads (MLOAM_KNN_TMA_MIN)
   DevBuf knn_trace;                // MLOAM_KNN_TRACE=1: 4 words per query of the last k_match_knn launch (diagnosis, tools/knn_micro.py)
   bool knn_trace_on = false;
+  // MLOAM_STAMP=1 (diagnosis, tools/stamp_frame.py): one-thread kernels that write %globaltimer between the stages of a frame, so that
+  // the stage times of a GRAPH REPLAY can be read (the event scopes of mloam_profile_enable force the stream path and add launch gaps)
+  bool stamp_on = false;
+  DevBuf stamps;
+  int stamp_n = 0;
+  std::vector<std::string> stamp_labels;
   int knn_min_blocks = 4;          // k_match_knn variant: resident CTAs per SM it is compiled for (MLOAM_KNN_MB = 2 | 3 | 4)
   int use_seeds = 1;               // seed the kNN of re-association iterations > 0 with the previous neighbour lists
   int s2m_ran = 0;
@@ -315,6 +321,7 @@ struct ExtractOut {
 int extract_device(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
                    ExtractOut out, float *d_curv_or_null, int *d_label_or_null);
 // in place: segment l of d_pts (points [d_off[l], d_off[l + 1])) <- float 3x4 matrix l times the point, intensity kept
+void stamp(Ctx *c, const char *label);  // api.cu
 int project_cloud_device(Ctx *c, const float4 *d_in, int n, int vertical_scans, int horizon_scans, double roi_range, float4 *d_out,
                          int *d_scan_start, int *d_scan_end, int *d_n_out);
 int transform_segments_device(Ctx *c, float4 *d_pts, int n, const int *d_off, int n_seg, const float *d_mat12);

@@ -65,6 +65,7 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
       const bool defer_fit = c->fuse_iter && P.gf_method == 0;
       rc = match_pair_device(c, jobs, 2, d_pose, cfg, &st->work[0], 0, defer_fit);
       if (rc) return rc;
+      stamp(c, "match");
     }
     // goodFeatureMatching (:503-532 with FLAGS_gf_method != wo_gf): select gf_ratio of the features per set, on the device;
     // the solve below only sees the selected ones.  Corner first, then surf, as in the reference.
@@ -92,6 +93,7 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
     }
     // :537-582 residual blocks + Evaluate -> J^T J -> evalDegenracy, and iteration 0 of ceres::Solve.  The device
     // only needs the degeneracy decision; scan2map_finish fills in the eigenvalue report of the last iteration.
+    if (P.gf_method != 0) stamp(c, "gf");
     c->want_eig = 0;
     c->lin_two_pass = c->fuse_iter && P.max_inner == 1;  // the one LM iteration's second evaluation rides in the same launch
     rc = linearize_device(c, sets, 2, sinfo, P.huber_a, nullptr, 1, 1, nullptr);
@@ -99,10 +101,12 @@ int scan2map_enqueue(Ctx *c, const ScanRef &S, const double *pose_init7) {
     const bool second_done = c->lin_two_pass;
     c->lin_two_pass = false;
     if (rc) return rc;
+    stamp(c, second_done ? "linearize x2" : "linearize");
     // :586-596 ceres::Solve, at most max_inner LM iterations; the device raises `done`
     for (int it = 0; it < P.max_inner && !second_done; it++) {
       rc = linearize_device(c, sets, 2, sinfo, P.huber_a, nullptr, 2, 2, nullptr);
       if (rc) return rc;
+      stamp(c, "linearize (candidate)");
       if (P.max_inner > 1) {
         MLOAM_CUDA_OK(c, cudaMemcpyAsync(h_done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         MLOAM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
@@ -242,8 +246,11 @@ int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start,
   FrameBufs F;
   rc = frame_bufs(c, n, &F);
   if (rc) return rc;
+  c->stamp_n = 0;
+  stamp(c, "start");
   rc = extract_device(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, F.ex, nullptr, nullptr);
   if (rc) return rc;
+  stamp(c, "extract");
   const int less_cap = n < 120 * n_scans ? n : 120 * n_scans;  // <= 20 less-sharp picks x 6 sectors per ring
   if (c->n_lidars > 1 || c->lidar_merge) {
     // batched sweeps of several LiDARs: features of LiDAR l go to the base frame with its extrinsic, intensity = l
@@ -293,7 +300,9 @@ int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start,
   rc = voxel_downsample_device(c, F.ex.less_flat, n, F.ex.counts + 3, P.surf_leaf, 1, F.surf_ds, F.n_surf_ds, 5);
   if (rc) return rc;
   if (fork_voxel) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join3, 0));
+  stamp(c, "voxel (surf; corner on the side stream)");
   if (forked) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join the map-build branch
+  if (forked) stamp(c, "map build join");
   ScanRef S{F.surf_ds, n, F.n_surf_ds, F.corner_ds, less_cap, F.n_corner_ds};
   *S_out = S;
   return scan2map_enqueue(c, S, pose_init7);
