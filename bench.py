@@ -316,17 +316,28 @@ def gpu_measure(m, syn, torch, dist, cfg_name, cfg, args, rank, local_rank, worl
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     h_surf = torch.from_numpy(surf_map).pin_memory()
     h_corner = torch.from_numpy(corner_map).pin_memory()
-    h_frames = [dict(cloud=torch.from_numpy(g["cloud"]).pin_memory(), ss=g["ss"], se=g["se"]) for g in my]
+    h_frames = [dict(cloud=torch.from_numpy(g["cloud"]).pin_memory(), ss=np.ascontiguousarray(g["ss"], np.int32), se=np.ascontiguousarray(g["se"], np.int32)) for g in my]
+    for hf in h_frames:
+        hf["cloud_np"] = hf["cloud"].numpy()  # one view per buffer: the look-ahead matches the announced sweep by its pointer
+    h_surf_np, h_corner_np = h_surf.numpy(), h_corner.numpy()
     KF = max(1, args.keyframe_every)
+
+    lookahead = not args.no_lookahead
 
     def step_device(k, rebuild):
         f, g, d = frames[k % n_frames], my[k % n_frames], d_frames[k % n_frames]
+        if lookahead:  # announce sweep k+1: it is extracted on a side stream while frame k is matched and solved
+            gn, dn = my[(k + 1) % n_frames], d_frames[(k + 1) % n_frames]
+            ctx.frame_set_next_device(dn["cloud"].data_ptr(), gn["cloud"].shape[0], dn["ss"].data_ptr(), dn["se"].data_ptr(), n_scans)
         return ctx.frame_device(d["cloud"].data_ptr(), g["cloud"].shape[0], d["ss"].data_ptr(), d["se"].data_ptr(), n_scans,
                                 d_surf.data_ptr(), surf_map.shape[0], d_corner.data_ptr(), corner_map.shape[0], f["init"], rebuild)
 
     def step_host(k, rebuild):
         f, hf = frames[k % n_frames], h_frames[k % n_frames]
-        return ctx.frame(hf["cloud"].numpy(), hf["ss"], hf["se"], h_surf.numpy(), h_corner.numpy(), f["init"], rebuild)
+        if lookahead:
+            hn = h_frames[(k + 1) % n_frames]
+            ctx.frame_set_next(hn["cloud_np"], hn["ss"], hn["se"])
+        return ctx.frame(hf["cloud_np"], hf["ss"], hf["se"], h_surf_np, h_corner_np, f["init"], rebuild)
 
     def barrier():
         if world > 1:
@@ -340,16 +351,18 @@ def gpu_measure(m, syn, torch, dist, cfg_name, cfg, args, rank, local_rank, worl
     sampler.wait_first()
     # warm-up: every (frame buffer, rebuild?) combination at least three times (first sighting allocates, the second captures
     # its CUDA graph, the third replays) so that no capture falls into the timed region; at least W steps in total
-    step_device(0, True)
-    n_warm = 1
+    # (with look-ahead the graph of a frame also depends on which half of the feature double buffer it uses, which alternates along an
+    # unbroken k -> k+1 chain: n_frames is even, so the chain below visits every combination the timed loop will)
+    n_warm = 0
     for rb in (True, False):
-        for _ in range(3):
+        for _ in range(4):
             for k in range(n_frames):
                 step_device(k, rb)
                 n_warm += 1
-    for k in range(max(0, warmup - n_warm)):
+    for k in range(n_frames * ((max(0, warmup - n_warm) + n_frames - 1) // n_frames)):
         step_device(k, False)
-    step_device(0, True)  # leave the resident maps freshly built
+    for k in range(n_frames):
+        step_device(k, k == n_frames - 1)  # leave the resident maps freshly built; the chain continues into the timed loop at k = 0
     barrier()
     sampler.mark()
     launches0 = ctx.launch_count()
@@ -429,10 +442,11 @@ def gpu_measure(m, syn, torch, dist, cfg_name, cfg, args, rank, local_rank, worl
     # ---- e2e: HOST buffers through the C ABI (H2D sweeps every step, both submaps on keyframe steps, D2H pose + state)
     e2e_steps = max(KF, steps) if full else max(KF, min(steps, 20))
     for rb in (True, False):
-        for _ in range(3):
+        for _ in range(4):
             for k in range(n_frames):
                 step_host(k, rb)
-    step_host(0, True)
+    for k in range(n_frames):
+        step_host(k, k == n_frames - 1)
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
@@ -479,6 +493,7 @@ def main():
     ap.add_argument("--keyframe-every", type=int, default=KEYFRAME_EVERY)
     ap.add_argument("--cpu-sample", type=int, default=0, help="rig frames of CPU work for cpu_baseline (0: ~10-30 s worth)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lookahead", action="store_true", help="do not announce sweep k+1 while frame k runs (no overlap of extraction with the solve)")
     ap.add_argument("--no-c4", action="store_true", help="skip the extra C4-on-one-GPU measurement of the default run")
     args = ap.parse_args()
 
@@ -591,6 +606,11 @@ def main():
     config = config_blurb(cfg_name, cfg, n_gpus, args, wl)
     if R.get("exchange"):
         config["exchange"] = R["exchange"]
+    if not cfg["calib"]:
+        config["lookahead"] = ("off" if args.no_lookahead else
+                           "sweep k+1 is announced with frame k (mloam_frame_set_next*): its extractCloud + scan down-sampling run on a side stream while frame k "
+                           "is matched and solved, and are joined before frame k returns — every timed step contains one extraction and one solve "
+                           "(the reference overlaps the same stages across its estimator and lidar_mapper nodes)")
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"

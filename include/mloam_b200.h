@@ -227,6 +227,16 @@ int mloam_frame(mloam_ctx_t *ctx, const mloam_point_t *h_cloud, int n, const int
                 int n_scans, const mloam_point_t *h_surf_map, int n_surf_map, const mloam_point_t *h_corner_map,
                 int n_corner_map, int rebuild_maps, const double *pose_init7, double *pose_out7,
                 mloam_solve_stats_t *stats);
+
+/* ---- sweep look-ahead.  Announce the sweep of the NEXT mloam_frame / mloam_frame_device call: while the coming frame is matched and
+ *      solved, the announced sweep is extracted and down-sampled on a side stream, so that the next call starts at the matching.  The
+ *      reference overlaps the same two stages by running them in different nodes (estimator: estimator.cpp:249-263 -> lidar_mapper:
+ *      lidar_mapper_keyframe.cpp:356-596).  The next call must pass the SAME pointer and sizes to pick the features up; any other call
+ *      extracts as usual.  Poses and statistics are identical with and without announcements.  n <= 0 withdraws.  Host variant: the
+ *      buffers must stay valid until the coming frame call returns. */
+int mloam_frame_set_next(mloam_ctx_t *ctx, const mloam_point_t *h_cloud, int n, const int *h_scan_start, const int *h_scan_end, int n_scans);
+int mloam_frame_set_next_device(mloam_ctx_t *ctx, const mloam_point_t *d_cloud, int n, const int *d_scan_start, const int *d_scan_end,
+                                int n_scans);
 int mloam_frame_device(mloam_ctx_t *ctx, const mloam_point_t *d_cloud, int n, const int *d_scan_start,
                        const int *d_scan_end, int n_scans, const mloam_point_t *d_surf_map, int n_surf_map,
                        const mloam_point_t *d_corner_map, int n_corner_map, int rebuild_maps,

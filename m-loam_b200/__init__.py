@@ -26,7 +26,7 @@ E_NO_DEVICE = -2
 ABI_SYMBOLS = [
     "mloam_default_params", "mloam_ctx_create", "mloam_ctx_destroy", "mloam_set_params", "mloam_set_stream", "mloam_sync",
     "mloam_last_error", "mloam_version", "mloam_launch_count", "mloam_profile_enable", "mloam_profile_get",
-    "mloam_profile_reset", "mloam_project_cloud", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
+    "mloam_profile_reset", "mloam_project_cloud", "mloam_frame_set_next", "mloam_frame_set_next_device", "mloam_extract_features", "mloam_extract_debug", "mloam_voxel_downsample", "mloam_map_build",
     "mloam_map_build_device", "mloam_map_size", "mloam_knn", "mloam_match_from_map", "mloam_factor_evaluate",
     "mloam_normal_equations", "mloam_pose_plus", "mloam_scan2map", "mloam_scan2map_device", "mloam_frame",
     "mloam_frame_device", "mloam_set_extrinsic", "mloam_set_lidars", "mloam_calib_frame", "mloam_compound_pose_cov", "mloam_cloud_uct_associate", "mloam_voxel_downsample_cov", "mloam_submap_assemble", "mloam_good_features_odom", "mloam_local_map_build", "mloam_match_from_scan", "mloam_track_cloud", "mloam_odom_solve", "mloam_point_uncertainty", "mloam_scan2map_ua", "mloam_good_features", "mloam_comm_unique_id", "mloam_comm_init", "mloam_comm_destroy", "mloam_comm_p2p_export", "mloam_comm_p2p_init", "mloam_comm_p2p_reset",
@@ -307,6 +307,22 @@ class Context:
                                    0 if sm is None else sm.shape[0], _p(cm), 0 if cm is None else cm.shape[0], int(rebuild_maps),
                                    _p(pi), _p(out), C.byref(st)))
         return out, st.as_dict()
+
+    def frame_set_next(self, cloud, scan_start, scan_end):
+        """Announce the sweep of the next frame() call (host arrays; pass the SAME arrays to that call): it is extracted on a side
+        stream while the coming frame is solved.  None withdraws."""
+        if cloud is None:
+            self._next_keep = None
+            self._ck(lib().mloam_frame_set_next(self._h, None, 0, None, None, 0))
+            return
+        cloud = _cloud(cloud)
+        ss = np.ascontiguousarray(scan_start, np.int32)
+        se = np.ascontiguousarray(scan_end, np.int32)
+        self._next_keep = (cloud, ss, se)  # must outlive the coming frame call
+        self._ck(lib().mloam_frame_set_next(self._h, _p(cloud), cloud.shape[0], _p(ss), _p(se), ss.shape[0]))
+
+    def frame_set_next_device(self, d_cloud: int, n: int, d_scan_start: int, d_scan_end: int, n_scans: int):
+        self._ck(lib().mloam_frame_set_next_device(self._h, C.c_void_p(d_cloud), n, C.c_void_p(d_scan_start), C.c_void_p(d_scan_end), n_scans))
 
     def frame_device(self, d_cloud: int, n: int, d_scan_start: int, d_scan_end: int, n_scans: int, d_surf_map: int, n_surf_map: int,
                      d_corner_map: int, n_corner_map: int, pose_init7, rebuild_maps: bool = True):

@@ -103,6 +103,13 @@ int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out
       cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream5, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork4, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join4, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_fork5, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_join5, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_next, cudaEventDisableTiming) != cudaSuccess ||
       cudaMallocHost(&c->pinned, kPinnedBytes) != cudaSuccess || c->lm_state.reserve(sizeof(LMState) + 64) != cudaSuccess ||
       c->scratch[7].reserve(4096) != cudaSuccess) {
     delete h;
@@ -118,6 +125,7 @@ int mloam_ctx_create(int device, const mloam_params_t *params, mloam_ctx_t **out
     if (v >= 2 && v <= 4) c->knn_min_blocks = v;
   }
   if (const char *e = getenv("MLOAM_KNN_TMA_MIN")) c->knn_tma_min = (unsigned)strtoul(e, nullptr, 10);
+  if (const char *e = getenv("MLOAM_LOOKAHEAD")) c->use_lookahead = (e[0] == '0') ? 0 : 1;
   if (const char *e = getenv("MLOAM_STAMP")) c->stamp_on = e[0] == '1';
   if (const char *e = getenv("MLOAM_FUSE_ITER")) c->fuse_iter = (e[0] == '0') ? 0 : 1;
   if (const char *e = getenv("MLOAM_DISABLE_SEEDS")) c->use_seeds = (e[0] == '0' || e[0] == '\0') ? 1 : 0;
@@ -144,6 +152,7 @@ void mloam_ctx_destroy(mloam_ctx_t *h) {
   c->knn_heavy_list.release(), c->knn_trace.release();
   c->partials.release(), c->lm_state.release();
   for (auto &s : c->scratch) s.release();
+  c->frame_main.release(), c->frame_alt.release(), c->next_in.release(), c->stamps.release();
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamSynchronize(c->stream2), cudaStreamDestroy(c->stream2);
@@ -153,6 +162,10 @@ void mloam_ctx_destroy(mloam_ctx_t *h) {
   if (c->stream3) cudaStreamSynchronize(c->stream3), cudaStreamDestroy(c->stream3);
   if (c->ev_fork3) cudaEventDestroy(c->ev_fork3);
   if (c->ev_join3) cudaEventDestroy(c->ev_join3);
+  if (c->stream4) cudaStreamSynchronize(c->stream4), cudaStreamDestroy(c->stream4);
+  if (c->stream5) cudaStreamSynchronize(c->stream5), cudaStreamDestroy(c->stream5);
+  for (cudaEvent_t ev : {c->ev_fork4, c->ev_join4, c->ev_fork5, c->ev_join5, c->ev_next})
+    if (ev) cudaEventDestroy(ev);
   delete h;
 }
 
@@ -160,6 +173,7 @@ int mloam_set_params(mloam_ctx_t *h, const mloam_params_t *p) {
   if (!h || !p) return MLOAM_E_INVALID;
   if (p->n_neigh != 5 && p->n_neigh != 10) return fail(&h->c, MLOAM_E_INVALID, "n_neigh must be 5 or 10");
   h->c.params = *p;
+  h->c.prefetched.valid = false;  // look-ahead features were extracted under the previous parameters
   return MLOAM_OK;
 }
 
@@ -266,7 +280,7 @@ __global__ void k_stamp(unsigned long long *slot) {
 }  // extern "C" (reopened below)
 namespace mloam {
 void stamp(Ctx *c, const char *label) {
-  if (!c->stamp_on || c->stamp_n >= 256) return;
+  if (!c->stamp_on || c->stamp_mute || c->stamp_n >= 256) return;
   if (c->stamps.reserve(256 * sizeof(unsigned long long)) != cudaSuccess) return;
   if ((int)c->stamp_labels.size() <= c->stamp_n) c->stamp_labels.resize(c->stamp_n + 1);
   c->stamp_labels[c->stamp_n] = label;

@@ -149,7 +149,7 @@ struct Ctx {
   DevBuf partials;                // per-block packed normal equations
   DevBuf lm_state;                // LMState
   void *ticket_zeroed_for = nullptr;  // partials allocation whose last-block ticket has been zeroed
-  DevBuf scratch[8];              // general scratch (knn outputs, factor batches, extraction, voxel)
+  DevBuf scratch[10];             // general scratch (knn outputs, factor batches, extraction, voxel)
   void *pinned = nullptr;         // pinned host staging (LMState mirror + small results)
   size_t pinned_cap = 0;
 
@@ -177,11 +177,40 @@ struct Ctx {
     const int *d_n_corner;
     const double *sinfo_surf, *sinfo_corner;  // nullable per-feature sqrt_info (uncertainty-aware mapping)
   };
+  // Sweep look-ahead (mloam_frame_set_next*): while frame k is matched and solved, the features of sweep k+1 are extracted and
+  // down-sampled on a side stream into the other half of a double buffer — the reference runs the two stages in different nodes
+  // (estimator -> lidar_mapper), so they overlap there too.  `Features` describes one half.
+  struct Features {
+    bool valid = false;
+    bool host = false;          // key_ptr is a host pointer (mloam_frame) / a device pointer (mloam_frame_device)
+    const void *key_ptr = nullptr;
+    int n = 0, n_scans = 0, parity = 0;
+    ScanRef S{};
+  };
+  struct NextSweep {
+    bool set = false, host = false;
+    const void *key_ptr = nullptr;      // what the caller will pass as the cloud of the next frame
+    const float4 *d_cloud = nullptr;    // where the sweep is (or will be, after the pending H2D) on the device
+    const int *d_scan_start = nullptr, *d_scan_end = nullptr;
+    int n = 0, n_scans = 0;
+  };
+  Features prefetched;             // features of the sweep announced with the previous frame, ready when that frame returned
+  NextSweep next;                  // announced for the frame being enqueued (consumed by it)
+  const void *cloud_key = nullptr; // mloam_frame: the HOST pointer of the sweep being processed (look-ahead matches on it)
+  const int *next_host_ss = nullptr, *next_host_se = nullptr;  // ScanInfo of a sweep announced from host memory
+  bool next_pending = false;       // its H2D copy was enqueued on stream4 outside of any capture (ev_next)
+  int frame_parity = 0;
+  int use_lookahead = 1;           // MLOAM_LOOKAHEAD=0: announcements are ignored
+  bool stamp_mute = false;
+  DevBuf frame_main, frame_alt, next_in;  // the two halves of the frame feature double buffer; the announced sweep's staging
+  cudaStream_t stream4 = nullptr, stream5 = nullptr;  // look-ahead extraction and its corner-voxel fork
+  cudaEvent_t ev_fork4 = nullptr, ev_join4 = nullptr, ev_fork5 = nullptr, ev_join5 = nullptr, ev_next = nullptr;
   struct GraphEntry {
     unsigned long long key = 0, epoch = 0;
     cudaGraphExec_t exec = nullptr;
     int launches = 0, seen = 0, s2m_ran = 0;
     ScanRef S{};
+    Features prefetched_out{};     // what the frame leaves in Ctx::prefetched
   };
   std::vector<GraphEntry> graphs;
   bool smem_opt_in_gf = false;     // k_gf_select's 200 KB pool

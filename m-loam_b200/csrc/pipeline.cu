@@ -185,8 +185,8 @@ struct FrameBufs {
   float4 *corner_ds, *surf_ds;
   int *n_corner_ds, *n_surf_ds;  // device counts
 };
-int frame_bufs(Ctx *c, int n, FrameBufs *F) {
-  DevBuf &B = c->scratch[6];
+int frame_bufs(Ctx *c, int n, FrameBufs *F, int parity = 0) {
+  DevBuf &B = parity ? c->frame_alt : c->frame_main;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -207,47 +207,19 @@ int frame_bufs(Ctx *c, int n, FrameBufs *F) {
   return MLOAM_OK;
 }
 
-int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
-                  const float4 *d_surf_map, int n_surf_map, const float4 *d_corner_map, int n_corner_map, int rebuild_maps,
-                  const double *pose_init7, ScanRef *S_out) {
+bool frame_has_prefetched(const Ctx *c, const void *key_ptr, int n, int n_scans) {
+  const Ctx::Features &f = c->prefetched;
+  return f.valid && c->use_lookahead && !c->prof_on && f.key_ptr == key_ptr && f.n == n && f.n_scans == n_scans;
+}
+
+// extractCloud + (multi-LiDAR merge | base-frame transform) + downsampleCurrentScan of one sweep on c->stream, into half `parity` of the
+// feature double buffer.  `side` / ev_fork_v / ev_join_v: the stream and events of the corner-filter fork.
+int features_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans, int parity,
+                     cudaStream_t side, cudaEvent_t ev_fork_v, cudaEvent_t ev_join_v, ScanRef *S_out) {
   const mloam_params_t &P = c->params;
-  int rc;
-  bool forked = false;
-  if (rebuild_maps) {  // lidar_mapper_keyframe.cpp:433-434 (every frame in the reference)
-    // The two submap builds do not depend on the sweep: they run on a forked side stream, concurrently with
-    // extraction + scan down-sampling, and join right before matching (also inside a captured graph).
-    // With stage profiling on the branch stays on the main stream so that per-stage event times do not overlap.
-    forked = !c->prof_on;
-    if (!forked) {
-      if (c->maps_pending) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_maps, 0));
-      rc = map_build_device(c, MLOAM_MAP_SURF, d_surf_map, n_surf_map, pick_cell(c, 0.f));
-      if (rc == MLOAM_OK) rc = map_build_device(c, MLOAM_MAP_CORNER, d_corner_map, n_corner_map, pick_cell(c, 0.f));
-      if (rc) return rc;
-    }
-  }
-  if (forked) {
-    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_fork, c->stream));
-    MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-    if (c->maps_pending) {
-      // mloam_frame copied the submaps on stream2 outside of any capture: inside a captured graph the branch waits
-      // on that record as an external event node; on the plain stream path stream2 is already ordered after it.
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      MLOAM_CUDA_OK(c, cudaStreamIsCapturing(c->stream2, &cs));
-      if (cs == cudaStreamCaptureStatusActive) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream2, c->ev_maps, cudaEventWaitExternal));
-    }
-    cudaStream_t main_stream = c->stream;
-    c->stream = c->stream2;
-    rc = map_build_device(c, MLOAM_MAP_SURF, d_surf_map, n_surf_map, pick_cell(c, 0.f));
-    if (rc == MLOAM_OK) rc = map_build_device(c, MLOAM_MAP_CORNER, d_corner_map, n_corner_map, pick_cell(c, 0.f));
-    c->stream = main_stream;
-    if (rc) return rc;
-    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_join, c->stream2));
-  }
   FrameBufs F;
-  rc = frame_bufs(c, n, &F);
+  int rc = frame_bufs(c, n, &F, parity);
   if (rc) return rc;
-  c->stamp_n = 0;
-  stamp(c, "start");
   rc = extract_device(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, F.ex, nullptr, nullptr);
   if (rc) return rc;
   stamp(c, "extract");
@@ -285,27 +257,134 @@ int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start,
   // surf one (own scratch slot), also inside a captured graph; with stage profiling on they stay serial.
   const bool fork_voxel = !c->prof_on;
   if (fork_voxel) {
-    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_fork3, c->stream));
-    MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream3, c->ev_fork3, 0));
+    MLOAM_CUDA_OK(c, cudaEventRecord(ev_fork_v, c->stream));
+    MLOAM_CUDA_OK(c, cudaStreamWaitEvent(side, ev_fork_v, 0));
     cudaStream_t main_stream = c->stream;
-    c->stream = c->stream3;
-    rc = voxel_downsample_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, P.corner_leaf, 1, F.corner_ds, F.n_corner_ds, 3);
+    c->stream = side;
+    rc = voxel_downsample_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, P.corner_leaf, 1, F.corner_ds, F.n_corner_ds, 8);
     c->stream = main_stream;
     if (rc) return rc;
-    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_join3, c->stream3));
+    MLOAM_CUDA_OK(c, cudaEventRecord(ev_join_v, side));
   } else {
-    rc = voxel_downsample_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, P.corner_leaf, 1, F.corner_ds, F.n_corner_ds, 3);
+    rc = voxel_downsample_device(c, F.ex.less_sharp, less_cap, F.ex.counts + 1, P.corner_leaf, 1, F.corner_ds, F.n_corner_ds, 8);
     if (rc) return rc;
   }
-  rc = voxel_downsample_device(c, F.ex.less_flat, n, F.ex.counts + 3, P.surf_leaf, 1, F.surf_ds, F.n_surf_ds, 5);
+  rc = voxel_downsample_device(c, F.ex.less_flat, n, F.ex.counts + 3, P.surf_leaf, 1, F.surf_ds, F.n_surf_ds, 9);
   if (rc) return rc;
-  if (fork_voxel) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join3, 0));
+  if (fork_voxel) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, ev_join_v, 0));
   stamp(c, "voxel (surf; corner on the side stream)");
-  if (forked) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join the map-build branch
-  if (forked) stamp(c, "map build join");
   ScanRef S{F.surf_ds, n, F.n_surf_ds, F.corner_ds, less_cap, F.n_corner_ds};
   *S_out = S;
-  return scan2map_enqueue(c, S, pose_init7);
+  return MLOAM_OK;
+}
+
+int frame_enqueue(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans,
+                  const float4 *d_surf_map, int n_surf_map, const float4 *d_corner_map, int n_corner_map, int rebuild_maps,
+                  const double *pose_init7, ScanRef *S_out) {
+  int rc;
+  bool forked = false;
+  if (rebuild_maps) {  // lidar_mapper_keyframe.cpp:433-434 (every frame in the reference)
+    // The two submap builds do not depend on the sweep: they run on a forked side stream, concurrently with
+    // extraction + scan down-sampling, and join right before matching (also inside a captured graph).
+    // With stage profiling on the branch stays on the main stream so that per-stage event times do not overlap.
+    forked = !c->prof_on;
+    if (!forked) {
+      if (c->maps_pending) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_maps, 0));
+      rc = map_build_device(c, MLOAM_MAP_SURF, d_surf_map, n_surf_map, pick_cell(c, 0.f));
+      if (rc == MLOAM_OK) rc = map_build_device(c, MLOAM_MAP_CORNER, d_corner_map, n_corner_map, pick_cell(c, 0.f));
+      if (rc) return rc;
+    }
+  }
+  if (forked) {
+    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_fork, c->stream));
+    MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    if (c->maps_pending) {
+      // mloam_frame copied the submaps on stream2 outside of any capture: inside a captured graph the branch waits
+      // on that record as an external event node; on the plain stream path stream2 is already ordered after it.
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      MLOAM_CUDA_OK(c, cudaStreamIsCapturing(c->stream2, &cs));
+      if (cs == cudaStreamCaptureStatusActive) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream2, c->ev_maps, cudaEventWaitExternal));
+    }
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->stream2;
+    rc = map_build_device(c, MLOAM_MAP_SURF, d_surf_map, n_surf_map, pick_cell(c, 0.f));
+    if (rc == MLOAM_OK) rc = map_build_device(c, MLOAM_MAP_CORNER, d_corner_map, n_corner_map, pick_cell(c, 0.f));
+    c->stream = main_stream;
+    if (rc) return rc;
+    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_join, c->stream2));
+  }
+  c->stamp_n = 0;
+  stamp(c, "start");
+  // features of this sweep: extracted while the previous frame was solved (look-ahead), or now
+  ScanRef S{};
+  int parity = c->frame_parity;
+  const void *key_now = c->cloud_key ? c->cloud_key : static_cast<const void *>(d_cloud);
+  const bool have = frame_has_prefetched(c, key_now, n, n_scans);
+  if (have) {
+    S = c->prefetched.S, parity = c->prefetched.parity;
+  } else {
+    rc = features_enqueue(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, parity, c->stream3, c->ev_fork3, c->ev_join3, &S);
+    if (rc) return rc;
+  }
+  c->prefetched.valid = false;
+  c->frame_parity = parity ^ 1;
+  // look-ahead: the announced next sweep goes through the same steps on stream4 into the other half while this frame is matched
+  // and solved (the extraction scratch is shared with the block above, hence the fork AFTER it)
+  bool ahead = false;
+  Ctx::Features nf{};
+  if (c->next.set && c->use_lookahead && !c->prof_on) {
+    const Ctx::NextSweep nx = c->next;
+    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_fork4, c->stream));
+    MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream4, c->ev_fork4, 0));
+    if (c->next_pending) {  // mloam_frame copied the next sweep on stream4 outside of any capture (as ev_maps above)
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      MLOAM_CUDA_OK(c, cudaStreamIsCapturing(c->stream4, &cs));
+      if (cs == cudaStreamCaptureStatusActive) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream4, c->ev_next, cudaEventWaitExternal));
+    }
+    cudaStream_t main_stream = c->stream;
+    c->stream = c->stream4;
+    c->stamp_mute = true;
+    ScanRef Sn{};
+    rc = features_enqueue(c, nx.d_cloud, nx.n, nx.d_scan_start, nx.d_scan_end, nx.n_scans, parity ^ 1, c->stream5, c->ev_fork5, c->ev_join5, &Sn);
+    c->stamp_mute = false;
+    c->stream = main_stream;
+    if (rc) return rc;
+    MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_join4, c->stream4));
+    ahead = true;
+    nf.valid = true, nf.host = nx.host, nf.key_ptr = nx.key_ptr, nf.n = nx.n, nf.n_scans = nx.n_scans, nf.parity = parity ^ 1, nf.S = Sn;
+  }
+  c->next.set = false;
+  stamp(c, have ? "features (prefetched)" : "extract + voxel");
+  if (forked) MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));  // join the map-build branch
+  if (forked) stamp(c, "map build join");
+  *S_out = S;
+  rc = scan2map_enqueue(c, S, pose_init7);
+  if (rc) return rc;
+  if (ahead) {  // the frame ends when both branches have: the features of the next sweep are complete when this call returns
+    MLOAM_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_join4, 0));
+    stamp(c, "look-ahead join");
+    c->prefetched = nf;
+  }
+  return MLOAM_OK;
+}
+
+// A sweep announced from HOST memory goes up on stream4 right away (outside of any capture); the look-ahead branch of the frame
+// waits on ev_next.  stream4's previous work — the look-ahead of the previous frame, which read next_in — was joined by that frame.
+int stage_next_sweep(Ctx *c) {
+  if (!c->next.set || !c->next.host || !c->use_lookahead || c->prof_on) return MLOAM_OK;
+  const int n = c->next.n, ns = c->next.n_scans;
+  DevBuf &in = c->next_in;
+  MLOAM_CUDA_OK(c, in.reserve(sizeof(float4) * (size_t)n + 1024 + 8 * (size_t)ns));
+  float4 *d_cloud = in.as<float4>();
+  int *d_ss = reinterpret_cast<int *>(in.as<char>() + sizeof(float4) * (size_t)n + 256);
+  int *d_se = d_ss + ns;
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_cloud, c->next.key_ptr, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream4));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ss, c->next_host_ss, sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream4));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_se, c->next_host_se, sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream4));
+  MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_next, c->stream4));
+  c->next.d_cloud = d_cloud, c->next.d_scan_start = d_ss, c->next.d_scan_end = d_se;
+  c->next_pending = true;
+  return MLOAM_OK;
 }
 
 unsigned long long fnv1a(unsigned long long h, const void *p, size_t n) {
@@ -341,6 +420,17 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
     key = fnv1a(key, &c->lidar_merge, sizeof(c->lidar_merge));
     key = fnv1a(key, c->lidar_ext, sizeof(double) * 7 * (size_t)c->n_lidars);
     key = fnv1a(key, &c->stream, sizeof(c->stream));
+    {  // look-ahead: which half holds this sweep's features (or that they are extracted now), and the announced next sweep
+      const void *key_now = c->cloud_key ? c->cloud_key : static_cast<const void *>(d_cloud);
+      const bool have = frame_has_prefetched(c, key_now, n, n_scans);
+      const bool ahead = c->next.set && c->use_lookahead;
+      const int la[8] = {have ? 1 : 0, have ? c->prefetched.parity : c->frame_parity, ahead ? 1 : 0, ahead ? c->next.n : 0, ahead ? c->next.n_scans : 0,
+                         (ahead && c->next.host) ? 1 : 0, (ahead && c->next_pending) ? 1 : 0, c->stamp_on ? 1 : 0};
+      const void *lp[5] = {key_now, ahead ? c->next.key_ptr : nullptr, ahead ? static_cast<const void *>(c->next.d_cloud) : nullptr,
+                           ahead ? static_cast<const void *>(c->next.d_scan_start) : nullptr, ahead ? static_cast<const void *>(c->next.d_scan_end) : nullptr};
+      key = fnv1a(key, la, sizeof(la));
+      key = fnv1a(key, lp, sizeof(lp));
+    }
     Ctx::GraphEntry *e = nullptr;
     for (auto &g : c->graphs)
       if (g.key == key) e = &g;
@@ -352,6 +442,10 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
       MLOAM_CUDA_OK(c, cudaGraphLaunch(e->exec, c->stream));
       c->launches += e->launches;
       c->s2m_ran = e->s2m_ran;
+      // the state transitions frame_enqueue makes at capture time
+      c->frame_parity = (frame_has_prefetched(c, c->cloud_key ? c->cloud_key : static_cast<const void *>(d_cloud), n, n_scans) ? c->prefetched.parity : c->frame_parity) ^ 1;
+      c->prefetched = e->prefetched_out;
+      c->next.set = false;
       return scan2map_finish(c, e->S, pose_init7, pose_out7, stats);
     }
     if (e && e->seen >= 1) {  // second sighting: capture
@@ -359,6 +453,9 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
       const long long l0 = c->launches;
       const unsigned long long ep0 = alloc_epoch();
       cudaGraph_t graph = nullptr;
+      const Ctx::Features pf0 = c->prefetched;  // frame_enqueue consumes these: put them back when the capture fails
+      const Ctx::NextSweep nx0 = c->next;
+      const int par0 = c->frame_parity;
       MLOAM_CUDA_OK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
       int rc = frame_enqueue(c, d_cloud, n, d_scan_start, d_scan_end, n_scans, d_surf_map, n_surf_map, d_corner_map, n_corner_map,
                              rebuild_maps, pose_init7, &S);
@@ -366,6 +463,7 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
       if (rc == MLOAM_OK && ce == cudaSuccess && graph && ep0 == alloc_epoch() &&
           cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess) {
         e->launches = (int)(c->launches - l0), e->epoch = ep0, e->S = S, e->s2m_ran = c->s2m_ran;
+        e->prefetched_out = c->prefetched;
         c->launches = l0;
         cudaGraphDestroy(graph);
         MLOAM_CUDA_OK(c, cudaGraphLaunch(e->exec, c->stream));
@@ -377,8 +475,9 @@ int frame_run(Ctx *c, const float4 *d_cloud, int n, const int *d_scan_start, con
       e->exec = nullptr, e->seen = 0;  // capture failed (e.g. a buffer had to grow, which is illegal while capturing): run this frame on
       c->launches = l0;                // the plain stream path below — it performs the allocation — and capture at a later sighting
       c->graph_capture_failures++;
+      c->prefetched = pf0, c->next = nx0, c->frame_parity = par0;
     } else if (!e) {
-      if (c->graphs.size() >= 32) {
+      if (c->graphs.size() >= 96) {
         if (c->graphs.front().exec) cudaGraphExecDestroy(c->graphs.front().exec);
         c->graphs.erase(c->graphs.begin());
       }
@@ -462,6 +561,7 @@ int mloam_extract_features(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, 
   cudaSetDevice(c->device);
   out->n_sharp = out->n_less_sharp = out->n_flat = out->n_less_flat = 0;
   if (n == 0) return MLOAM_OK;
+  c->prefetched.valid = false;  // this call reuses half 0 of the frame feature buffers
   FrameBufs F;
   int rc = frame_bufs(c, n, &F);
   if (rc) return rc;
@@ -575,9 +675,39 @@ int mloam_frame_device(mloam_ctx_t *h, const mloam_point_t *d_cloud, int n, cons
                        int rebuild_maps, const double *pose_init7, double *pose_out7, mloam_solve_stats_t *stats) {
   if (!h || !pose_init7 || !pose_out7 || n <= 0 || !d_cloud || !d_scan_start || !d_scan_end) return MLOAM_E_INVALID;
   cudaSetDevice(h->c.device);
-  return frame_run(&h->c, reinterpret_cast<const float4 *>(d_cloud), n, d_scan_start, d_scan_end, n_scans,
-                   reinterpret_cast<const float4 *>(d_surf_map), n_surf_map, reinterpret_cast<const float4 *>(d_corner_map),
-                   n_corner_map, rebuild_maps, pose_init7, pose_out7, stats);
+  Ctx *c = &h->c;
+  int rc = stage_next_sweep(c);
+  if (rc) return rc;
+  rc = frame_run(c, reinterpret_cast<const float4 *>(d_cloud), n, d_scan_start, d_scan_end, n_scans,
+                 reinterpret_cast<const float4 *>(d_surf_map), n_surf_map, reinterpret_cast<const float4 *>(d_corner_map),
+                 n_corner_map, rebuild_maps, pose_init7, pose_out7, stats);
+  c->next_pending = false, c->next.set = false;
+  return rc;
+}
+
+// Look-ahead: announce the sweep of the NEXT mloam_frame* call.  While the coming frame is matched and solved, that sweep is extracted
+// and down-sampled on a side stream (in the reference the two stages run in different nodes, estimator -> lidar_mapper); the next
+// call finds its features ready when it passes the same pointer (and sizes) — otherwise it extracts as usual.  One announcement is
+// consumed by one frame; results are identical with or without it.
+int mloam_frame_set_next_device(mloam_ctx_t *h, const mloam_point_t *d_cloud, int n, const int *d_scan_start, const int *d_scan_end, int n_scans) {
+  if (!h) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  c->next = Ctx::NextSweep{};
+  if (!d_cloud || n <= 0) return MLOAM_OK;  // withdraw
+  if (!d_scan_start || !d_scan_end || n_scans <= 0 || n_scans > MLOAM_MAX_RINGS) return MLOAM_E_INVALID;
+  c->next.set = true, c->next.host = false, c->next.key_ptr = d_cloud, c->next.d_cloud = reinterpret_cast<const float4 *>(d_cloud);
+  c->next.d_scan_start = d_scan_start, c->next.d_scan_end = d_scan_end, c->next.n = n, c->next.n_scans = n_scans;
+  return MLOAM_OK;
+}
+int mloam_frame_set_next(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *h_scan_start, const int *h_scan_end, int n_scans) {
+  if (!h) return MLOAM_E_INVALID;
+  Ctx *c = &h->c;
+  c->next = Ctx::NextSweep{};
+  if (!h_cloud || n <= 0) return MLOAM_OK;  // withdraw
+  if (!h_scan_start || !h_scan_end || n_scans <= 0 || n_scans > MLOAM_MAX_RINGS) return MLOAM_E_INVALID;
+  c->next.set = true, c->next.host = true, c->next.key_ptr = h_cloud, c->next.n = n, c->next.n_scans = n_scans;
+  c->next_host_ss = h_scan_start, c->next_host_se = h_scan_end;
+  return MLOAM_OK;
 }
 
 int mloam_frame(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *h_scan_start, const int *h_scan_end, int n_scans,
@@ -593,9 +723,17 @@ int mloam_frame(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *
   float4 *d_cloud = in.as<float4>();
   int *d_ss = reinterpret_cast<int *>(in.as<char>() + sizeof(float4) * (size_t)n + 256);
   int *d_se = d_ss + n_scans;
-  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_cloud, h_cloud, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
-  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ss, h_scan_start, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
-  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_se, h_scan_end, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
+  // the sweep was announced with the previous frame and its features are ready (look-ahead): nothing to copy
+  const bool have = c->prefetched.host && frame_has_prefetched(c, h_cloud, n, n_scans);
+  if (!have) {
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_cloud, h_cloud, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ss, h_scan_start, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_se, h_scan_end, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
+  }
+  {
+    const int rc_next = stage_next_sweep(c);
+    if (rc_next) return rc_next;
+  }
   const float4 *d_sm = nullptr, *d_cm = nullptr;
   if (rebuild_maps) {
     if (!h_surf_map || !h_corner_map || n_surf_map < 0 || n_corner_map < 0) return MLOAM_E_INVALID;
@@ -610,8 +748,10 @@ int mloam_frame(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *
     c->maps_pending = true;
     d_sm = ms.as<float4>(), d_cm = mc.as<float4>();
   }
+  c->cloud_key = h_cloud;
   const int rc = frame_run(c, d_cloud, n, d_ss, d_se, n_scans, d_sm, n_surf_map, d_cm, n_corner_map, rebuild_maps, pose_init7, pose_out7, stats);
-  c->maps_pending = false;
+  c->cloud_key = nullptr;
+  c->maps_pending = false, c->next_pending = false, c->next.set = false;
   return rc;
 }
 
@@ -619,6 +759,7 @@ int mloam_set_lidars(mloam_ctx_t *h, int n_lidars, const double *ext7) {
   if (!h || n_lidars < 1 || n_lidars > MLOAM_MAX_LIDARS || (n_lidars > 1 && !ext7)) return MLOAM_E_INVALID;
   Ctx *c = &h->c;
   c->n_lidars = n_lidars;
+  c->prefetched.valid = false;  // look-ahead features were merged with the previous extrinsics
   c->lidar_merge = ext7 != nullptr;  // also for ONE LiDAR with an extrinsic: same float transform + laser id as in a rig
   for (int l = 0; l < n_lidars; l++)
     for (int k = 0; k < 7; k++) c->lidar_ext[l][k] = ext7 ? ext7[7 * l + k] : (k == 6 ? 1.0 : 0.0);
@@ -629,6 +770,7 @@ int mloam_set_extrinsic(mloam_ctx_t *h, const double *ext7) {
   if (!h) return MLOAM_E_INVALID;
   Ctx *c = &h->c;
   c->has_ext = ext7 != nullptr;
+  c->prefetched.valid = false;
   for (int k = 0; k < 7; k++) c->ext[k] = ext7 ? ext7[k] : (k == 6 ? 1.0 : 0.0);
   return MLOAM_OK;
 }

@@ -738,6 +738,78 @@ def test_frame_graph_replay_equals_stream_path(mloam, c1):
     g.close()
 
 
+@pytest.mark.parametrize("n_lidars", [1, 2])
+@pytest.mark.parametrize("gf", [0, orc.GF_GD])
+def test_frame_lookahead_is_exact(mloam, n_lidars, gf):
+    """Sweep look-ahead (mloam_frame_set_next / _device): the next sweep is extracted on a side stream while the current frame is
+    solved.  A sequence of frames must give bit-identical poses and statistics with and without announcements — through the host
+    API and the device API, on the stream path and from replayed graphs, when an announcement is NOT followed by that sweep, and
+    with the map rebuilt on some frames only (the keyframe cadence)."""
+    import torch
+
+    scene = syn.make_scene()
+    traj = syn.trajectory(8)
+    surf_map, corner_map = syn.make_submap(scene, 200_000)
+    p = mloam.default_params()
+    p.n_scans, p.max_outer, p.max_inner, p.map_cell, p.max_ring_points = 16, 4, 1, 0.0, 1024
+    p.gf_method, p.gf_ratio = gf, 0.5
+    rng = np.random.Generator(np.random.PCG64(5))
+    sweeps = []
+    for k in range(4):
+        if n_lidars == 1:
+            cloud, ss, se = syn.make_sweep(scene, traj[2 + k], 16, 1024, seed=30 + k)
+            ext = None
+        else:
+            cloud, ss, se, ext = syn.make_multi_sweep(scene, traj[2 + k], n_lidars, 16, 1024, seed=30 + k)
+        sweeps.append(dict(cloud=np.ascontiguousarray(cloud, np.float32), ss=np.ascontiguousarray(ss, np.int32), se=np.ascontiguousarray(se, np.int32),
+                           init=syn.perturb_pose(traj[2 + k], rng)))
+    order = [0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 1, 3]  # the last two break the announced order
+    rebuild = [k % 3 == 0 for k in range(len(order))]
+
+    def new_ctx():
+        c = mloam.Context(0, p)
+        if n_lidars > 1:
+            c.set_lidars(n_lidars, ext)
+        return c
+
+    def run_host(c, announce):
+        out = []
+        for i, k in enumerate(order):
+            s = sweeps[k]
+            if announce:
+                nk = (k + 1) % 4  # what a sequential reader would announce; wrong for the last two frames of `order`
+                c.frame_set_next(sweeps[nk]["cloud"], sweeps[nk]["ss"], sweeps[nk]["se"])
+            pose, st = c.frame(s["cloud"], s["ss"], s["se"], surf_map, corner_map, s["init"], rebuild[i])
+            out.append((pose, st["n_surf"], st["n_corner"], st["n_surf_in"], st["n_corner_in"], st["final_cost"]))
+        return out
+
+    plain = new_ctx()
+    ref = run_host(plain, False)
+    l_plain = plain.launch_count()
+    plain.close()
+    ahead = new_ctx()
+    got = run_host(ahead, True)
+    ahead.close()
+    for a, b in zip(got, ref):
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+    assert ref[0][1] > 500 and l_plain > 0
+    # device API: sweeps and maps resident, announcements by device pointer
+    dev = torch.device("cuda", 0)
+    d_s = [dict(cloud=torch.from_numpy(s["cloud"]).to(dev), ss=torch.from_numpy(s["ss"]).to(dev), se=torch.from_numpy(s["se"]).to(dev)) for s in sweeps]
+    d_sm, d_cm = torch.from_numpy(surf_map).to(dev), torch.from_numpy(corner_map).to(dev)
+    c = new_ctx()
+    got_d = []
+    for i, k in enumerate(order):
+        nk = (k + 1) % 4
+        c.frame_set_next_device(d_s[nk]["cloud"].data_ptr(), sweeps[nk]["cloud"].shape[0], d_s[nk]["ss"].data_ptr(), d_s[nk]["se"].data_ptr(), sweeps[nk]["ss"].shape[0])
+        pose, st = c.frame_device(d_s[k]["cloud"].data_ptr(), sweeps[k]["cloud"].shape[0], d_s[k]["ss"].data_ptr(), d_s[k]["se"].data_ptr(), sweeps[k]["ss"].shape[0],
+                                  d_sm.data_ptr(), surf_map.shape[0], d_cm.data_ptr(), corner_map.shape[0], sweeps[k]["init"], rebuild[i])
+        got_d.append((pose, st["n_surf"], st["n_corner"], st["n_surf_in"], st["n_corner_in"], st["final_cost"]))
+    c.close()
+    for a, b in zip(got_d, ref):
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
+
+
 @pytest.mark.parametrize("outer,inner,guess", [(6, 1, 0.0), (3, 4, 0.0), (4, 1, 0.6)])
 def test_seeded_reassociation_is_exact(mloam, c1, outer, inner, guess):
     """From the second re-association on, the kNN is seeded with the previous neighbour lists and unchanged lists keep

@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="C2")
     ap.add_argument("--frames", type=int, default=40)
+    ap.add_argument("--lookahead", action="store_true", help="announce sweep k+1 with frame k (extraction on the side stream)")
     a = ap.parse_args()
     cfg = dict(bench.CONFIGS[a.config])
     m = bench.load_mloam()
@@ -40,11 +41,14 @@ def main():
 
     def step(k, rebuild):
         f, g, dd = wl["frames"][k % 4], my[k % 4], d[k % 4]
+        if a.lookahead:
+            gn, dn = my[(k + 1) % 4], d[(k + 1) % 4]
+            ctx.frame_set_next_device(dn["cloud"].data_ptr(), gn["cloud"].shape[0], dn["ss"].data_ptr(), dn["se"].data_ptr(), cfg["rings"] * L)
         return ctx.frame_device(dd["cloud"].data_ptr(), g["cloud"].shape[0], dd["ss"].data_ptr(), dd["se"].data_ptr(), cfg["rings"] * L,
                                 d_surf.data_ptr(), wl["surf_map"].shape[0], d_corner.data_ptr(), wl["corner_map"].shape[0], f["init"], rebuild)
 
     for rb in (True, False):
-        for _ in range(3):
+        for _ in range(4):
             for k in range(4):
                 step(k, rb)
     rows = {}
