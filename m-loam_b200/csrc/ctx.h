@@ -103,6 +103,7 @@ struct MapStorage {
   }
 };
 
+constexpr size_t kPinnedScanInfo = 32768, kPinnedScanInfoNext = 40960;  // 2 x MLOAM_MAX_RINGS ints each inside Ctx::pinned (ScanInfo staging of mloam_frame / of the announced sweep)
 constexpr size_t kKnnPathStatsOffset = 3072;  // 64 B of matcher counters inside Ctx::scratch[7] (zeroed at creation / profile reset)
 
 struct ProfSlot {

@@ -378,9 +378,12 @@ int stage_next_sweep(Ctx *c) {
   float4 *d_cloud = in.as<float4>();
   int *d_ss = reinterpret_cast<int *>(in.as<char>() + sizeof(float4) * (size_t)n + 256);
   int *d_se = d_ss + ns;
+  // ScanInfo goes through the context's pinned block: an async copy from pageable memory would block the host behind the sweep's copy
+  int *pin = reinterpret_cast<int *>(reinterpret_cast<char *>(c->pinned) + kPinnedScanInfoNext);
+  std::memcpy(pin, c->next_host_ss, sizeof(int) * ns), std::memcpy(pin + MLOAM_MAX_RINGS, c->next_host_se, sizeof(int) * ns);
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ss, pin, sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream4));
+  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_se, pin + MLOAM_MAX_RINGS, sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream4));
   MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_cloud, c->next.key_ptr, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream4));
-  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ss, c->next_host_ss, sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream4));
-  MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_se, c->next_host_se, sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream4));
   MLOAM_CUDA_OK(c, cudaEventRecord(c->ev_next, c->stream4));
   c->next.d_cloud = d_cloud, c->next.d_scan_start = d_ss, c->next.d_scan_end = d_se;
   c->next_pending = true;
@@ -726,9 +729,11 @@ int mloam_frame(mloam_ctx_t *h, const mloam_point_t *h_cloud, int n, const int *
   // the sweep was announced with the previous frame and its features are ready (look-ahead): nothing to copy
   const bool have = c->prefetched.host && frame_has_prefetched(c, h_cloud, n, n_scans);
   if (!have) {
+    int *pin = reinterpret_cast<int *>(reinterpret_cast<char *>(c->pinned) + kPinnedScanInfo);
+    std::memcpy(pin, h_scan_start, sizeof(int) * n_scans), std::memcpy(pin + MLOAM_MAX_RINGS, h_scan_end, sizeof(int) * n_scans);
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ss, pin, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
+    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_se, pin + MLOAM_MAX_RINGS, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
     MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_cloud, h_cloud, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
-    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_ss, h_scan_start, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
-    MLOAM_CUDA_OK(c, cudaMemcpyAsync(d_se, h_scan_end, sizeof(int) * n_scans, cudaMemcpyHostToDevice, st));
   }
   {
     const int rc_next = stage_next_sweep(c);
