@@ -1,7 +1,7 @@
 // match_kernels.cu — FeatureExtract::matchCornerFromMap / matchSurfFromMap (feature_extract.hpp:378-643;
 // per-point forms :645-883) as two kernels:
 //
-//   k_match_knn  one WARP per feature: pointAssociateToMap + exact K-nearest search in the voxel-hash map
+//   k_match_knn  one WARP per feature: pointAssociateToMap + exact K-nearest search in the dense voxel grid
 //                (knn.cuh) + the distance gate sqdist[K-1] < MIN_MATCH_SQ_DIS.  Corner and surf features share one
 //                launch; the features that needed a real search in the previous iteration are scheduled first (HeavyQ),
 //                so long queries — features in sparse regions — do not form the tail of the launch.  Output: K neighbour positions per feature (20 B).
@@ -9,7 +9,9 @@
 //                3x3 eigen) or the plane (5x3 column-pivoted QR), applies the lambda / plane-distance / FOV gates
 //                and writes valid + coefficients.  Running the fit one-thread-per-feature instead of redundantly
 //                in all 32 lanes of the search warp removes ~1/3 of the matcher's warp instructions and halves its
-//                register footprint.
+//                register footprint.  The per-feature routine lives in match_fit.cuh; scan2map without good-feature
+//                selection defers it into the first evaluation of the solve (k_linearize), so that a GN iteration is
+//                two launches.
 #include <cstdlib>
 
 #include "ctx.h"

@@ -396,7 +396,7 @@ unsigned long long fnv1a(unsigned long long h, const void *p, size_t n) {
   return h;
 }
 
-// One frame.  With max_inner == 1 the ~170 launches of a frame form a fixed sequence that depends on the host only
+// One frame.  With max_inner == 1 the ~60 launches of a frame form a fixed sequence that depends on the host only
 // through the pose guess (staged in pinned memory) — it is captured once per (buffers, sizes, parameters) into a CUDA
 // graph and replayed: the first call with a new key runs on the stream (and performs every allocation), the second
 // captures + instantiates, later ones replay.  Profiling, multi-GPU (NCCL on the stream) and max_inner > 1 (the host
