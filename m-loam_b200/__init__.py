@@ -52,10 +52,30 @@ class SolveStats(C.Structure):
     ]
 
     def as_dict(self):
-        return {"ran": self.ran, "n_surf": self.n_surf, "n_corner": self.n_corner, "lm_iterations": self.lm_iterations,
-                "degenerate": self.degenerate, "termination": self.termination, "final_cost": self.final_cost,
-                "eig": np.array(self.eig[:]), "H": np.array(self.H[:]).reshape(6, 6), "n_surf_in": self.n_surf_in,
-                "n_corner_in": self.n_corner_in}
+        return _Stats(self)
+
+
+class _Stats(dict):
+    """Solve statistics as a dict; the two array entries ("eig", "H") are materialised on first access (a frame call every
+    0.7 ms should not pay for arrays nobody reads)."""
+
+    def __init__(self, st: "SolveStats"):
+        super().__init__(ran=st.ran, n_surf=st.n_surf, n_corner=st.n_corner, lm_iterations=st.lm_iterations, degenerate=st.degenerate,
+                         termination=st.termination, final_cost=st.final_cost, n_surf_in=st.n_surf_in, n_corner_in=st.n_corner_in)
+        self._st = st
+
+    def __missing__(self, key):
+        if key == "eig":
+            v = np.array(self._st.eig[:])
+        elif key == "H":
+            v = np.array(self._st.H[:]).reshape(6, 6)
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def __contains__(self, key):
+        return key in ("eig", "H") or dict.__contains__(self, key)
 
 
 class Features(C.Structure):
@@ -108,7 +128,8 @@ def _cloud(a) -> np.ndarray:
 
 
 def _p(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    # c_void_p built from the buffer address: several times cheaper than ndarray.ctypes.data_as on a per-frame call path
+    return None if a is None else C.c_void_p(a.__array_interface__["data"][0])
 
 
 class MloamError(RuntimeError):
