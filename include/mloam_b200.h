@@ -79,7 +79,8 @@ typedef struct {
   int n_corner;       /* matched corner features, last outer iteration */
   int lm_iterations;  /* LM iterations over all outer iterations */
   int degenerate;     /* PoseLocalParameterization::is_degenerate_ of the last outer iteration */
-  int termination;    /* last Solve: 0 max-iter, 1 function tol, 2 parameter tol, 3 gradient tol, 4 failure */
+  int termination;    /* last Solve: 0 max-iter, 1 function tol, 2 parameter tol, 3 gradient tol, 4 failure, 5 too few correspondences (iteration skipped),
+                       * 8 the two-evaluation launch timed out at its grid barrier (MLOAM_E_STATE), 9 peer-memory exchange failed (MLOAM_E_NCCL) */
   double final_cost;
   double eig[6];      /* eigenvalues of J^T J (evalDegenracy) of the last outer iteration */
   double H[36];       /* loss-corrected J^T J evaluated before the last Solve (:575-581) */
