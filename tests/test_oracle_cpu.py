@@ -420,3 +420,213 @@ def test_solver_restatement_converges_to_independent_optimum():
     r = residuals(sol.x)
     rho = np.where(np.abs(r) <= 0.1, r * r, 2 * 0.1 * np.abs(r) - 0.01)
     assert abs(0.5 * rho.sum() - st["final_cost"]) < 1e-6 * max(1.0, st["final_cost"])
+
+
+# ------------------------------------------------------------------------------------------------ round-2 restatements: known answers
+def _skew(v):
+    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]], float)
+
+
+def _se3_exp(xi):
+    """exp of [rho | phi] (translation first, as associate_uct.hpp's pose covariances) -> (R, t)."""
+    rho, phi = xi[:3], xi[3:]
+    th = np.linalg.norm(phi)
+    K = _skew(phi)
+    if th < 1e-12:
+        return np.eye(3) + K, rho + 0.5 * K @ rho
+    R = np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
+    J = np.eye(3) + (1 - np.cos(th)) / th ** 2 * K + (th - np.sin(th)) / th ** 3 * K @ K
+    return R, J @ rho
+
+
+def _rand_spd(rng, scale):
+    A = rng.normal(size=(6, 6))
+    return scale * (A @ A.T + 0.5 * np.eye(6))
+
+
+def test_compound_pose_with_cov_first_order_and_identities():
+    """compoundPoseWithCov (associate_uct.hpp:9-88): the pose is the product; for small covariances the result tends to the first-order
+    propagation cov1 + Ad(T1) cov2 Ad(T1)^T (written here independently, [translation | rotation] ordering); the 4th-order terms are
+    O(cov^2); compounding with an exactly known identity is the identity."""
+    rng = np.random.default_rng(3)
+    p1 = syn.pose7([1.0, -2.0, 0.5], syn.quat_from_rpy(0.1, -0.2, 0.7))
+    p2 = syn.pose7([0.3, 0.2, -0.1], syn.quat_from_rpy(-0.05, 0.15, -0.4))
+    R1, t1 = syn.quat_to_mat(p1[3:]), p1[:3]
+    Ad = np.zeros((6, 6))
+    Ad[:3, :3], Ad[:3, 3:], Ad[3:, 3:] = R1, _skew(t1) @ R1, R1
+    for scale, tol in ((1e-9, 1e-6), (1e-4, 2e-3)):
+        c1, c2 = _rand_spd(rng, scale), _rand_spd(rng, scale)
+        pc, cc = orc.compound_pose_cov(p1, c1, p2, c2)
+        assert max(syn.pose_err(pc, syn.pose_mul(p1, p2))) < 1e-12
+        first = c1 + Ad @ c2 @ Ad.T
+        assert np.allclose(cc, cc.T, atol=1e-18) and np.all(np.linalg.eigvalsh(cc) > 0)
+        assert np.linalg.norm(cc - first) / np.linalg.norm(first) < tol
+    ident = syn.pose7([0, 0, 0], [0, 0, 0, 1])
+    c1 = _rand_spd(rng, 1e-3)
+    pc, cc = orc.compound_pose_cov(p1, c1, ident, np.zeros((6, 6)))
+    assert np.allclose(pc, p1) and np.allclose(cc, c1, rtol=0, atol=1e-15)
+    # Monte-Carlo: T = exp(xi1^) T1 exp(xi2^) T2 with xi ~ N(0, cov); the compounded covariance is that of log(T * inv(T1 T2))
+    c1, c2 = _rand_spd(rng, 2e-4), _rand_spd(rng, 2e-4)
+    _, cc = orc.compound_pose_cov(p1, c1, p2, c2)
+    L1, L2 = np.linalg.cholesky(c1), np.linalg.cholesky(c2)
+    R2, t2 = syn.quat_to_mat(p2[3:]), p2[:3]
+    Rm, tm = R1 @ R2, R1 @ t2 + t1
+    n = 20000
+    xs = np.zeros((n, 6))
+    for i in range(n):
+        Ra, ta = _se3_exp(L1 @ rng.normal(size=6))
+        Rb, tb = _se3_exp(L2 @ rng.normal(size=6))
+        Rl, tl = Ra @ R1, Ra @ t1 + ta          # exp(xi1) T1
+        Rr, tr = Rb @ R2, Rb @ t2 + tb          # exp(xi2) T2
+        R, t = Rl @ Rr, Rl @ tr + tl
+        dR, dt = R @ Rm.T, t - R @ Rm.T @ tm    # T * inv(mean)
+        phi = 0.5 * np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])  # small angles: log ~ vee of the skew part
+        xs[i] = np.concatenate([dt - 0.5 * np.cross(phi, dt), phi])
+    mc = xs.T @ xs / n
+    assert np.linalg.norm(mc - cc) / np.linalg.norm(cc) < 0.06
+
+
+def test_point_uncertainty_is_the_propagated_jacobian():
+    """evalPointUncertainty (associate_uct.hpp:164-215): cov = G blockdiag(cov_pose, cov_meas) G^T with G = [I | -(Rp+t)^ | R]; G is
+    checked here against numerical derivatives of y = exp(xi^) T (p + d)."""
+    rng = np.random.default_rng(4)
+    pose = syn.pose7([2.0, -1.0, 0.3], syn.quat_from_rpy(0.2, 0.1, -0.9))
+    R, t = syn.quat_to_mat(pose[3:]), pose[:3]
+    pts = np.concatenate([rng.uniform(-20, 20, (50, 3)), np.zeros((50, 1))], 1).astype(np.float32)
+    cov_pose, cm = _rand_spd(rng, 1e-3), np.diag([0.0025, 0.0025, 0.0025])
+    got = orc.point_uncertainty(pts, pose, cov_pose, cm)
+    for i in (0, 7, 49):
+        p = pts[i, :3].astype(float)
+
+        def f(xi, d):
+            Re, te = _se3_exp(xi)
+            return Re @ (R @ (p + d) + t) + te
+
+        G = np.zeros((3, 9))
+        h = 1e-6
+        for k in range(6):
+            e = np.zeros(6)
+            e[k] = h
+            G[:, k] = (f(e, np.zeros(3)) - f(-e, np.zeros(3))) / (2 * h)
+        for k in range(3):
+            e = np.zeros(3)
+            e[k] = h
+            G[:, 6 + k] = (f(np.zeros(6), e) - f(np.zeros(6), -e)) / (2 * h)
+        S = np.zeros((9, 9))
+        S[:6, :6], S[6:, 6:] = cov_pose, cm
+        Cn = G @ S @ G.T
+        want = np.array([Cn[0, 0], Cn[0, 1], Cn[0, 2], Cn[1, 1], Cn[1, 2], Cn[2, 2]])
+        assert np.allclose(got[i], want, rtol=2e-4, atol=1e-7), (got[i], want)
+
+
+def test_voxel_grid_cov_hand_computed_merge():
+    """VoxelGridCovarianceMLOAM<PointIWithCov> merge (voxel_grid_covariance_mloam_impl.hpp:293-333): weight w = threshold - trace,
+    centroid = sum(w x) / sum(w), covariance = sum(w^2 C) / sum(w)^2, intensity of the heaviest point, points with |trace| >= threshold
+    skipped; voxels come out in index order (x fastest)."""
+    thr = 1.0
+    pts = np.array([[0.10, 0.10, 0.10, 5.0], [0.30, 0.20, 0.10, 7.0], [0.20, 0.30, 0.30, 9.0],   # voxel (0,0,0) at leaf 0.5
+                    [0.70, 0.10, 0.10, 1.0],                                                   # voxel (1,0,0)
+                    [0.10, 0.10, 0.60, 2.0], [0.20, 0.20, 0.70, 3.0]], np.float32)             # voxel (0,0,1); the second one is over the threshold
+    tr = np.array([0.2, 0.5, 0.8, 0.1, 0.4, 1.5], np.float32)
+    c6 = np.zeros((6, 6), np.float32)
+    c6[:, 0], c6[:, 3], c6[:, 5] = tr / 2, tr / 4, tr / 4   # xx, yy, zz; trace = tr
+    c6[:, 1] = 0.01
+    op, oc, ot, ok = orc.voxel_grid_cov(pts, c6, tr, 0.5, thr)
+    assert ok and op.shape[0] == 3
+    w = thr - tr[:3]
+    mu = (w[:, None] * pts[:3, :3]).sum(0) / w.sum()
+    assert np.allclose(op[0, :3], mu, atol=1e-6) and op[0, 3] == 5.0          # heaviest point: the first (w = 0.8)
+    assert np.allclose(oc[0], (w[:, None] ** 2 * c6[:3]).sum(0) / w.sum() ** 2, atol=1e-7)
+    assert np.isclose(ot[0], oc[0, 0] + oc[0, 3] + oc[0, 5])
+    assert np.allclose(op[1], pts[3]) and np.allclose(oc[1], c6[3], atol=1e-7)  # single point: w cancels
+    assert np.allclose(op[2], pts[4]) and np.allclose(oc[2], c6[4], atol=1e-7)  # the over-threshold point is ignored
+    # a voxel whose points are ALL over the threshold still emits a point: weight_total falls back to 1 -> zero centroid (reference :326)
+    op2, oc2, ot2, _ = orc.voxel_grid_cov(pts[5:6], c6[5:6], tr[5:6], 0.5, thr)
+    assert op2.shape[0] == 1 and np.all(op2[0, :3] == 0) and ot2[0] == 0
+
+
+def test_project_cloud_known_pixels():
+    """ImageSegmenter::projectCloud (image_segmenter.hpp:88-136) + ring order + ScanInfo (:381-389) on points with known pixels."""
+    H = 1800
+    res = 360.0 / H
+
+    def pt(elev_deg, az_deg, r=10.0, w=0.25):
+        e, a = np.deg2rad(elev_deg), np.deg2rad(az_deg)  # azimuth measured as atan2(x, y)
+        return [r * np.cos(e) * np.sin(a), r * np.cos(e) * np.cos(a), r * np.sin(e), w]
+
+    # VLP-16: row = int((elev + 15.1) / 2): ring elevations -15, -13, ... ; column = -round((az - 90) / res) + H/2 (wrapped)
+    cloud = np.array([pt(-15, 90), pt(-13, 90), pt(15, 90),            # rows 0, 1, 15 at column H/2
+                      pt(-15, 90 - 10 * res), pt(-15, 90 + 10 * res),    # columns H/2 + 10, H/2 - 10
+                      pt(-15, 90.02),                                    # same pixel as the first point: dropped (first wins)
+                      pt(-15, 90, r=0.3),                                # inside ROI_RANGE 0.5: dropped
+                      pt(-17.5, 90), pt(17.5, 90),                       # below row 0 / above row 15: dropped
+                      pt(-13, -100)], np.float32)                        # az -100 deg: column H/2 + 950 -> wraps to 50
+    pix = orc.project_pixels(cloud, 16, H, 0.5)
+    assert list(pix[:5]) == [0 * H + H // 2, 1 * H + H // 2, 15 * H + H // 2, H // 2 + 10, H // 2 - 10]
+    assert pix[5] == pix[0] and list(pix[6:9]) == [-1, -1, -1] and pix[9] == 1 * H + 50
+    out, ss, se = orc.project_cloud(cloud, 16, H, 0.5)
+    # ring order: row 0 (points 0, 3, 4 in input order), row 1 (points 1, 9), row 15 (point 2); intensity += row
+    assert out.shape[0] == 6
+    assert np.array_equal(out[:, :3], cloud[[0, 3, 4, 1, 9, 2], :3])
+    assert np.allclose(out[:, 3], [0.25, 0.25, 0.25, 1.25, 1.25, 15.25])
+    assert list(ss[:3]) == [5, 8, 10] and list(se[:3]) == [-3, -1, -1] and ss[15] == 10 and se[15] == 0
+    # HDL-64E: row = int((2 - elev) * 3 + 0.5) down to -8.83 deg, then 32 + int((-8.83 - elev) * 2 + 0.5); rows above 50 are dropped
+    c64 = np.array([pt(2, 90), pt(0, 90), pt(-8.5, 90), pt(-9.0, 90), pt(-17.83, 90), pt(-18.5, 90), pt(2.2, 90), pt(-24.5, 90)], np.float32)
+    rows = orc.project_pixels(c64, 64, 2048, 0.5)
+    assert list(rows // 2048 * (rows >= 0) + (rows < 0) * -1) == [0, 6, 32, 32, 50, -1, -1, -1]
+    # 32 rings: ang_res_y = 41.33 / 31, bottom 30.67
+    r32 = orc.project_pixels(np.array([pt(-30.67 + 41.33 / 31 * (k + 0.5), 45) for k in range(32)], np.float32), 32, 2169, 0.5)
+    assert list(r32 // 2169) == list(range(32))
+
+
+def test_frame_multi_reduces_to_frame_and_local_map_build_to_its_parts():
+    """One LiDAR with an identity extrinsic through the rig path gives the single-LiDAR frame; buildLocalMap's map half equals
+    transform (PCL float matrix) + concatenation + VoxelGrid done by hand."""
+    scene = syn.make_scene()
+    traj = syn.trajectory(6)
+    surf_map, corner_map = syn.make_submap(scene, 50000)
+    cloud, ss, se = syn.make_sweep(scene, traj[3], 16, 1024, seed=8)
+    init = syn.perturb_pose(traj[3], np.random.Generator(np.random.PCG64(2)))
+    o = orc.default_opts()
+    o[orc.O_MAX_OUTER], o[orc.O_MAX_INNER] = 3, 1
+    a, sa = orc.frame(cloud, ss, se, surf_map, corner_map, init, o)
+    ident = np.array([[0, 0, 0, 0, 0, 0, 1.0]])
+    b, sb = orc.frame_multi(cloud, ss, se, 1, ident, surf_map, corner_map, init, o)
+    assert max(syn.pose_err(a, b)) < 1e-12 and int(sa["n_surf"]) == int(sb["n_surf"]) and int(sa["n_corner"]) == int(sb["n_corner"])
+    # two LiDARs: the second one's features enter through its extrinsic — the frame still lands on the truth
+    cl2, ss2, se2, ext = syn.make_multi_sweep(scene, traj[3], 2, 16, 1024, seed=8)
+    c, sc = orc.frame_multi(cl2, ss2, se2, 2, ext, surf_map, corner_map, init, o)
+    et, er = syn.pose_err(c, traj[3])
+    assert et < 0.05 and er < 3e-3 and int(sc["n_surf"]) > int(sb["n_surf"])
+    # local map: three window clouds brought to the pivot frame and filtered
+    f = orc.extract_cloud(cloud, ss, se)["surf_points_less_flat"]
+    poses = np.stack([syn.pose7([0.1 * k, 0.05 * k, 0.0], syn.quat_from_rpy(0, 0, 0.02 * k)) for k in range(3)])
+    got = orc.local_map_build([f, f[::2], f[::3]], poses, 0.4)
+    parts = []
+    for cl, p in zip([f, f[::2], f[::3]], poses):
+        M = np.eye(4, dtype=np.float32)
+        M[:3, :3], M[:3, 3] = syn.quat_to_mat(p[3:]).astype(np.float32), p[:3].astype(np.float32)
+        q = cl.copy()
+        x, y, z = cl[:, 0], cl[:, 1], cl[:, 2]
+        for r in range(3):  # pcl::transformPointCloud: float, m(r,0) x + m(r,1) y + m(r,2) z + m(r,3)
+            q[:, r] = M[r, 0] * x + M[r, 1] * y + M[r, 2] * z + M[r, 3]
+        parts.append(q)
+    want, _ = orc.voxel_grid(np.concatenate(parts), 0.4, False)
+    assert got.shape == want.shape and np.allclose(got, want, atol=2e-5)
+
+
+def test_calib_frame_oracle_reduces_the_extrinsic_error():
+    """The 12-DoF step [pose_i | ext_cal] (buildCalibMap association + LidarPureOdom rows of the reference LiDAR + LidarOnlineCalib rows of
+    the second one, estimator.cpp:687-848,1067-1156): from a 2 deg / 5 cm wrong extrinsic the step moves towards the true one; with the
+    second LiDAR's rows absent the extrinsic block does not move; the row count is the number of gated matches of both groups."""
+    scene = syn.make_scene()
+    cs = syn.make_calib_case(scene, orc.extract_cloud, orc.voxel_grid, 16, 1024, 100_000)
+    e0 = syn.pose_err(cs["ext_cal_init"], cs["ext_cal"])
+    pi, ec, st = orc.calib_frame(cs["surf_map"], cs["corner_map"], cs["surf_ref"], cs["corner_ref"], cs["surf_cal"], cs["corner_cal"], cs["pivot"],
+                                 cs["pose_i_init"], cs["ext_ref"], cs["ext_cal_init"], 10, 1)
+    e1 = syn.pose_err(ec, cs["ext_cal"])
+    assert e0[1] > 0.03 and e1[1] < 0.5 * e0[1] and e1[0] < e0[0]
+    assert st["rows"] > 1000 and st["lm_iterations"] >= 5
+    pi_only, ec_same, st_only = orc.calib_frame(cs["surf_map"], cs["corner_map"], cs["surf_ref"], cs["corner_ref"], None, None, cs["pivot"],
+                                                cs["pose_i_init"], cs["ext_ref"], cs["ext_cal_init"], 10, 1)
+    assert np.allclose(ec_same, cs["ext_cal_init"], atol=1e-12) and 0 < st_only["rows"] < st["rows"]
