@@ -155,3 +155,28 @@ def test_projection_arithmetic_matches_oracle_on_the_host():
                 h.host_project_pixels(pts.ctypes.data_as(C.c_void_p), n, rings, hs, C.c_double(roi), got.ctypes.data_as(C.c_void_p))
                 assert np.array_equal(got, want), (rings, roi, int((got != want).sum()))
                 assert (want >= 0).sum() > n // 4
+
+
+def test_bench_contract_on_a_cpu_box():
+    """bench.py without a GPU: the reference arm (CPU restatement, the one leg that may execute oracle/) prints ONE JSON line with the
+    contract's keys; our arm refuses to run (no CPU fallback) with a JSON error and a non-zero exit code."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "scan_to_map_lidar_frames_per_sec" and d["unit"] == "frames/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    assert d["config"]["workload"].startswith("C2") and d["data"] == "synthetic"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "rig frame" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if not torch.cuda.is_available():
+        ours = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+        assert ours.returncode != 0 and "no CUDA device" in ours.stdout
